@@ -1,0 +1,84 @@
+/*
+ * Batched shell-tuple entry points of the B200 ERI engine (new in this repository; the reference
+ * has no batched call -- its callers loop over shell quartets from OpenMP threads,
+ * examples/time_c60.c:196-219).  Plain C ABI: pointers, ints and size_t only.
+ *
+ * A context owns everything that depends on one (atm, bas, env): the device copy of the basis,
+ * the screened primitive-pair tables (the device counterpart of CINTOpt's PairData,
+ * src/optimizer.c:288-342) and class-sorted shell-pair lists.  It is the same object an
+ * `*_optimizer` call of include/cint.h returns as CINTOpt.
+ *
+ * Every function returns a negative CINTB200_E* code on failure and prints the reason to stderr.
+ * There is no CPU fallback.
+ */
+#ifndef CINT_B200_H
+#define CINT_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CINTOpt cintb200_ctx;   /* same object as the CINTOpt of include/cint.h */
+
+#define CINTB200_SPH   0
+#define CINTB200_CART  1
+
+#define CINTB200_ENODEV   (-1)   /* no usable CUDA device / CUDA runtime error */
+#define CINTB200_EINVAL   (-2)   /* bad argument (shell id, angular momentum beyond CINTB200_LMAX, ...) */
+#define CINTB200_ENOMEM   (-3)
+#define CINTB200_ENOSUP   (-4)   /* valid libcint input this build does not implement yet */
+#define CINTB200_LMAX     6      /* highest angular momentum accepted per shell */
+
+/* Build / destroy a context on CUDA device `device` (-1: current device).  Replaces the work of
+ * CINTall_2e_optimizer (src/optimizer.c:183) + the per-call CINTinit_int2e_EnvVars (src/g2e.c:21). */
+int  cintb200_create(cintb200_ctx **ctx, const int *atm, int natm, const int *bas, int nbas,
+                     const double *env, int device);
+void cintb200_destroy(cintb200_ctx *ctx);
+int  cintb200_device(const cintb200_ctx *ctx);
+
+/*
+ * Evaluate n shell quartets (ij|kl), shls[4*t .. 4*t+3] = i,j,k,l (0-based shell ids).
+ *   kind      CINTB200_SPH  -> values of int2e_sph  (src/cint2e.c:1186)
+ *             CINTB200_CART -> values of int2e_cart (src/cint2e.c:1202)
+ *   out_off   element offset of each quartet's block inside `out`; NULL -> blocks packed back to back
+ *             in input order.  Each block is column-major (di,dj,dk,dl), i fastest, exactly the
+ *             `out` of the reference call with dims == NULL.
+ *   out       host pointer (on_device = 0; staged through pinned memory) or device pointer
+ *             (on_device = 1) with room for every block.
+ *   nonzero   optional host array[n]: the reference's return value per quartet (1 if any primitive
+ *             survived exponent screening, else 0 and the block is zero-filled).
+ * Returns the number of quartets evaluated (n) or a negative error code.
+ */
+long cintb200_int2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                          const size_t *out_off, double *out, int on_device, int *nonzero);
+
+/* Same for shell triples (ij|k), shls[3*t .. 3*t+2]; block (di,dj,dk).  int3c2e_sph/_cart,
+ * src/cint3c2e.c:693,710. */
+long cintb200_int3c2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                            const size_t *out_off, double *out, int on_device, int *nonzero);
+
+/* Size in doubles of one block / of a packed batch (host-side helper). */
+size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, int ncenter);
+
+/*
+ * Whole-job driver for the reference benchmark loop (examples/time_c60.c:200-219): every unique
+ * quartet i>=j, k>=l, k<=i of int2e_sph, evaluated class by class into a device-resident ring of
+ * `chunk_bytes` (0 -> default).  Rank `rank` of `nranks` evaluates a static, cost-balanced shard
+ * (no communication).  If `host_sink` != NULL every finished chunk is copied to it (pinned host
+ * buffer of at least chunk_bytes) inside the call -- the end-to-end mode.
+ *   stats[0] shell quartets evaluated     stats[1] integrals written
+ *   stats[2] primitive quartets executed  stats[3] sum of all integrals (checksum)
+ *   stats[4] kernel launches              stats[5] device->host bytes
+ *   stats[6] model FLOPs of the executed primitive quartets (SURVEY 8d formula)
+ *   stats[7] GPU milliseconds of the ERI kernels (CUDA events on the launch stream)
+ */
+int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
+                                  double *host_sink, double *stats);
+
+/* Last error text of the calling thread ("" if none). */
+const char *cintb200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""libcint_b200 -- B200 (sm_100a) implementation of libcint's ERI hot path behind the libcint C ABI.
+
+The product is the shared library ``libcint_b200/libcint_b200.so`` (sources in ``csrc/``, C headers in
+``include/``).  This Python module is only the ctypes mirror of how the reference's own tests drive
+libcint (``testsuite/test_cint.py:16-20``): same function names, same argument order.
+
+There is no CPU fallback: importing works anywhere, but any compute call raises / returns an error
+when the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcint_b200.so")
+DATA_DIR = os.path.join(_HERE, "data")
+
+SPH, CART = 0, 1
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the CUDA library; fails loudly if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error("%s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cd, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+    lib.cintb200_create.argtypes = [ctypes.POINTER(vp), vp, ci, vp, ci, vp, ci]
+    lib.cintb200_create.restype = ci
+    lib.cintb200_destroy.argtypes = [vp]
+    lib.cintb200_destroy.restype = None
+    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, ci, vp, sz, vp, vp, ci, vp]
+        f.restype = ctypes.c_long
+    lib.cintb200_block_size.argtypes = [vp, ci, vp, ci]
+    lib.cintb200_block_size.restype = sz
+    lib.cintb200_last_error.restype = ctypes.c_char_p
+    if hasattr(lib, "cintb200_int2e_sph_all_unique"):
+        lib.cintb200_int2e_sph_all_unique.argtypes = [vp, ci, ci, sz, vp, vp]
+        lib.cintb200_int2e_sph_all_unique.restype = ci
+    for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
+        f.restype = ci
+    for name in ("cint2e_sph", "cint2e_cart", "cint3c2e_sph", "cint3c2e_cart"):
+        f = getattr(lib, name)
+        f.argtypes = [vp, vp, vp, ci, vp, ci, vp, vp]
+        f.restype = ci
+    lib.CINTgto_norm.argtypes = [ci, cd]
+    lib.CINTgto_norm.restype = cd
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _as_basis(atm, bas, env):
+    atm = np.ascontiguousarray(atm, dtype=np.int32).reshape(-1, 6)
+    bas = np.ascontiguousarray(bas, dtype=np.int32).reshape(-1, 8)
+    env = np.ascontiguousarray(env, dtype=np.float64)
+    return atm, bas, env
+
+
+def shell_dims(bas, shls, cart=False):
+    bas = np.asarray(bas).reshape(-1, 8)
+    out = []
+    for s in shls:
+        l = int(bas[s, 1])
+        out.append(((l + 1) * (l + 2) // 2 if cart else 2 * l + 1) * int(bas[s, 3]))
+    return out
+
+
+class Context:
+    """Device-resident basis + shell-pair tables (the object the C API hands out as ``CINTOpt*``)."""
+
+    def __init__(self, atm, bas, env, device=-1):
+        self.lib = load_library()
+        self.atm, self.bas, self.env = _as_basis(atm, bas, env)
+        h = ctypes.c_void_p()
+        rc = self.lib.cintb200_create(ctypes.byref(h), _p(self.atm), len(self.atm), _p(self.bas), len(self.bas),
+                                      _p(self.env), device)
+        if rc != 0:
+            raise B200Error("cintb200_create failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.cintb200_destroy(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def _batch(self, fn, ncenter, shls, kind, out=None, out_off=None, device_ptr=None):
+        shls = np.ascontiguousarray(shls, dtype=np.int32).reshape(-1, ncenter)
+        n = len(shls)
+        cart = kind == CART
+        sizes = np.array([int(np.prod(shell_dims(self.bas, s, cart))) for s in shls], dtype=np.uint64)
+        if out_off is None:
+            offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
+            total = int(sizes.sum())
+        else:
+            offs = np.ascontiguousarray(out_off, dtype=np.uint64)
+            total = int((offs + sizes).max()) if n else 0
+        nz = np.zeros(n, dtype=np.int32)
+        if device_ptr is not None:
+            rc = fn(self.handle, kind, _p(shls), n, _p(offs), ctypes.c_void_p(device_ptr), 1, _p(nz))
+            res = None
+        else:
+            if out is None:
+                out = np.zeros(total)
+            rc = fn(self.handle, kind, _p(shls), n, _p(offs), _p(out), 0, _p(nz))
+            res = out
+        if rc < 0:
+            raise B200Error("batch failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return res, offs.astype(np.int64), sizes.astype(np.int64), nz
+
+    def int2e_batch(self, shls, kind=SPH, **kw):
+        """Evaluate many shell quartets; returns (packed values, offsets, sizes, nonzero flags)."""
+        return self._batch(self.lib.cintb200_int2e_batch, 4, shls, kind, **kw)
+
+    def int3c2e_batch(self, shls, kind=SPH, **kw):
+        return self._batch(self.lib.cintb200_int3c2e_batch, 3, shls, kind, **kw)
+
+    def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
+        """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array."""
+        stats = np.zeros(16)
+        rc = self.lib.cintb200_int2e_sph_all_unique(self.handle, rank, nranks, chunk_bytes,
+                                                    ctypes.c_void_p(host_sink) if host_sink else None, _p(stats))
+        if rc < 0:
+            raise B200Error("all_unique failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return stats
+
+
+def _call_single(name, ncenter, shls, atm, bas, env, opt=None, dims=None, out=None, cart=False):
+    """One libcint-style call through the drop-in symbol `name` (e.g. 'int2e_sph')."""
+    lib = load_library()
+    atm, bas, env = _as_basis(atm, bas, env)
+    d = shell_dims(bas, shls, cart)
+    if out is None:
+        shape = tuple(dims) if dims is not None else tuple(d)
+        out = np.zeros(shape, order="F")
+    cshls = (ctypes.c_int * ncenter)(*[int(s) for s in shls])
+    cdims = (ctypes.c_int * ncenter)(*[int(x) for x in dims]) if dims is not None else None
+    rc = getattr(lib, name)(_p(out), cdims, cshls, _p(atm), len(atm), _p(bas), len(bas), _p(env),
+                            opt.handle if isinstance(opt, Context) else opt, None)
+    return out, rc
+
+
+def int2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int2e_sph", 4, shls, atm, bas, env, opt, dims, out)
+
+
+def int2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int2e_cart", 4, shls, atm, bas, env, opt, dims, out, cart=True)
+
+
+def int3c2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int3c2e_sph", 3, shls, atm, bas, env, opt, dims, out)
+
+
+def int3c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int3c2e_cart", 3, shls, atm, bas, env, opt, dims, out, cart=True)
+
+
+def load_fixture(name):
+    """atm, bas, env of a committed benchmark molecule (see tools/make_fixtures.py)."""
+    d = np.load(os.path.join(DATA_DIR, name + ".npz"))
+    return d["atm"].astype(np.int32), d["bas"].astype(np.int32), d["env"].astype(np.float64)

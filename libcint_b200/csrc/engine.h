@@ -1,0 +1,46 @@
+// Definition of the context object (the CINTOpt handed to callers of include/cint.h).
+#pragma once
+#include <vector>
+#include <mutex>
+#include <cuda_runtime.h>
+#include "types.h"
+
+#define B200_CTX_MAGIC 0x42323030
+
+struct ShellInfo {
+    int l, nprim, nctr;
+    int ao_sph, ao_cart;
+    const double *r, *exps, *coef;      // into CINTOpt::env
+};
+
+struct CINTOpt {
+    int magic = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int natm = 0, nbas = 0;
+    int nao_sph = 0, nao_cart = 0;
+    uint64_t hash = 0;
+    double expcutoff4 = 60, expcutoff3 = 60, omega = 0;
+    std::vector<int> atm, bas;
+    std::vector<double> env;
+    std::vector<ShellInfo> shells;
+    std::vector<PairHdr> pairs;
+    std::vector<PrimPair> prims;
+    std::vector<double> pcoef;
+    // device tables
+    PairHdr *d_pairs = nullptr;
+    PrimPair *d_prims = nullptr;
+    double *d_pcoef = nullptr, *d_rys = nullptr, *d_c2s = nullptr;
+    // reusable work buffers
+    Task *d_tasks = nullptr;        size_t cap_tasks = 0;
+    double *d_out = nullptr;        size_t cap_out = 0;
+    int *d_nonzero = nullptr;       size_t cap_nonzero = 0;
+    double *d_scratch = nullptr;    size_t cap_scratch = 0;
+    void *h_stage = nullptr;        size_t cap_stage = 0;
+    unsigned long long *d_counters = nullptr;
+    long long launches = 0;
+    std::mutex mtx;
+};
+
+int b200_fail(int code, const char *fmt, ...);
+int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_host);

@@ -1,0 +1,353 @@
+// Generic ERI kernel: one thread block per shell tuple, any angular momentum up to B200_LMAX, any
+// contraction pattern, 4-centre (ij|kl) and 3-centre (ij|k) tuples, spherical or Cartesian output.
+//
+// It is the catch-all of the engine: classes without a specialised kernel (kern_spd.cu) run here.
+// Stages per tuple, with the reference function each one replaces:
+//   primitive loop + screening   CINT2e_loop            src/cint2e.c:660-758  (rule :694,:720)
+//   roots / weights              CINTrys_roots          src/rys_roots.c:57     -> table polynomials (rys.cuh)
+//   recurrence coefficients      CINTg0_2e              src/g2e.c:4518-4540    -> written in t^2
+//   2-D VRR                      CINTg0_2e_2d           src/g2e.c:272-421      -> one thread per (root, axis), smem
+//   [e0|f0] quadrature sum       CINTgout2e             src/cint2e.c:961       -> one thread per Cartesian element
+//   contraction                  CINTprim_to_ctr_0/1    src/g1e.c:530-560      -> coefficient products from the pair table
+//   HRR                          CINTg0_*2d_4d          src/g2e.c:428-693      -> applied ONCE per contracted tuple on
+//                                                                                [e0|f0] (exact identity; the reference
+//                                                                                applies it per primitive and root)
+//   cart->sph, scatter           c2s_sph_2e1            src/cart2sph.c:5324    -> dense small matrices, strided store
+#include "types.h"
+#include "rys.cuh"
+#include "kernels.h"
+
+__constant__ int c_cart_off[2 * B200_LMAX + 2];                 // first component of degree l
+__constant__ unsigned char c_cart_xyz[3 * 560];                 // (lx,ly,lz) of every component, l = 0..2*LMAX
+
+__device__ __forceinline__ int cart_index(int lx, int lz, int l)
+{
+    int r = l - lx;
+    return r * (r + 1) / 2 + lz;
+}
+
+// One HRR level on a [pre][part][post] array.  Input level holds, for every le in [l0, ltop],
+// ncart(le) x ncart(jb-1) entries; output level holds le in [l0, ltop-1] with ncart(jb).
+//   (a, b + 1_d | = (a + 1_d, b | + AB_d (a, b |
+__device__ void hrr_level(const double *in, double *out, int pre, int post, int l0, int ltop, int jb,
+                          const double *ab)
+{
+    const int nb_in = B200_NCART(jb - 1), nb_out = B200_NCART(jb);
+    int in_part = 0, out_part = 0;
+    for (int le = l0; le <= ltop; le++) in_part += B200_NCART(le) * nb_in;
+    for (int le = l0; le < ltop; le++) out_part += B200_NCART(le) * nb_out;
+    const int total = pre * out_part * post;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int q = idx % post;
+        int part = (idx / post) % out_part;
+        int p = idx / (post * out_part);
+        int le = l0, in_off = 0;
+        while (part >= B200_NCART(le) * nb_out) {
+            part -= B200_NCART(le) * nb_out;
+            in_off += B200_NCART(le) * nb_in;
+            le++;
+        }
+        int ie = part / nb_out, ib = part - ie * nb_out;
+        const unsigned char *bc = c_cart_xyz + 3 * (c_cart_off[jb] + ib);
+        const unsigned char *ac = c_cart_xyz + 3 * (c_cart_off[le] + ie);
+        int bx = bc[0], by = bc[1], bz = bc[2];
+        int ax = ac[0], az = ac[2];
+        int d = bx ? 0 : (by ? 1 : 2);
+        bx -= (d == 0); bz -= (d == 2);
+        int ibp = cart_index(bx, bz, jb - 1);
+        int iep = cart_index(ax + (d == 0), az + (d == 2), le + 1);
+        const double *base = in + (size_t)p * in_part * post;
+        double lo = base[(size_t)(in_off + ie * nb_in + ibp) * post + q];
+        double hi = base[(size_t)(in_off + B200_NCART(le) * nb_in + iep * nb_in + ibp) * post + q];
+        out[idx] = hi + ab[d] * lo;
+    }
+}
+
+// out[p][m][q] = sum_c C[m][c] in[p][c][q]
+__device__ void c2s_index(const double *in, double *out, int pre, int post, int l, const double *__restrict__ cmat)
+{
+    const int nin = B200_NCART(l), nout = 2 * l + 1;
+    const int total = pre * nout * post;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int q = idx % post;
+        int m = (idx / post) % nout;
+        int p = idx / (post * nout);
+        const double *src = in + (size_t)p * nin * post + q;
+        const double *cm = cmat + m * nin;
+        double s = 0;
+        for (int c = 0; c < nin; c++) s = fma(__ldg(cm + c), src[(size_t)c * post], s);
+        out[idx] = s;
+    }
+}
+
+__global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
+                                   double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters)
+{
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x;
+    const int la = C.la, lb = C.lb, lc = C.lc, ld = C.ld;
+    const int nmax = la + lb, mmax = lc + ld, nroots = C.nroots;
+    const int nE = C.nE, nF = C.nF, nEF = nE * nF;
+    const int ncomb = C.ncab * C.nccd;
+    const int gstride_r = (nmax + 1) * (mmax + 1);
+
+    double *s_rw = sm;                                   // [2*nroots]  t2,w interleaved as p
+    double *s_g = s_rw + 2 * nroots;                     // [3][nroots][nmax+1][mmax+1]
+    int *s_ecomp = (int *)(s_g + 3 * nroots * gstride_r);   // [nE], [nF] packed exponents
+    int *s_fcomp = s_ecomp + nE;
+    double *s_dyn = (double *)(s_fcomp + nF + ((nE + nF) & 1));
+    double *gscratch = C.scratch + (size_t)blockIdx.x * C.scratch_per_block;
+    double *acc, *w0, *w1;
+    if (C.acc_in_smem) { acc = s_dyn; s_dyn += (size_t)ncomb * nEF; }
+    else { acc = gscratch; gscratch += (size_t)ncomb * nEF; }
+    if (C.work_in_smem) { w0 = s_dyn; w1 = w0 + C.work_size; }
+    else { w0 = gscratch; w1 = w0 + C.work_size; }
+
+    // component tables of the [e0| and |f0] index ranges
+    for (int e = tid; e < nE; e += blockDim.x) {
+        int le = la, r = e;
+        while (r >= B200_NCART(le)) { r -= B200_NCART(le); le++; }
+        const unsigned char *c = c_cart_xyz + 3 * (c_cart_off[le] + r);
+        s_ecomp[e] = c[0] | (c[1] << 8) | (c[2] << 16);
+    }
+    for (int f = tid; f < nF; f += blockDim.x) {
+        int lf = lc, r = f;
+        while (r >= B200_NCART(lf)) { r -= B200_NCART(lf); lf++; }
+        const unsigned char *c = c_cart_xyz + 3 * (c_cart_off[lf] + r);
+        s_fcomp[f] = c[0] | (c[1] << 8) | (c[2] << 16);
+    }
+    const double fsp[2] = {0.282094791773878143, 0.488602511902919921};
+    const double common = 34.986836655249725693 /* 2 pi^3 / sqrt(pi) */
+        * (la < 2 ? fsp[la] : 1.0) * (lb < 2 ? fsp[lb] : 1.0) * (lc < 2 ? fsp[lc] : 1.0) * (ld < 2 ? fsp[ld] : 1.0);
+
+    for (long long t = blockIdx.x; t < ntasks; t += gridDim.x) {
+        const Task task = tasks[t];
+        const PairHdr hb = P.pairs[task.bra];
+        const PairHdr hk = P.pairs[task.ket];
+        __syncthreads();
+        for (int i = tid; i < ncomb * nEF; i += blockDim.x) acc[i] = 0.0;
+        int executed = 0;
+
+        for (int kq = 0; kq < hk.npp; kq++) {
+            const PrimPair pk = P.prims[hk.pp_off + kq];
+            if (pk.cce > P.expcutoff) continue;
+            for (int bq = 0; bq < hb.npp; bq++) {
+                const PrimPair pb = P.prims[hb.pp_off + bq];
+                if (pb.cce + pk.cce > P.expcutoff) continue;
+                executed++;
+                const double aij = pb.aij, akl = pk.aij;
+                const double asum = aij + akl;
+                const double a1 = aij * akl;
+                const double a0 = a1 / asum;
+                const double dx = pb.px - pk.px, dy = pb.py - pk.py, dz = pb.pz - pk.pz;
+                double x = a0 * (dx * dx + dy * dy + dz * dz);
+                double fac1 = common * pb.kij * pk.kij * sqrt(a0 / (a1 * a1 * a1));
+                double theta = 1.0;
+                if (P.omega > 0) {              // long-range attenuation, src/g2e.c:4477-4492
+                    theta = P.omega * P.omega / (P.omega * P.omega + a0);
+                    x *= theta;
+                    fac1 *= sqrt(theta);
+                }
+                __syncthreads();                // previous primitive's G fully consumed
+                if (tid < 2 * nroots) s_rw[tid] = rys_value(P.rys_coef, nroots, x, tid);
+                __syncthreads();
+                if (tid < 3 * nroots) {
+                    const int r = tid / 3, xyz = tid - 3 * r;
+                    const double s = s_rw[2 * r] * theta;          // t^2 (LR: theta t^2)
+                    const double sa = s * akl / asum, sk = s * aij / asum;
+                    const double b00 = 0.5 * s / asum;
+                    const double b10 = 0.5 * (1.0 - sa) / aij;
+                    const double b01 = 0.5 * (1.0 - sk) / akl;
+                    const double pq = xyz == 0 ? dx : (xyz == 1 ? dy : dz);
+                    const double pa = (xyz == 0 ? pb.px : (xyz == 1 ? pb.py : pb.pz)) - hb.ra[xyz];
+                    const double qc = (xyz == 0 ? pk.px : (xyz == 1 ? pk.py : pk.pz)) - hk.ra[xyz];
+                    const double c00 = pa - sa * pq;
+                    const double c0p = qc + sk * pq;
+                    double *g = s_g + (size_t)(xyz * nroots + r) * gstride_r;
+                    const int ms = mmax + 1;
+                    g[0] = (xyz == 2) ? s_rw[2 * r + 1] * fac1 : 1.0;
+                    if (nmax > 0) g[ms] = c00 * g[0];
+                    for (int n = 1; n < nmax; n++) g[(n + 1) * ms] = c00 * g[n * ms] + n * b10 * g[(n - 1) * ms];
+                    for (int m = 0; m < mmax; m++)
+                        for (int n = 0; n <= nmax; n++) {
+                            double v = c0p * g[n * ms + m];
+                            if (m > 0) v += m * b01 * g[n * ms + m - 1];
+                            if (n > 0) v += n * b00 * g[(n - 1) * ms + m];
+                            g[n * ms + m + 1] = v;
+                        }
+                }
+                __syncthreads();
+                const double *ccb = P.pcoef + hb.cc_off + (size_t)bq * C.ncab;
+                const double *cck = P.pcoef + hk.cc_off + (size_t)kq * C.nccd;
+                for (int idx = tid; idx < nEF; idx += blockDim.x) {
+                    const int e = idx / nF, f = idx - e * nF;
+                    const int ec = s_ecomp[e], fc = s_fcomp[f];
+                    const int ms = mmax + 1;
+                    const int ox = (ec & 255) * ms + (fc & 255);
+                    const int oy = ((ec >> 8) & 255) * ms + ((fc >> 8) & 255);
+                    const int oz = ((ec >> 16) & 255) * ms + ((fc >> 16) & 255);
+                    const double *gx = s_g + ox, *gy = s_g + (size_t)nroots * gstride_r + oy,
+                                 *gz = s_g + (size_t)2 * nroots * gstride_r + oz;
+                    double v = 0;
+                    for (int r = 0; r < nroots; r++)
+                        v = fma(gx[r * gstride_r] * gy[r * gstride_r], gz[r * gstride_r], v);
+                    for (int ck = 0; ck < C.nccd; ck++) {
+                        const double vk = v * __ldg(cck + ck);
+                        for (int cb = 0; cb < C.ncab; cb++)
+                            acc[(size_t)(ck * C.ncab + cb) * nEF + idx] += vk * __ldg(ccb + cb);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (nonzero) nonzero[t] = executed > 0;
+            if (counters) atomicAdd(counters, (unsigned long long)executed);
+        }
+
+        // ---- epilogue per contraction combination: HRR (bra, ket), c2s, strided store ----
+        const int nfa = B200_NCART(la), nfb = B200_NCART(lb), nfc = B200_NCART(lc), nfd = B200_NCART(ld);
+        const int da = P.cart ? nfa : 2 * la + 1, db = P.cart ? nfb : 2 * lb + 1;
+        const int dc = P.cart ? nfc : 2 * lc + 1, dd = P.cart ? nfd : 2 * ld + 1;
+        for (int comb = 0; comb < ncomb; comb++) {
+            const int cab = comb % C.ncab, ccd = comb / C.ncab;
+            const int ca = cab % hb.nca, cb = cab / hb.nca;
+            const int cc = ccd % hk.nca, cd = ccd / hk.nca;
+            const double *cur = acc + (size_t)comb * nEF;
+            double *nxt = w0;
+            for (int jb = 1; jb <= lb; jb++) {
+                hrr_level(cur, nxt, 1, nF, la, la + lb - jb + 1, jb, hb.ab);
+                __syncthreads();
+                cur = nxt;
+                nxt = (nxt == w0) ? w1 : w0;
+            }
+            for (int jd = 1; jd <= ld; jd++) {
+                hrr_level(cur, nxt, nfa * nfb, 1, lc, lc + ld - jd + 1, jd, hk.ab);
+                __syncthreads();
+                cur = nxt;
+                nxt = (nxt == w0) ? w1 : w0;
+            }
+            if (!P.cart) {
+                if (la > 1) { c2s_index(cur, nxt, 1, nfb * nfc * nfd, la, P.c2s + C.c2s_off[0]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (lb > 1) { c2s_index(cur, nxt, da, nfc * nfd, lb, P.c2s + C.c2s_off[1]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (lc > 1) { c2s_index(cur, nxt, da * db, nfd, lc, P.c2s + C.c2s_off[2]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (ld > 1) { c2s_index(cur, nxt, da * db * dc, 1, ld, P.c2s + C.c2s_off[3]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+            }
+            // store: thread index runs over the index with the smallest stride first
+            const int n_out = da * db * dc * dd;
+            double *dst = out + task.off + (long long)ca * da * task.sa + (long long)cb * db * task.sb
+                        + (long long)cc * dc * task.sc + (long long)cd * dd * task.sd;
+            const bool a_fast = task.sa <= task.sb;
+            for (int idx = tid; idx < n_out; idx += blockDim.x) {
+                int ma, mb, r;
+                if (a_fast) { ma = idx % da; r = idx / da; mb = r % db; r /= db; }
+                else        { mb = idx % db; r = idx / db; ma = r % da; r /= da; }
+                const int mc = r % dc, md = r / dc;
+                dst[(long long)ma * task.sa + (long long)mb * task.sb + mc * task.sc + md * task.sd]
+                    = cur[((ma * db + mb) * dc + mc) * dd + md];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int sum_ncart(int l0, int l1) { int s = 0; for (int l = l0; l <= l1; l++) s += B200_NCART(l); return s; }
+
+// sizes of every intermediate of the epilogue, to dimension the ping-pong buffers
+static size_t epilogue_work_size(int la, int lb, int lc, int ld, int cart)
+{
+    size_t mx = 1;
+    const int nF = sum_ncart(lc, lc + ld);
+    const int nfa = B200_NCART(la), nfb = B200_NCART(lb), nfc = B200_NCART(lc), nfd = B200_NCART(ld);
+    for (int jb = 1; jb <= lb; jb++) {
+        size_t part = 0;
+        for (int le = la; le <= la + lb - jb; le++) part += (size_t)B200_NCART(le) * B200_NCART(jb);
+        if (part * nF > mx) mx = part * nF;
+    }
+    for (int jd = 1; jd <= ld; jd++) {
+        size_t part = 0;
+        for (int lf = lc; lf <= lc + ld - jd; lf++) part += (size_t)B200_NCART(lf) * B200_NCART(jd);
+        if (part * nfa * nfb > mx) mx = part * nfa * nfb;
+    }
+    size_t full = (size_t)nfa * nfb * nfc * nfd;
+    if (full > mx) mx = full;
+    (void)cart;
+    return mx;
+}
+
+int generic_setup_constants()
+{
+    int off[2 * B200_LMAX + 2];
+    static unsigned char xyz[3 * 560];
+    int n = 0;
+    for (int l = 0; l <= 2 * B200_LMAX; l++) {
+        off[l] = n;
+        for (int lx = l; lx >= 0; lx--)
+            for (int ly = l - lx; ly >= 0; ly--, n++) {
+                xyz[3 * n] = (unsigned char)lx;
+                xyz[3 * n + 1] = (unsigned char)ly;
+                xyz[3 * n + 2] = (unsigned char)(l - lx - ly);
+            }
+    }
+    off[2 * B200_LMAX + 1] = n;
+    if (n > 560) return -1;
+    if (cudaMemcpyToSymbol(c_cart_off, off, sizeof off) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(c_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
+    return 0;
+}
+
+// Plan a launch for one class; returns 0 on success.  scratch is (re)allocated by the caller.
+int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
+                 int cart, long long ntasks, const int *c2s_off_table)
+{
+    memset(C, 0, sizeof *C);
+    C->la = la; C->lb = lb; C->lc = lc; C->ld = ld;
+    C->nroots = (la + lb + lc + ld) / 2 + 1;
+    if (C->nroots > RYS_NMAX) return -1;
+    C->ncab = ncab; C->nccd = nccd;
+    C->nE = sum_ncart(la, la + lb);
+    C->nF = sum_ncart(lc, lc + ld);
+    C->work_size = (int)epilogue_work_size(la, lb, lc, ld, cart);
+    C->c2s_off[0] = c2s_off_table[la]; C->c2s_off[1] = c2s_off_table[lb];
+    C->c2s_off[2] = c2s_off_table[lc]; C->c2s_off[3] = c2s_off_table[ld];
+    const size_t nEF = (size_t)C->nE * C->nF;
+    const int nmax = la + lb, mmax = lc + ld;
+    size_t fixed = sizeof(double) * (2 * C->nroots + (size_t)3 * C->nroots * (nmax + 1) * (mmax + 1))
+                 + sizeof(int) * (C->nE + C->nF + 2);
+    size_t acc_b = sizeof(double) * nEF * ncab * nccd;
+    size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
+    const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
+    size_t smem = fixed;
+    C->acc_in_smem = (smem + acc_b <= budget);
+    if (C->acc_in_smem) smem += acc_b;
+    C->work_in_smem = (smem + work_b <= budget);
+    if (C->work_in_smem) smem += work_b;
+    if (smem > 200 * 1024) return -1;
+    C->scratch_per_block = (C->acc_in_smem ? 0 : nEF * ncab * nccd) + (C->work_in_smem ? 0 : 2 * (size_t)C->work_size);
+    int threads = (int)((nEF + 31) / 32 * 32);
+    if (threads < 64) threads = 64;        // >= 3 * nroots for nroots <= 13 needs 39 threads
+    if (threads > 256) threads = 256;
+    L->threads = threads;
+    L->smem = smem;
+    int per_sm = (int)(budget * 2 / (smem > 4096 ? smem : 4096));
+    if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+    if (per_sm > 16) per_sm = 16;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)148 * per_sm;
+    if (grid > ntasks) grid = ntasks;
+    L->grid = (int)grid;
+    return 0;
+}
+
+int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLaunch &L, const Task *tasks,
+                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream)
+{
+    if (ntasks <= 0) return 0;
+    if (L.smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(eri_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem) != cudaSuccess)
+            return -1;
+    }
+    eri_generic_kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

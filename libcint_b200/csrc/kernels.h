@@ -1,0 +1,25 @@
+// Launch-side interface between the host engine (engine.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+#include "types.h"
+
+struct GenericClass {           // uniform per launch of eri_generic_kernel
+    int la, lb, lc, ld;
+    int nroots;
+    int ncab, nccd;             // contraction combinations of the bra / ket pair
+    int nE, nF;                 // Cartesian components of [e0| (e = la..la+lb) and |f0]
+    int acc_in_smem, work_in_smem;
+    int work_size;              // doubles per ping-pong buffer of the epilogue
+    int c2s_off[4];             // offsets of the four c2s matrices inside EngineParams::c2s
+    double *scratch;            // global scratch, scratch_per_block doubles per block
+    size_t scratch_per_block;
+};
+
+struct GenericLaunch { int grid, threads; size_t smem; };
+
+int generic_setup_constants();
+int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
+                 int cart, long long ntasks, const int *c2s_off_table);
+int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLaunch &L, const Task *tasks,
+                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream);

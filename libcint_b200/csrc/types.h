@@ -1,0 +1,61 @@
+// Shared host/device data layout of the B200 ERI engine.
+//
+// HBM layout (all built once per context, read-only afterwards):
+//   PairHdr  pairs[npair]     one per unordered shell pair {i,j} (canonical orientation: the shell
+//                             with the larger angular momentum is `a`), followed by nbas
+//                             single-shell pseudo pairs used as the ket of 3-centre integrals.
+//   PrimPair prims[]          surviving primitive pairs of every shell pair, back to back (64 B each).
+//   double   pcoef[]          contraction-coefficient products c_a[ca][ip] * c_b[cb][jp] per
+//                             primitive pair, nca*ncb doubles each (ca fastest).
+// This is the device counterpart of the reference's CINTOpt/PairData (include/cint.h.in:140-152,
+// src/optimizer.c:288-342); screening uses the same cce estimate.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#define B200_LMAX 6            // per-shell angular momentum limit of this build
+#define B200_MAXROOTS 13       // (4*LMAX)/2+1
+#define B200_NCART(l) (((l) + 1) * ((l) + 2) / 2)
+
+struct PairHdr {               // 96 bytes
+    int sh_a, sh_b;            // shell ids in canonical orientation (sh_b = -1: single-shell pseudo pair)
+    int la, lb;
+    int npp;                   // surviving primitive pairs
+    int pp_off;                // first PrimPair
+    int nca, ncb;              // contraction counts of a, b
+    int cc_off;                // first coefficient product (doubles)
+    int ao_a, ao_b;            // AO offsets (spherical) of a and b -- used by tile mode only
+    int pad;
+    double ra[3];              // centre of a
+    double ab[3];              // ra - rb  (HRR shift)
+};
+
+struct PrimPair {              // 64 bytes, 16-byte aligned for vector loads
+    double aij;                // a_a + a_b
+    double px, py, pz;         // Gaussian product centre
+    double kij;                // exp(-a_a a_b / aij |ab|^2) (times 2 sqrt(pi) for pseudo pairs)
+    double cce;                // screening estimate of CINTset_pairdata (src/optimizer.c:325)
+    double inv_aij;            // 1 / aij
+    int ipa, ipb;              // primitive indices inside shells a, b
+};
+
+// One unit of work for the kernels: (bra pair | ket pair) -> block written at out + off with
+// strides given for the CANONICAL indices a,b,c,d (elements).
+struct Task {
+    int bra, ket;              // indices into pairs[]
+    int sb;                    // stride of b   (stride of a is sa)
+    int sa;
+    long long sc, sd;          // strides of c, d
+    long long off;             // block offset in `out`
+};
+
+struct EngineParams {          // passed by value to kernels
+    const PairHdr *pairs;
+    const PrimPair *prims;
+    const double *pcoef;
+    const double *rys_coef;    // all nroots tables back to back (RYS_TAB_COEF)
+    const double *c2s;         // C2S_COEF
+    double expcutoff;          // quartet primitive screening: cce_ij + cce_kl <= expcutoff
+    double omega;              // env[PTR_RANGE_OMEGA]; > 0 long range, 0 plain Coulomb
+    int cart;                  // 1: Cartesian output (int2e_cart), 0: real spherical
+};

@@ -1,0 +1,78 @@
+/*
+ * TEST/BENCH INFRASTRUCTURE: times the UNMODIFIED reference library (oracle/_ref/libcint_ref.so, or
+ * any library exporting the libcint ABI) on the host cores, with the loop shape of the reference's own
+ * benchmark driver (examples/time_c60.c:196-219: OpenMP `for ij` schedule(dynamic,2), kl <= pairs with
+ * k <= i, optimizer on).  Differences from that driver, all stated in the JSON it prints:
+ *   - the basis comes from a binary dump (natm, nbas, nenv, atm, bas, env) instead of inline C;
+ *   - only every `stride`-th ij pair (offset `phase`) is evaluated so the run is a bounded sample;
+ *   - one buffer per thread instead of malloc/free per quartet (the library call is what is timed).
+ * usage: time_ref <lib.so> <basis.bin> <stride> <phase> [repeat]
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <dlfcn.h>
+#include <omp.h>
+
+typedef int (*intor_t)(double *, int *, int *, int *, int, int *, int, double *, void *, double *);
+typedef void (*optim_t)(void **, int *, int, int *, int, double *);
+typedef void (*delopt_t)(void **);
+
+int main(int argc, char **argv)
+{
+        if (argc < 5) { fprintf(stderr, "usage: %s lib.so basis.bin stride phase\n", argv[0]); return 2; }
+        void *h = dlopen(argv[1], RTLD_NOW);
+        if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 1; }
+        intor_t intor = (intor_t)dlsym(h, "int2e_sph");
+        optim_t optim = (optim_t)dlsym(h, "int2e_optimizer");
+        delopt_t delopt = (delopt_t)dlsym(h, "CINTdel_optimizer");
+        FILE *f = fopen(argv[2], "rb");
+        if (!f || !intor || !optim) { fprintf(stderr, "bad input\n"); return 1; }
+        int hdr[3];
+        if (fread(hdr, sizeof(int), 3, f) != 3) return 1;
+        int natm = hdr[0], nbas = hdr[1], nenv = hdr[2];
+        int *atm = malloc(sizeof(int) * natm * 6), *bas = malloc(sizeof(int) * nbas * 8);
+        double *env = malloc(sizeof(double) * nenv);
+        if (fread(atm, sizeof(int), natm * 6, f) != (size_t)natm * 6) return 1;
+        if (fread(bas, sizeof(int), nbas * 8, f) != (size_t)nbas * 8) return 1;
+        if (fread(env, sizeof(double), nenv, f) != (size_t)nenv) return 1;
+        fclose(f);
+        long stride = atol(argv[3]), phase = atol(argv[4]);
+        long npair = (long)nbas * (nbas + 1) / 2;
+        int *ish = malloc(sizeof(int) * npair), *jsh = malloc(sizeof(int) * npair);
+        int *dim = malloc(sizeof(int) * nbas);
+        long ij = 0;
+        int maxd = 0;
+        for (int i = 0; i < nbas; i++) {
+                dim[i] = (2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3];
+                if (dim[i] > maxd) maxd = dim[i];
+                for (int j = 0; j <= i; j++, ij++) { ish[ij] = i; jsh[ij] = j; }
+        }
+        void *opt = NULL;
+        optim(&opt, atm, natm, bas, nbas, env);
+        double nints = 0, checksum = 0;
+        long nquart = 0;
+        double t0 = omp_get_wtime();
+#pragma omp parallel reduction(+ : nints, checksum, nquart)
+        {
+                double *buf = malloc(sizeof(double) * maxd * maxd * maxd * maxd);
+#pragma omp for schedule(dynamic, 2)
+                for (long p = phase; p < npair; p += stride) {
+                        int i = ish[p], j = jsh[p];
+                        long klmax = (long)(i + 1) * (i + 2) / 2;
+                        for (long kl = 0; kl < klmax; kl++) {
+                                int shls[4] = {i, j, ish[kl], jsh[kl]};
+                                intor(buf, NULL, shls, atm, natm, bas, nbas, env, opt, NULL);
+                                long n = (long)dim[i] * dim[j] * dim[shls[2]] * dim[shls[3]];
+                                nints += n;
+                                checksum += buf[0] + buf[n - 1];
+                        }
+                        nquart += klmax;
+                }
+                free(buf);
+        }
+        double t1 = omp_get_wtime();
+        if (delopt) delopt(&opt);
+        printf("{\"seconds\": %.6f, \"integrals\": %.0f, \"quartets\": %ld, \"threads\": %d, \"stride\": %ld, \"phase\": %ld, \"checksum\": %.15e}\n",
+               t1 - t0, nints, nquart, omp_get_max_threads(), stride, phase, checksum);
+        return 0;
+}

@@ -1,0 +1,65 @@
+"""CPU test: the C-ABI shared library loads and exports every function include/*.h declares."""
+import ctypes
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = set()
+    for h in ("cint.h", "cint_b200.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        src = re.sub(r"//[^\n]*", "", src)
+        for m in re.finditer(r"\b(?:CINTIntegralFunction|CINTOptimizerFunction)\s+(\w+)\s*;", src):
+            names.add(m.group(1))
+        for m in re.finditer(r"^[A-Za-z_][\w \*]*?\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M):
+            if m.group(1) not in ("CINTIntegralFunction", "CINTOptimizerFunction"):
+                names.add(m.group(1))
+    return sorted(names)
+
+
+def test_headers_declare_the_hot_path():
+    names = declared_functions()
+    for must in ("int2e_sph", "int2e_cart", "int2e_optimizer", "int3c2e_sph", "cint2e_sph", "CINTdel_optimizer",
+                 "cintb200_create", "cintb200_int2e_batch", "cintb200_int3c2e_batch", "CINTgto_norm",
+                 "CINTcgto_spheric", "CINTtot_cgto_spheric"):
+        assert must in names, must
+
+
+def test_library_exports_every_declared_symbol():
+    import libcint_b200
+    assert os.path.exists(libcint_b200.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(libcint_b200.LIB_PATH)
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_host_helpers_without_gpu():
+    # pure host bookkeeping entry points (src/cint_bas.c, src/misc.c:86) need no device
+    import numpy as np
+    import libcint_b200
+    from libcint_b200.basis import gto_norm
+    lib = libcint_b200.load_library()
+    atm, bas, env = libcint_b200.load_fixture("c60_ccpvdz")
+    assert lib.CINTtot_cgto_spheric(bas.ctypes.data_as(ctypes.c_void_p), 300) == 840
+    assert lib.CINTtot_pgto_spheric(bas.ctypes.data_as(ctypes.c_void_p), 300) == 1560
+    assert lib.CINTcgto_spheric(4, bas.ctypes.data_as(ctypes.c_void_p)) == 5
+    for l, a in ((0, 0.3), (1, 2.5), (2, 0.55), (4, 11.0)):
+        assert abs(lib.CINTgto_norm(l, a) / gto_norm(l, a) - 1) < 1e-14
+    # CINTgto_norm(0, a) = (2a/pi)^(3/4) * 2 sqrt(pi)  (normalised s Gaussian over r^2 dr)
+    assert abs(lib.CINTgto_norm(0, 1.0) - 2 * np.pi ** .5 * (2 / np.pi) ** .75) < 1e-14
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import libcint_b200
+    atm, bas, env = libcint_b200.load_fixture("c2h6_631g")
+    with pytest.raises(libcint_b200.B200Error):
+        libcint_b200.Context(atm, bas, env)
+    out, rc = libcint_b200.int2e_sph((0, 0, 0, 0), atm, bas, env)
+    assert rc == 0

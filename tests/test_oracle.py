@@ -1,0 +1,135 @@
+"""CPU tests: pin the oracle (port) against the reference's known answers, committed golden vectors
+generated from the compiled reference, the mpmath roots, and -- when oracle/_ref exists -- the reference itself."""
+import os
+import ctypes
+import numpy as np
+import pytest
+import oracle_util as ou
+from libcint_b200 import load_fixture
+from libcint_b200.basis import reference_test_basis
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def fp(v):
+    return np.array([np.abs(v).sum(), (v * np.cos(np.arange(v.size))).sum()])
+
+
+def test_known_answer_int2e_sph():
+    # testsuite/test_cint.py:235-256,479: sum |(ij|kl)| over l, k<=l, j, i<=j == 56243.88080655417 (8 places)
+    atm, bas, env = reference_test_basis()
+    tot, cnt = 0.0, 0
+    for l in range(8):
+        for k in range(l + 1):
+            for j in range(8):
+                for i in range(j + 1):
+                    v, _ = ou.eval_tuple("port", "int2e_sph", (i, j, k, l), atm, bas, env)
+                    tot += np.abs(v).sum()
+                    cnt += v.size
+    assert round(abs(tot - 56243.88080655417) / cnt ** .5, 8) == 0
+    assert abs(tot - 56243.88080655417) < 1e-9
+
+
+def test_known_answer_int3c2e_sph():
+    # testsuite/test_3c2e.py:173-202,303: sum over i,j,k < 4 == 1586.350797347553 (10 places) and
+    # element-wise equality with int2e_sph + zero-exponent s shell of coefficient 2 sqrt(pi)
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    tot, cnt = 0.0, 0
+    for k in range(4):
+        bas[8, 0] = bas[k, 0]
+        for j in range(4):
+            for i in range(4):
+                v3, _ = ou.eval_tuple("port", "int3c2e_sph", (i, j, k), atm, bas, env)
+                v4, _ = ou.eval_tuple("port", "int2e_sph", (i, j, k, 8), atm, bas, env)
+                assert np.abs(v3 - v4).max() <= 1e-12 * max(1.0, np.abs(v4).max())
+                tot += np.abs(v3).sum()
+                cnt += v3.size
+    assert round(abs(tot - 1586.350797347553) / cnt ** .5, 10) == 0
+
+
+def test_port_vs_golden_testbasis():
+    g = np.load(os.path.join(GOLD, "testbasis.npz"))
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    for key_q, key_f, name, e in (("q4", "f4", "int2e_sph", env), ("q3", "f3", "int3c2e_sph", env),
+                                  ("qcart", "fcart", "int2e_cart", env)):
+        q, f = g[key_q], g[key_f]
+        step = 3 if key_q == "q4" else 1
+        for s, fr in zip(q[::step], f[::step]):
+            v, _ = ou.eval_tuple("port", name, s, atm, bas, e)
+            assert np.allclose(fp(v), fr, rtol=1e-11, atol=1e-11), (name, s)
+    env_lr = env.copy()
+    env_lr[8] = float(g["omega_lr"])
+    for s, fr in zip(g["qlr"][::2], g["flr"][::2]):
+        v, _ = ou.eval_tuple("port", "int2e_sph", s, atm, bas, env_lr)
+        assert np.allclose(fp(v), fr, rtol=1e-11, atol=1e-11), ("lr", s)
+
+
+def test_port_vs_golden_c60():
+    g = np.load(os.path.join(GOLD, "c60_blocks.npz"))
+    atm, bas, env = load_fixture("c60_ccpvdz")
+    for n, s in enumerate(g["shls"][:40]):
+        v, _ = ou.eval_tuple("port", "int2e_sph", s, atm, bas, env)
+        r = g["values"][g["offsets"][n]:g["offsets"][n + 1]]
+        assert np.abs(v - r).max() < 1e-12, s
+    # SURVEY appendix D literals (oracle build of the survey): (4,3,2,0) sum|v| and fp
+    v, _ = ou.eval_tuple("port", "int2e_sph", (4, 3, 2, 0), atm, bas, env)
+    assert abs(np.abs(v).sum() - 2.7340034950083425e-01) < 1e-13
+    assert abs((v * np.cos(np.arange(v.size))).sum() - 1.2520722866190770e-02) < 1e-13
+
+
+def test_rys_roots_vs_mpmath():
+    # golden from the reference's scripts/rys_roots.py (mpmath, 60 digits); reference tolerance in
+    # testsuite/test_rys_roots.py:87-121 is 1e-3/1e-7, we demand 1e-13
+    tab = np.load(os.path.join(GOLD, "rys_mpmath.npz"))["table"]
+    lib = ou.port()
+    for row in tab:
+        n, x = int(row[0]), row[1]
+        t2 = np.zeros(n)
+        w = np.zeros(n)
+        assert lib.oracle_rys_t2w(n, ctypes.c_double(x), ou._p(t2), ou._p(w)) == 0
+        assert np.abs(t2 - row[2:2 + n]).max() < 1e-13, (n, x)
+        assert np.abs(w - row[13:13 + n]).max() < 1e-13 * max(1.0, w.max()), (n, x)
+
+
+def test_c2s_fingerprint():
+    # dense matrices agree with first principles: rows orthonormal under the Cartesian Gaussian metric
+    # is checked indirectly by the known answers; here check d-shell literals (src/cart2sph.c:52-86)
+    m = np.zeros((5, 6))
+    assert ou.port().oracle_c2s_matrix(2, ou._p(m)) == 0
+    assert abs(m[0, 1] - 1.092548430592079070) < 1e-15      # xy
+    assert abs(m[2, 5] - 0.630783130505040012) < 1e-15      # z^2 coefficient of 3z^2-r^2
+    assert abs(m[4, 0] - 0.546274215296039535) < 1e-15      # x^2 of x^2-y^2
+
+
+@pytest.mark.skipif(ou.ref() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_port_vs_reference_elementwise():
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    rng = np.random.default_rng(5)
+    worst = 0
+    for _ in range(300):
+        s = tuple(int(x) for x in rng.integers(0, 8, 4))
+        a, ra = ou.eval_tuple("port", "int2e_sph", s, atm, bas, env)
+        b, rb = ou.eval_tuple("ref", "int2e_sph", s, atm, bas, env)
+        assert ra == rb
+        worst = max(worst, np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+    assert worst < 1e-12
+    # dims embedding (src/cint2e.c:853-856)
+    s = (1, 5, 2, 0)
+    d = ou.dims_of(bas, s)
+    dims = [d[0] + 2, d[1] + 1, d[2] + 3, d[3] + 1]
+    a, _ = ou.eval_tuple("port", "int2e_sph", s, atm, bas, env, dims=dims)
+    b, _ = ou.eval_tuple("ref", "int2e_sph", s, atm, bas, env, dims=dims)
+    assert np.abs(a - b).max() < 1e-12
+
+
+@pytest.mark.skipif(ou.ref() is None, reason="oracle/_ref not built")
+def test_port_sr_lr_vs_reference():
+    atm, bas, env = reference_test_basis()
+    for om in (0.3, -0.3):
+        e = env.copy()
+        e[8] = om
+        for s in [(0, 1, 2, 3), (4, 4, 4, 4), (5, 1, 6, 2), (7, 0, 3, 4), (3, 3, 3, 3)]:
+            a, _ = ou.eval_tuple("port", "int2e_sph", s, atm, bas, e)
+            b, _ = ou.eval_tuple("ref", "int2e_sph", s, atm, bas, e)
+            tol = 1e-12 if om > 0 else 1e-10      # README.rst:219-223: SR accuracy of the reference ~1e-10
+            assert np.abs(a - b).max() <= tol * max(1.0, np.abs(b).max()), (om, s)

@@ -47,6 +47,13 @@ def load_library():
     if hasattr(lib, "cintb200_int2e_sph_all_unique"):
         lib.cintb200_int2e_sph_all_unique.argtypes = [vp, ci, ci, sz, vp, vp]
         lib.cintb200_int2e_sph_all_unique.restype = ci
+    if hasattr(lib, "cintb200_debug_chunk"):
+        lib.cintb200_debug_chunk.argtypes = [vp, ci, vp, sz, vp]
+        lib.cintb200_debug_chunk.restype = ci
+        lib.cintb200_debug_pair_offsets.argtypes = [vp, ci, ci, vp, vp]
+        lib.cintb200_debug_pair_offsets.restype = ci
+        lib.cintb200_debug_force_generic.argtypes = [vp, ci]
+        lib.cintb200_debug_force_generic.restype = None
     for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
@@ -140,6 +147,32 @@ class Context:
         if rc < 0:
             raise B200Error("all_unique failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return stats
+
+
+    # ---- verification helpers (tests only) ----
+    def force_generic(self, on=True):
+        self.lib.cintb200_debug_force_generic(self.handle, int(on))
+
+    def chunk(self, k):
+        """Tile of chunk k after all_unique(): (values[ld, ncols] F-order, geometry dict)."""
+        geom = np.zeros(8, dtype=np.int64)
+        rc = self.lib.cintb200_debug_chunk(self.handle, k, None, 0, _p(geom))
+        if rc < 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        ld, ncols = int(geom[3]), int(geom[4])
+        out = np.zeros(ld * ncols)
+        rc = self.lib.cintb200_debug_chunk(self.handle, k, _p(out), out.size, _p(geom))
+        if rc < 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        return out.reshape((ld, ncols), order="F"), dict(i0=int(geom[0]), i1=int(geom[1]), row0=int(geom[2]),
+                                                         ld=ld, ncols=ncols, nchunks=int(geom[5]))
+
+    def pair_offsets(self, i, j):
+        """(global row offset, this rank's column offset or -1) of the block of shell pair (i, j), i >= j."""
+        r = ctypes.c_longlong()
+        c = ctypes.c_longlong()
+        self.lib.cintb200_debug_pair_offsets(self.handle, i, j, ctypes.byref(r), ctypes.byref(c))
+        return r.value, c.value
 
 
 def _call_single(name, ncenter, shls, atm, bas, env, opt=None, dims=None, out=None, cart=False):

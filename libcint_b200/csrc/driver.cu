@@ -1,0 +1,450 @@
+// Whole-job / tile driver: evaluates every unique shell quartet of the reference benchmark loop
+// (examples/time_c60.c:200-219: i>=j, k>=l, k<=i) class by class into column-major tiles
+//     out[row(ij) + ld * col(kl)],  row/col blocks laid out like the reference's per-quartet `buf`.
+//
+// Host-side work done once per (context, rank, nranks, chunk size) and cached as a JobPlan:
+//   * shell pairs grouped into pair classes (la, lb, nca, ncb, padded primitive count Q), each list
+//     sorted by the larger shell index so that "k <= i" is a prefix/suffix of a list;
+//   * structure-of-arrays primitive tables per class (coalesced per-thread loads in kern_reg.cuh);
+//   * row numbering (all pairs, enumeration order) and this rank's column numbering (kets are dealt
+//     round-robin inside every class list: static sharding, no communication);
+//   * chunks = ranges of the bra shell index i whose tile fits the device buffer.
+// Per chunk and (T class, U class) one kernel launch: the register kernel if the class has one,
+// else the generic block-per-quartet kernel in tile mode.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/cint_b200.h"
+#include "types.h"
+#include "kernels.h"
+#include "engine.h"
+
+int rys_tab_off(int nroots);
+extern const int *engine_c2s_off();
+
+#define CU_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return b200_fail(CINTB200_ENODEV, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+struct PairClass {
+    int la, lb, nca, ncb, Q;
+    std::vector<int> ids, I, npp;
+    std::vector<long long> npp_prefix;      // prefix sums of npp over the list
+    double *d_tprim = nullptr, *d_tgeom = nullptr;
+    long long *d_trow = nullptr, *d_ucol = nullptr;
+    int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr;
+};
+
+struct LaunchRec;
+struct JobPlan {
+    int rank = 0, nranks = 1;
+    size_t chunk_bytes = 0;
+    std::vector<PairClass> classes;
+    std::vector<long long> rowoff;          // per pair id
+    std::vector<long long> rows_before;     // [nbas+1] rows of pairs with I < i
+    std::vector<long long> cols_before;     // [nbas+1] this rank's columns of kets with K < i
+    std::vector<std::pair<int, int>> chunks;
+    double *d_out[2] = {nullptr, nullptr};
+    size_t out_doubles = 0;
+    long long *d_uprefix = nullptr; size_t cap_uprefix = 0;
+    double *d_scratch = nullptr; size_t cap_scratch = 0;
+    int force_generic = 0;
+    std::vector<long long> colof;           // per pair id: this rank's column offset or -1
+    std::vector<struct LaunchRec> launches;
+    double st_quartets = 0, st_integrals = 0, st_prim = 0, st_flops = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
+};
+
+void jobplan_free(JobPlan *p)
+{
+    if (!p) return;
+    for (PairClass &c : p->classes) {
+        cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
+        cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride);
+    }
+    cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch);
+    if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (int b = 0; b < 2; b++) {
+        if (p->ev_done[b]) cudaEventDestroy(p->ev_done[b]);
+        if (p->ev_copied[b]) cudaEventDestroy(p->ev_copied[b]);
+    }
+    if (p->ev_t0) cudaEventDestroy(p->ev_t0);
+    if (p->ev_t1) cudaEventDestroy(p->ev_t1);
+    delete p;
+}
+
+static int bucket_q(int npp)
+{
+    static const int b[] = {1, 2, 3, 4, 6, 8, 9, 12, 16, 24, 32, 48, 64};
+    for (int v : b) if (npp <= v) return v;
+    return (npp + 15) / 16 * 16;
+}
+
+template <class T>
+static int upload(T **dst, const std::vector<T> &src)
+{
+    if (cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(1, src.size())) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", sizeof(T) * src.size());
+    if (!src.empty() && cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        return b200_fail(CINTB200_ENODEV, "upload failed");
+    return 0;
+}
+
+// algorithmic FLOPs per executed primitive quartet / per contracted quartet
+static void model_flops(int li, int lj, int lk, int ll, int nc, double *per_prim, double *per_quartet)
+{
+    const int nmax = li + lj, mmax = lk + ll, n = (nmax + mmax) / 2 + 1;
+    const double nf = (double)B200_NCART(li) * B200_NCART(lj) * B200_NCART(lk) * B200_NCART(ll);
+    double V = 0;
+    if (nmax > 0) V += 1 + 4 * (nmax - 1);
+    if (mmax > 0) V += 1 + 4 * (mmax - 1);
+    if (nmax > 0 && mmax > 0) V += 3 + 6 * (mmax - 1);
+    V += 7.0 * mmax * std::max(nmax - 1, 0);
+    double H = 0;
+    const int mnij = std::min(li, lj), mxij = std::max(li, lj), mnkl = std::min(lk, ll);
+    for (int a = 1; a <= mnij; a++) H += (nmax - a + 1) * (mmax + 1);
+    for (int c = 1; c <= mnkl; c++) H += (mmax - c + 1) * (mnij + 1) * (mxij + 1);
+    *per_prim = 40 + 58.0 * n + 23.0 * n + 3.0 * n * V + 6.0 * n * H + 3.0 * n * nf + 2.0 * nf * std::min(nc, 2);
+    *per_quartet = 4.0 * nf * nc;
+}
+
+static int build_plan(CINTOpt *c, JobPlan *plan)
+{
+    const int nbas = c->nbas;
+    const size_t npair = (size_t)nbas * (nbas + 1) / 2;
+    std::map<std::vector<int>, int> key2class;
+    std::vector<int> cls_of(npair), idx_in_cls(npair);
+    plan->rowoff.resize(npair);
+    plan->rows_before.assign(nbas + 1, 0);
+    plan->cols_before.assign(nbas + 1, 0);
+    long long rows = 0;
+    for (int i = 0; i < nbas; i++) {
+        plan->rows_before[i] = rows;
+        for (int j = 0; j <= i; j++) {
+            const size_t p = (size_t)i * (i + 1) / 2 + j;
+            const PairHdr &h = c->pairs[p];
+            const int q = bucket_q(std::max(1, h.npp));
+            std::vector<int> key = {h.la, h.lb, h.nca, h.ncb, q};
+            auto it = key2class.find(key);
+            int ci;
+            if (it == key2class.end()) {
+                ci = (int)plan->classes.size();
+                key2class[key] = ci;
+                PairClass pc;
+                pc.la = h.la; pc.lb = h.lb; pc.nca = h.nca; pc.ncb = h.ncb; pc.Q = q;
+                plan->classes.push_back(pc);
+            } else ci = it->second;
+            PairClass &pc = plan->classes[ci];
+            cls_of[p] = ci;
+            idx_in_cls[p] = (int)pc.ids.size();
+            pc.ids.push_back((int)p);
+            pc.I.push_back(i);
+            pc.npp.push_back(h.npp);
+            plan->rowoff[p] = rows;
+            const ShellInfo &si = c->shells[i], &sj = c->shells[j];
+            rows += (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
+        }
+    }
+    plan->rows_before[nbas] = rows;
+    // this rank's column numbering: kets dealt round-robin inside each class list
+    std::vector<long long> &colof = plan->colof;
+    colof.assign(npair, -1);
+    long long cols = 0;
+    for (int i = 0; i < nbas; i++) {
+        plan->cols_before[i] = cols;
+        for (int j = 0; j <= i; j++) {
+            const size_t p = (size_t)i * (i + 1) / 2 + j;
+            if (idx_in_cls[p] % plan->nranks != plan->rank) continue;
+            colof[p] = cols;
+            const ShellInfo &si = c->shells[i], &sj = c->shells[j];
+            cols += (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
+        }
+    }
+    plan->cols_before[nbas] = cols;
+
+    for (PairClass &pc : plan->classes) {
+        const size_t NT = pc.ids.size();
+        const int nct = pc.nca * pc.ncb, Q = pc.Q;
+        std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
+        std::vector<long long> trow(NT), ucol(NT);
+        std::vector<int> tstride(2 * NT), ustride(2 * NT);
+        pc.npp_prefix.assign(NT + 1, 0);
+        for (size_t n = 0; n < NT; n++) {
+            const int p = pc.ids[n];
+            const PairHdr &h = c->pairs[p];
+            pc.npp_prefix[n + 1] = pc.npp_prefix[n] + h.npp;
+            for (int d = 0; d < 3; d++) { tgeom[d * NT + n] = h.ra[d]; tgeom[(3 + d) * NT + n] = h.ab[d]; }
+            for (int q = 0; q < Q; q++) {
+                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
+                if (q < h.npp) {
+                    const PrimPair &pp = c->prims[h.pp_off + q];
+                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
+                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
+                    tprim[5 * F + o] = pp.kij;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
+                } else {            // zero-weight padding primitive
+                    tprim[o] = 1.0; tprim[F + o] = 1.0;
+                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
+                    tprim[5 * F + o] = 0.0;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+                }
+            }
+            // strides of the canonical indices inside the (i,j) block: i fastest
+            const int i = pc.I[n];
+            const int j = (h.sh_a == i) ? h.sh_b : h.sh_a;
+            const ShellInfo &si = c->shells[i];
+            const int di = (2 * si.l + 1) * si.nctr;
+            const bool a_is_i = (h.sh_a == i);
+            (void)j;
+            tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
+            ustride[n] = a_is_i ? 1 : di;  ustride[NT + n] = a_is_i ? di : 1;
+            trow[n] = plan->rowoff[p];
+            ucol[n] = colof[p];
+        }
+        if (upload(&pc.d_tprim, tprim) || upload(&pc.d_tgeom, tgeom) || upload(&pc.d_trow, trow) || upload(&pc.d_ucol, ucol) ||
+            upload(&pc.d_tstride, tstride) || upload(&pc.d_ustride, ustride) || upload(&pc.d_tI, pc.I) || upload(&pc.d_tpair, pc.ids))
+            return CINTB200_ENOMEM;
+    }
+    // chunks: ranges of i with rows(i0..i1) * cols(K < i1) * 8 <= chunk_bytes
+    const size_t cap = plan->chunk_bytes / sizeof(double);
+    int i0 = 0;
+    size_t need = 1;
+    while (i0 < nbas) {
+        int i1 = i0 + 1;
+        while (i1 < nbas) {
+            size_t r = (size_t)(plan->rows_before[i1 + 1] - plan->rows_before[i0]);
+            size_t cc = (size_t)plan->cols_before[i1 + 1];
+            if (r * cc > cap) break;
+            i1++;
+        }
+        size_t r = (size_t)(plan->rows_before[i1] - plan->rows_before[i0]);
+        size_t cc = (size_t)plan->cols_before[i1];
+        need = std::max(need, r * std::max<size_t>(cc, 1));
+        plan->chunks.push_back({i0, i1});
+        i0 = i1;
+    }
+    plan->out_doubles = need;
+    for (int b = 0; b < 2; b++)
+        if (cudaMalloc((void **)&plan->d_out[b], sizeof(double) * need) != cudaSuccess)
+            return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
+    CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_done[b], cudaEventDisableTiming));
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_copied[b], cudaEventDisableTiming));
+    }
+    CU_OK(cudaEventCreate(&plan->ev_t0));
+    CU_OK(cudaEventCreate(&plan->ev_t1));
+    return 0;
+}
+
+struct LaunchRec {
+    int chunk;
+    TileParams P;               // out / row0 / ld filled per run (buffer alternates)
+    RegKernelFn fn;             // nullptr -> generic kernel
+    int nroots, ncu, gx, gy;
+    GenericClass GC; GenericLaunch GL;
+    long long ntasks;           // generic: number of quartets
+    size_t uprefix_off;         // generic: offset into plan->d_uprefix
+};
+
+static int build_launches(CINTOpt *c, JobPlan *plan)
+{
+    const int rank = plan->rank, nranks = plan->nranks, nbas = c->nbas;
+    std::vector<long long> uprefix_all;
+    size_t scratch_need = 0;
+    plan->st_quartets = plan->st_integrals = plan->st_prim = plan->st_flops = 0;
+    // first T index with I >= k, per class
+    std::vector<std::vector<int>> first_t(plan->classes.size(), std::vector<int>(nbas + 1));
+    for (size_t ci = 0; ci < plan->classes.size(); ci++) {
+        const PairClass &T = plan->classes[ci];
+        for (int k = 0; k <= nbas; k++) first_t[ci][k] = (int)(std::lower_bound(T.I.begin(), T.I.end(), k) - T.I.begin());
+    }
+    for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
+        const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
+        const long long row0 = plan->rows_before[i0];
+        const long long ld = plan->rows_before[i1] - row0;
+        if (ld == 0 || plan->cols_before[i1] == 0) continue;
+        for (size_t ct = 0; ct < plan->classes.size(); ct++) {
+            PairClass &T = plan->classes[ct];
+            const int t_begin = first_t[ct][i0], t_end = first_t[ct][i1];
+            if (t_end <= t_begin) continue;
+            for (size_t cu = 0; cu < plan->classes.size(); cu++) {
+                PairClass &U = plan->classes[cu];
+                const int nu_valid = first_t[cu][i1];
+                if (nu_valid <= rank) continue;
+                const int nu_mine = (nu_valid - rank + nranks - 1) / nranks;
+                LaunchRec L;
+                memset(&L, 0, sizeof L);
+                TileParams &P = L.P;
+                P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
+                P.tI = T.d_tI; P.tpair = T.d_tpair;
+                P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
+                P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
+                P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = rank; P.nca_u = U.nca;
+                P.tri = 1;
+                P.row0 = row0; P.ld = ld;
+                P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
+                L.chunk = (int)ch;
+                L.nroots = (T.la + T.lb + U.la + U.lb) / 2 + 1;
+                L.ncu = U.nca * U.ncb;
+                P.rys = c->d_rys + rys_tab_off(L.nroots);
+                std::vector<long long> uprefix(nu_mine + 1, 0);
+                double prim_here = 0;
+                for (int j = 0; j < nu_mine; j++) {
+                    const int u = rank + nranks * j;
+                    const int tl = std::max(t_begin, std::min(t_end, first_t[ct][U.I[u]]));
+                    uprefix[j + 1] = uprefix[j] + (t_end - tl);
+                    prim_here += (double)U.npp[u] * (double)(T.npp_prefix[t_end] - T.npp_prefix[tl]);
+                }
+                const double q_here = (double)uprefix[nu_mine];
+                if (q_here == 0) continue;
+                const double blk = (double)(2 * T.la + 1) * (2 * T.lb + 1) * T.nca * T.ncb * (2 * U.la + 1) * (2 * U.lb + 1) * U.nca * U.ncb;
+                double fp, fq;
+                model_flops(T.la, T.lb, U.la, U.lb, T.nca * T.ncb * U.nca * U.ncb, &fp, &fq);
+                plan->st_quartets += q_here; plan->st_integrals += q_here * blk; plan->st_prim += prim_here;
+                plan->st_flops += prim_here * fp + q_here * fq;
+                L.ntasks = uprefix[nu_mine];
+                L.fn = c->force_generic ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
+                if (L.fn) {
+                    L.gx = (t_end - t_begin + 127) / 128;
+                    for (int y0 = 0; y0 < nu_mine; y0 += 65535) {
+                        LaunchRec L2 = L;
+                        L2.P.u_first = rank + nranks * y0;
+                        L2.gy = std::min(65535, nu_mine - y0);
+                        plan->launches.push_back(L2);
+                    }
+                } else {
+                    if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off()))
+                        return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits", T.la, T.lb, U.la, U.lb);
+                    scratch_need = std::max(scratch_need, L.GC.scratch_per_block * (size_t)L.GL.grid);
+                    L.uprefix_off = uprefix_all.size();
+                    uprefix_all.insert(uprefix_all.end(), uprefix.begin(), uprefix.end());
+                    plan->launches.push_back(L);
+                }
+            }
+        }
+    }
+    if (upload(&plan->d_uprefix, uprefix_all)) return CINTB200_ENOMEM;
+    if (scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cannot allocate generic-kernel scratch");
+    return 0;
+}
+
+extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes,
+                                             double *host_sink, double *stats)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (c->omega < 0) return b200_fail(CINTB200_ENOSUP, "short-range Coulomb not implemented in this build");
+    std::lock_guard<std::mutex> lock(c->mtx);
+    CU_OK(cudaSetDevice(c->device));
+    if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
+    JobPlan *plan = c->plan;
+    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic) {
+        if (plan) { cudaDeviceSynchronize(); jobplan_free(plan); c->plan = nullptr; }
+        plan = new JobPlan();
+        plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic;
+        int rc = build_plan(c, plan);
+        if (!rc) rc = build_launches(c, plan);
+        if (rc) { jobplan_free(plan); return rc; }
+        c->plan = plan;
+    }
+    EngineParams EP;
+    EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
+    EP.expcutoff = c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
+
+    double d2h = 0;
+    long long nlaunch = 0, reg_launches = 0;
+    cudaStream_t st = c->stream;
+    CU_OK(cudaEventRecord(plan->ev_t0, st));
+    int buf = 0, cur_chunk = -1;
+    auto finish_chunk = [&](int ch, int b) -> int {
+        CU_OK(cudaEventRecord(plan->ev_done[b], st));
+        if (host_sink) {
+            const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
+            const size_t bytes = sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->cols_before[i1];
+            CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_done[b], 0));
+            CU_OK(cudaMemcpyAsync(host_sink, plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
+            CU_OK(cudaEventRecord(plan->ev_copied[b], plan->copy_stream));
+            d2h += (double)bytes;
+        }
+        return 0;
+    };
+    for (LaunchRec &L : plan->launches) {
+        if (L.chunk != cur_chunk) {
+            if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; buf ^= 1; }
+            cur_chunk = L.chunk;
+            if (host_sink) CU_OK(cudaStreamWaitEvent(st, plan->ev_copied[buf], 0));   // buffer drained?
+        }
+        L.P.out = plan->d_out[buf];
+        if (L.fn) {
+            if (reg_kernel_launch(L.fn, L.nroots, L.ncu, L.P, L.gx, L.gy, st))
+                return b200_fail(CINTB200_ENODEV, "register kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            reg_launches++;
+        } else {
+            L.GC.scratch = plan->d_scratch;
+            if (generic_launch(EP, L.GC, L.GL, nullptr, L.ntasks, plan->d_out[buf], nullptr, nullptr, st, &L.P, plan->d_uprefix + L.uprefix_off))
+                return b200_fail(CINTB200_ENODEV, "generic kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        nlaunch++;
+    }
+    if (cur_chunk >= 0 && finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV;
+    CU_OK(cudaEventRecord(plan->ev_t1, st));
+    CU_OK(cudaStreamSynchronize(st));
+    if (host_sink) CU_OK(cudaStreamSynchronize(plan->copy_stream));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return b200_fail(CINTB200_ENODEV, "kernel execution failed: %s", cudaGetErrorString(le));
+    float ms = 0;
+    CU_OK(cudaEventElapsedTime(&ms, plan->ev_t0, plan->ev_t1));
+    if (stats) {
+        stats[0] = plan->st_quartets; stats[1] = plan->st_integrals; stats[2] = plan->st_prim; stats[3] = 0;
+        stats[4] = (double)nlaunch; stats[5] = d2h; stats[6] = plan->st_flops; stats[7] = ms;
+        stats[8] = (double)reg_launches; stats[9] = (double)plan->chunks.size();
+        stats[10] = (double)plan->out_doubles * 8; stats[11] = (double)plan->classes.size();
+    }
+    c->launches += nlaunch;
+    return 0;
+}
+
+// Copy a rectangle of the most recent tile of chunk `chunk` ... (verification helper for tests):
+// evaluates ONE chunk and returns it on the host together with its geometry.
+extern "C" int cintb200_debug_chunk(cintb200_ctx *c, int chunk, double *host_out, size_t host_cap, long long *geom)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan) return b200_fail(CINTB200_EINVAL, "run cintb200_int2e_sph_all_unique first");
+    JobPlan *plan = c->plan;
+    if (chunk < 0 || chunk >= (int)plan->chunks.size()) return b200_fail(CINTB200_EINVAL, "chunk out of range");
+    const int i0 = plan->chunks[chunk].first, i1 = plan->chunks[chunk].second;
+    geom[0] = i0; geom[1] = i1;
+    geom[2] = plan->rows_before[i0]; geom[3] = plan->rows_before[i1] - plan->rows_before[i0];
+    geom[4] = plan->cols_before[i1];
+    geom[5] = (long long)plan->chunks.size();
+    const size_t n = (size_t)geom[3] * (size_t)geom[4];
+    if (!host_out) return 0;
+    if (n > host_cap) return b200_fail(CINTB200_EINVAL, "host buffer too small");
+    // chunks alternate between the two buffers in evaluation order
+    int buf = 0;
+    for (int k = 0; k < chunk; k++) {
+        const long long ld = plan->rows_before[plan->chunks[k].second] - plan->rows_before[plan->chunks[k].first];
+        if (ld == 0 || plan->cols_before[plan->chunks[k].second] == 0) continue;
+        buf ^= 1;
+    }
+    CU_OK(cudaSetDevice(c->device));
+    CU_OK(cudaMemcpy(host_out, plan->d_out[buf], sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// column offset (this rank's numbering) and row offset of a pair, for tests
+extern "C" int cintb200_debug_pair_offsets(cintb200_ctx *c, int i, int j, long long *row, long long *col_owner_rank)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan) return b200_fail(CINTB200_EINVAL, "no plan");
+    JobPlan *plan = c->plan;
+    if (i < j) std::swap(i, j);
+    const int p = i * (i + 1) / 2 + j;
+    *row = plan->rowoff[p];
+    *col_owner_rank = plan->colof[p];       // -1: another rank owns this ket
+    return 0;
+}

@@ -308,6 +308,7 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_c2s);
     cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_nonzero); cudaFree(c->d_scratch); cudaFree(c->d_counters);
+    if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->magic = 0;
@@ -569,10 +570,8 @@ void CINTdel_2e_optimizer(CINTOpt **opt)
 void CINTdel_optimizer(CINTOpt **opt) { CINTdel_2e_optimizer(opt); }
 }
 
-// placeholder until driver.cu lands
-extern "C" __attribute__((weak)) int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
-                                             double *host_sink, double *stats)
-{
-    (void)ctx; (void)rank; (void)nranks; (void)chunk_bytes; (void)host_sink; (void)stats;
-    return b200_fail(CINTB200_ENOSUP, "whole-job driver not built");
-}
+const int *engine_c2s_off() { return C2S_OFF; }
+extern "C" void cintb200_debug_force_generic(cintb200_ctx *c, int on) { if (c && c->magic == B200_CTX_MAGIC) c->force_generic = on; }
+
+int rys_tab_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_NINT[nroots] : 0; }
+int rys_tab_off(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_OFF[nroots] : 0; }

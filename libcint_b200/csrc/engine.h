@@ -39,8 +39,12 @@ struct CINTOpt {
     void *h_stage = nullptr;        size_t cap_stage = 0;
     unsigned long long *d_counters = nullptr;
     long long launches = 0;
+    struct JobPlan *plan = nullptr;     // cached whole-job plan (driver.cu)
+    int force_generic = 0;              // tests: route every class through the generic kernel
     std::mutex mtx;
 };
 
+struct JobPlan;
+void jobplan_free(JobPlan *p);
 int b200_fail(int code, const char *fmt, ...);
 int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_host);

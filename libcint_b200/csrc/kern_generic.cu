@@ -80,8 +80,38 @@ __device__ void c2s_index(const double *in, double *out, int pre, int post, int 
     }
 }
 
+// tile mode: work item w -> (u, t) through the prefix array of valid T counts per U pair
+__device__ __forceinline__ Task tile_task(const TileParams &T, const long long *__restrict__ uprefix, long long w)
+{
+    int lo = 0, hi = T.NU;                       // last j with uprefix[j] <= w
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (uprefix[mid] <= w) lo = mid; else hi = mid;
+    }
+    const int j = lo;
+    const int u = T.u_first + T.u_step * j;
+    int t_lo = T.t_begin;
+    if (T.tri) {
+        int a = T.t_begin, b = T.t_end;
+        const int K = T.uK[u];
+        while (a < b) { int mid = (a + b) >> 1; if (T.tI[mid] < K) a = mid + 1; else b = mid; }
+        t_lo = a;
+    }
+    const int t = t_lo + (int)(w - uprefix[j]);
+    Task k;
+    k.bra = T.tpair[t];
+    k.ket = T.upair[u];
+    k.sa = T.tstride[t];
+    k.sb = T.tstride[T.NT + t];
+    k.sc = (long long)T.ustride[u] * T.ld;
+    k.sd = (long long)T.ustride[T.NU_all + u] * T.ld;
+    k.off = (T.trow[t] - T.row0) + T.ucol[u] * T.ld;
+    return k;
+}
+
 __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
-                                   double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters)
+                                   double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters,
+                                   TileParams TP, const long long *__restrict__ uprefix)
 {
     extern __shared__ double sm[];
     const int tid = threadIdx.x;
@@ -121,7 +151,7 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
         * (la < 2 ? fsp[la] : 1.0) * (lb < 2 ? fsp[lb] : 1.0) * (lc < 2 ? fsp[lc] : 1.0) * (ld < 2 ? fsp[ld] : 1.0);
 
     for (long long t = blockIdx.x; t < ntasks; t += gridDim.x) {
-        const Task task = tasks[t];
+        const Task task = tasks ? tasks[t] : tile_task(TP, uprefix, t);
         const PairHdr hb = P.pairs[task.bra];
         const PairHdr hk = P.pairs[task.ket];
         __syncthreads();
@@ -341,13 +371,17 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
 }
 
 int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLaunch &L, const Task *tasks,
-                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream)
+                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream,
+                   const TileParams *tile, const long long *uprefix)
 {
+    TileParams TP;
+    memset(&TP, 0, sizeof TP);
+    if (tile) TP = *tile;
     if (ntasks <= 0) return 0;
     if (L.smem > 48 * 1024) {
         if (cudaFuncSetAttribute(eri_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem) != cudaSuccess)
             return -1;
     }
-    eri_generic_kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters);
+    eri_generic_kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters, TP, uprefix);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

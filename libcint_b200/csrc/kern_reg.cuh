@@ -1,0 +1,439 @@
+// Register-resident ERI kernel: ONE THREAD PER SHELL QUARTET, fully specialised at compile time on
+// the angular class (LA LB | LC LD) and on the number of contraction combinations of each pair.
+//
+// Used by the whole-job / tile driver (driver.cu) for every class whose [e0|f0] block fits the
+// register file.  Geometry of a launch ("tile"):
+//   T side = bra pairs (ab|, one per THREAD, consecutive threads = consecutive pairs of one pair
+//            class, primitive data read from a structure-of-arrays table -> fully coalesced loads;
+//   U side = ket pair |cd), UNIFORM per block (blockIdx.y), primitive data staged once in smem and
+//            read back as broadcasts.
+// so the primitive loops have block-uniform trip counts (T pairs are padded to the class maximum
+// with zero-weight primitives) and there is no divergence.  Output goes to a column-major tile
+// out[row(ab) + ld * col(cd)] -- consecutive threads write consecutive rows.
+//
+// Reference stages replaced (same math, different order of operations):
+//   CINT2e_loop (src/cint2e.c:660-758)   -> the two primitive loops below (pair-level screening only:
+//                                           the quartet-level test would drop 3% more primitives, all < e^-60)
+//   CINTrys_roots (src/rys_roots.c:57)   -> rys_roots_t2w<N> from the smem-staged table
+//   CINTg0_2e (src/g2e.c:4518-4540)      -> b00/b10/b01/c00/c0p written in t^2, no division
+//   CINTg0_2e_2d (src/g2e.c:272-421)     -> register VRR, unrolled
+//   CINTg0_*2d_4d + CINTgout2e           -> [e0|f0] accumulation per root, HRR once per contracted quartet
+//   CINTprim_to_ctr_0/1 (src/g1e.c:530)  -> coefficient products from the pair table
+//   c2s_sph_2e1 (src/cart2sph.c:5324)    -> constexpr sparse transforms + direct strided store
+#pragma once
+#include <utility>
+#include <type_traits>
+#include "types.h"
+#include "rys.cuh"
+#include "c2s_constexpr.inc"
+
+// ----------------------------------------------------------------------------- compile-time helpers
+template <class F, int... I>
+__device__ __forceinline__ void static_for_impl(F &&f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    static_for_impl(static_cast<F &&>(f), std::make_integer_sequence<int, N>{});
+}
+
+__host__ __device__ constexpr int cx_ncart(int l) { return (l + 1) * (l + 2) / 2; }
+__host__ __device__ constexpr int cx_lx(int l, int idx)
+{
+    int n = 0;
+    for (int lx = l; lx >= 0; lx--)
+        for (int ly = l - lx; ly >= 0; ly--, n++)
+            if (n == idx) return lx;
+    return -1;
+}
+__host__ __device__ constexpr int cx_ly(int l, int idx)
+{
+    int n = 0;
+    for (int lx = l; lx >= 0; lx--)
+        for (int ly = l - lx; ly >= 0; ly--, n++)
+            if (n == idx) return ly;
+    return -1;
+}
+__host__ __device__ constexpr int cx_lz(int l, int idx) { return l - cx_lx(l, idx) - cx_ly(l, idx); }
+__host__ __device__ constexpr int cx_idx(int l, int lx, int lz) { return (l - lx) * (l - lx + 1) / 2 + lz; }
+// number of components of degrees l0..l1
+__host__ __device__ constexpr int cx_nrange(int l0, int l1)
+{
+    int s = 0;
+    for (int l = l0; l <= l1; l++) s += cx_ncart(l);
+    return s;
+}
+// degree / sub-index of component e of the range starting at l0
+__host__ __device__ constexpr int cx_range_l(int l0, int e)
+{
+    int l = l0;
+    while (e >= cx_ncart(l)) { e -= cx_ncart(l); l++; }
+    return l;
+}
+__host__ __device__ constexpr int cx_range_i(int l0, int e)
+{
+    int l = l0;
+    while (e >= cx_ncart(l)) { e -= cx_ncart(l); l++; }
+    return e;
+}
+// size of HRR level J: sum_{le=L0}^{L0+LB-J} ncart(le)*ncart(J)
+__host__ __device__ constexpr int cx_hrr_size(int l0, int lb, int j)
+{
+    int s = 0;
+    for (int le = l0; le <= l0 + lb - j; le++) s += cx_ncart(le) * cx_ncart(j);
+    return s;
+}
+__host__ __device__ constexpr int cx_hrr_off(int l0, int le, int j)   // offset of block le inside level j
+{
+    int s = 0;
+    for (int l = l0; l < le; l++) s += cx_ncart(l) * cx_ncart(j);
+    return s;
+}
+
+
+#define REG_THREADS 128
+#define REG_MAXU 64            // most primitive pairs of a U pair (8 x 8)
+
+// row stride (doubles) of the smem copy of the Rys table: odd, so rows fall on distinct 8-byte bank pairs
+__host__ __device__ constexpr int rys_smem_stride(int n) { return (RYS_DEG + 1) * 2 * n + 1; }
+
+template <int N>
+__device__ __forceinline__ void rys_roots_smem(const double *tab, double x, double (&t2)[N], double (&w)[N])
+{
+    if (x >= 35.0 + 5.0 * N) {
+        const double ix = 1.0 / x;
+        const double isx = sqrt(ix);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            t2[k] = c_rys_lx_r[N * (N - 1) / 2 + k] * ix;
+            w[k] = c_rys_lx_v[N * (N - 1) / 2 + k] * isx;
+        }
+        return;
+    }
+    int idx;
+    double y;
+    rys_locate(x, idx, y);
+    const double *c = tab + idx * rys_smem_stride(N);
+    double v[2 * N];
+#pragma unroll
+    for (int p = 0; p < 2 * N; p++) v[p] = c[RYS_DEG * 2 * N + p];
+#pragma unroll
+    for (int j = RYS_DEG - 1; j >= 0; j--) {
+#pragma unroll
+        for (int p = 0; p < 2 * N; p++) v[p] = fma(v[p], y, c[j * 2 * N + p]);
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) { t2[k] = v[2 * k]; w[k] = v[2 * k + 1]; }
+}
+
+// ----------------------------------------------------------------------------- HRR in registers
+// in : level J-1, layout [PRE][part(J-1)][POST];  out: level J.   (a, b+1_d| = (a+1_d, b| + AB_d (a, b|
+template <int L0, int LB, int J, int PRE, int POST>
+__device__ __forceinline__ void hrr_step_reg(const double *in, double *out, const double (&ab)[3])
+{
+    constexpr int NB_IN = cx_ncart(J - 1), NB_OUT = cx_ncart(J);
+    constexpr int IN_PART = cx_hrr_size(L0, LB, J - 1), OUT_PART = cx_hrr_size(L0, LB, J);
+    static_for<LB - J + 1>([&](auto LEI) {
+        constexpr int le = L0 + decltype(LEI)::value;
+        static_for<cx_ncart(le)>([&](auto IE) {
+            constexpr int ie = decltype(IE)::value;
+            static_for<NB_OUT>([&](auto IB) {
+                constexpr int ib = decltype(IB)::value;
+                constexpr int bx = cx_lx(J, ib), by = cx_ly(J, ib), bz = cx_lz(J, ib);
+                constexpr int d = bx ? 0 : (by ? 1 : 2);
+                constexpr int ibp = cx_idx(J - 1, bx - (d == 0), bz - (d == 2));
+                constexpr int ax = cx_lx(le, ie), az = cx_lz(le, ie);
+                constexpr int iep = cx_idx(le + 1, ax + (d == 0), az + (d == 2));
+                constexpr int o_out = cx_hrr_off(L0, le, J) + ie * NB_OUT + ib;
+                constexpr int o_lo = cx_hrr_off(L0, le, J - 1) + ie * NB_IN + ibp;
+                constexpr int o_hi = cx_hrr_off(L0, le + 1, J - 1) + iep * NB_IN + ibp;
+                static_for<PRE>([&](auto PP) {
+                    constexpr int p = decltype(PP)::value;
+                    static_for<POST>([&](auto QQ) {
+                        constexpr int q = decltype(QQ)::value;
+                        out[(p * OUT_PART + o_out) * POST + q] =
+                            fma(ab[d], in[(p * IN_PART + o_lo) * POST + q], in[(p * IN_PART + o_hi) * POST + q]);
+                    });
+                });
+            });
+        });
+    });
+}
+
+// full HRR of one pair: in [PRE][range L0..L0+LB][POST] -> out [PRE][ncart(L0)][ncart(LB)][POST]
+template <int L0, int LB, int PRE, int POST>
+__device__ __forceinline__ void hrr_pair_reg(const double *in, double *out, const double (&ab)[3])
+{
+    if constexpr (LB == 0) {
+        static_for<PRE * cx_ncart(L0) * POST>([&](auto I) { out[decltype(I)::value] = in[decltype(I)::value]; });
+    } else if constexpr (LB == 1) {
+        hrr_step_reg<L0, LB, 1, PRE, POST>(in, out, ab);
+    } else {
+        static_assert(LB == 2, "register HRR implemented up to LB = 2");
+        double tmp[PRE * cx_hrr_size(L0, LB, 1) * POST];
+        hrr_step_reg<L0, LB, 1, PRE, POST>(in, tmp, ab);
+        hrr_step_reg<L0, LB, 2, PRE, POST>(tmp, out, ab);
+    }
+}
+
+// cart -> real spherical on one index of a register array: in [PRE][ncart(L)][POST] -> out [PRE][2L+1][POST]
+template <int L, int PRE, int POST>
+__device__ __forceinline__ void c2s_reg(const double *in, double *out)
+{
+    static_assert(L <= C2S_CX_LMAX, "constexpr c2s table too small");
+    constexpr int NC = cx_ncart(L), NS = 2 * L + 1;
+    static_for<PRE>([&](auto PP) {
+        constexpr int p = decltype(PP)::value;
+        static_for<NS>([&](auto MM) {
+            constexpr int m = decltype(MM)::value;
+            static_for<POST>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                double s = 0;
+                static_for<NC>([&](auto CC) {
+                    constexpr int c = decltype(CC)::value;
+                    constexpr double coef = c2s_cx(L, m, c);
+                    if constexpr (coef != 0.0) s = fma(coef, in[(p * NC + c) * POST + q], s);
+                });
+                out[(p * NS + m) * POST + q] = s;
+            });
+        });
+    });
+}
+
+template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart(L) : 2 * L + 1; };
+
+// ----------------------------------------------------------------------------- the kernel
+template <int LA, int LB, int LC, int LD, int NCT, int NCU>
+__global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const TileParams P)
+{
+    constexpr int NMAX = LA + LB, MMAX = LC + LD;
+    constexpr int N = (LA + LB + LC + LD) / 2 + 1;
+    constexpr int NE = cx_nrange(LA, LA + LB), NF = cx_nrange(LC, LC + LD), NEF = NE * NF;
+    constexpr int NFA = cx_ncart(LA), NFB = cx_ncart(LB), NFC = cx_ncart(LC), NFD = cx_ncart(LD);
+    constexpr int DA = SphDim<LA>::value, DB = SphDim<LB>::value, DC = SphDim<LC>::value, DD = SphDim<LD>::value;
+    constexpr int USTR = 9 + NCU;      // doubles per staged U primitive
+
+    extern __shared__ double smem[];
+    double *s_rys = smem;                                       // [nint][stride]
+    const int u = P.u_first + P.u_step * blockIdx.y;
+    const int tid = threadIdx.x;
+
+    // --- which T pairs does this block cover? ---
+    const int K = P.uK[u];
+    int t_lo = P.t_begin;
+    if (P.tri) {                       // first T pair with I >= K (lists are sorted by I)
+        int lo = P.t_begin, hi = P.t_end;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+        }
+        t_lo = lo;
+    }
+    const int t0 = t_lo + blockIdx.x * REG_THREADS;
+    if (t0 >= P.t_end) return;          // block-uniform
+    const int t = t0 + tid;
+    const bool active = t < P.t_end;
+    const int tt = active ? t : P.t_end - 1;
+
+    // --- stage the Rys table of N roots and the U pair's primitives ---
+    const int nint = c_rys_meta.nint[N];
+    {
+        constexpr int ROW = (RYS_DEG + 1) * 2 * N;
+        for (int i = tid; i < nint * ROW; i += REG_THREADS) {
+            int r = i / ROW, c = i - r * ROW;
+            s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
+        }
+    }
+    double *s_u = s_rys + nint * rys_smem_stride(N);           // [nppu][USTR]
+    const PairHdr hu = P.pairs[P.upair[u]];
+    for (int i = tid; i < hu.npp; i += REG_THREADS) {
+        const PrimPair pp = P.prims[hu.pp_off + i];
+        double *d = s_u + i * USTR;
+        d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
+        d[5] = pp.px - hu.ra[0]; d[6] = pp.py - hu.ra[1]; d[7] = pp.pz - hu.ra[2];
+        if constexpr (NCU == 1) {
+            d[8] = pp.kij * P.pcoef[hu.cc_off + i];
+            d[9] = 1.0;
+        } else {
+            d[8] = pp.kij;
+            for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
+        }
+    }
+    __syncthreads();
+
+    // --- per-thread (T pair) constants ---
+    const size_t NT = P.NT;
+    double ra[3], abT[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) { ra[d] = P.tgeom[d * NT + tt]; abT[d] = P.tgeom[(3 + d) * NT + tt]; }
+    const double abU[3] = {hu.ab[0], hu.ab[1], hu.ab[2]};
+    constexpr double fsp0 = 0.282094791773878143, fsp1 = 0.488602511902919921;
+    constexpr double common = 34.986836655249725693
+        * (LA == 0 ? fsp0 : LA == 1 ? fsp1 : 1.0) * (LB == 0 ? fsp0 : LB == 1 ? fsp1 : 1.0)
+        * (LC == 0 ? fsp0 : LC == 1 ? fsp1 : 1.0) * (LD == 0 ? fsp0 : LD == 1 ? fsp1 : 1.0);
+
+    constexpr int NACC = NCT * NCU * NEF;
+    double acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+
+    const int nppu = hu.npp;
+    for (int tq = 0; tq < P.Q; tq++) {
+        const size_t o = (size_t)tq * NT + tt;
+        const size_t F = (size_t)P.Q * NT;
+        const double aT = P.tprim[o], iaT = P.tprim[F + o];
+        const double ptx = P.tprim[2 * F + o], pty = P.tprim[3 * F + o], ptz = P.tprim[4 * F + o];
+        double kT = P.tprim[5 * F + o];
+        double ccT[NCT];
+        if constexpr (NCT == 1) { kT *= P.tprim[6 * F + o]; ccT[0] = 1.0; }
+        else {
+#pragma unroll
+            for (int c = 0; c < NCT; c++) ccT[c] = P.tprim[(6 + c) * F + o];
+        }
+        const double pa[3] = {ptx - ra[0], pty - ra[1], ptz - ra[2]};
+        // accumulator of the inner (U) loop; aliases acc when the T side is uncontracted
+        double accu[(NCT == 1) ? 1 : NCU * NEF];
+        if constexpr (NCT > 1) {
+#pragma unroll
+            for (int i = 0; i < NCU * NEF; i++) accu[i] = 0.0;
+        }
+#pragma unroll 1
+        for (int uq = 0; uq < nppu; uq++) {
+            const double *su = s_u + uq * USTR;
+            const double aU = su[0], iaU = su[1];
+            const double asum = aT + aU;
+            const double rs = rsqrt(asum);
+            const double inv = rs * rs;
+            const double pq[3] = {ptx - su[2], pty - su[3], ptz - su[4]};
+            const double qc[3] = {su[5], su[6], su[7]};
+            const double a0 = aT * aU * inv;
+            const double x = a0 * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
+            const double fac = common * kT * su[8] * iaT * iaU * rs;
+            double t2[N], w[N];
+            rys_roots_smem<N>(s_rys, x, t2, w);
+            const double rho_u = aU * inv, rho_t = aT * inv;
+            double val[(NCU == 1) ? 1 : NEF];
+            if constexpr (NCU > 1) {
+#pragma unroll
+                for (int i = 0; i < NEF; i++) val[i] = 0.0;
+            }
+            static_for<N>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                const double s = t2[r];
+                const double su_ = s * rho_u, st_ = s * rho_t;
+                const double b00 = 0.5 * s * inv;
+                const double b10 = (0.5 - 0.5 * su_) * iaT;
+                const double b01 = (0.5 - 0.5 * st_) * iaU;
+                double g[3][NMAX + 1][MMAX + 1];
+                static_for<3>([&](auto DDm) {
+                    constexpr int d = decltype(DDm)::value;
+                    const double c00 = pa[d] - su_ * pq[d];
+                    const double c0p = qc[d] + st_ * pq[d];
+                    g[d][0][0] = (d == 2) ? w[r] * fac : 1.0;
+                    if constexpr (NMAX > 0) g[d][1][0] = c00 * g[d][0][0];
+                    static_for<(NMAX > 1 ? NMAX - 1 : 0)>([&](auto NN) {
+                        constexpr int n = decltype(NN)::value + 1;
+                        g[d][n + 1][0] = fma(c00, g[d][n][0], (n * b10) * g[d][n - 1][0]);
+                    });
+                    static_for<MMAX>([&](auto MM) {
+                        constexpr int m = decltype(MM)::value;
+                        static_for<NMAX + 1>([&](auto NN) {
+                            constexpr int n = decltype(NN)::value;
+                            double v = c0p * g[d][n][m];
+                            if constexpr (m > 0) v = fma(m * b01, g[d][n][m - 1], v);
+                            if constexpr (n > 0) v = fma(n * b00, g[d][n - 1][m], v);
+                            g[d][n][m + 1] = v;
+                        });
+                    });
+                });
+                static_for<NE>([&](auto EE) {
+                    constexpr int e = decltype(EE)::value;
+                    constexpr int le = cx_range_l(LA, e), ie = cx_range_i(LA, e);
+                    constexpr int ex = cx_lx(le, ie), ey = cx_ly(le, ie), ez = cx_lz(le, ie);
+                    static_for<NF>([&](auto FF) {
+                        constexpr int f = decltype(FF)::value;
+                        constexpr int lf = cx_range_l(LC, f), jf = cx_range_i(LC, f);
+                        constexpr int fx = cx_lx(lf, jf), fy = cx_ly(lf, jf), fz = cx_lz(lf, jf);
+                        const double xy = g[0][ex][fx] * g[1][ey][fy];
+                        if constexpr (NCU == 1) {
+                            if constexpr (NCT == 1) acc[e * NF + f] = fma(xy, g[2][ez][fz], acc[e * NF + f]);
+                            else accu[e * NF + f] = fma(xy, g[2][ez][fz], accu[e * NF + f]);
+                        } else {
+                            val[e * NF + f] = fma(xy, g[2][ez][fz], val[e * NF + f]);
+                        }
+                    });
+                });
+            });
+            if constexpr (NCU > 1) {
+#pragma unroll
+                for (int c = 0; c < NCU; c++) {
+                    const double cc = su[9 + c];
+#pragma unroll
+                    for (int i = 0; i < NEF; i++) {
+                        if constexpr (NCT == 1) acc[c * NEF + i] = fma(cc, val[i], acc[c * NEF + i]);
+                        else accu[c * NEF + i] = fma(cc, val[i], accu[c * NEF + i]);
+                    }
+                }
+            }
+        }
+        if constexpr (NCT > 1) {
+#pragma unroll
+            for (int ct = 0; ct < NCT; ct++)
+#pragma unroll
+                for (int i = 0; i < NCU * NEF; i++) acc[ct * NCU * NEF + i] = fma(ccT[ct], accu[i], acc[ct * NCU * NEF + i]);
+        }
+    }
+    if (!active) return;
+
+    // --- epilogue: HRR, c2s, store ---
+    const int sa = P.tstride[tt], sb = P.tstride[NT + tt];
+    const long long sc = (long long)P.ustride[u] * P.ld, sd = (long long)P.ustride[P.NU_all + u] * P.ld;
+    double *obase = P.out + (P.trow[tt] - P.row0) + P.ucol[u] * P.ld;
+    const int nca_t = P.nca_t, nca_u = P.nca_u;
+#pragma unroll 1
+    for (int comb = 0; comb < NCT * NCU; comb++) {
+        const int ct = comb / NCU, cu = comb - ct * NCU;
+        // select the accumulator block of this combination (dynamic index -> predicated copies)
+        double ef[NEF];
+        static_for<NCT * NCU>([&](auto CI) {
+            constexpr int ci = decltype(CI)::value;
+            if (comb == ci) {
+#pragma unroll
+                for (int i = 0; i < NEF; i++) ef[i] = acc[ci * NEF + i];
+            }
+        });
+        double abf[NFA * NFB * NF];
+        hrr_pair_reg<LA, LB, 1, NF>(ef, abf, abT);                   // [ab][F]
+        double abcd[NFA * NFB * NFC * NFD];
+        hrr_pair_reg<LC, LD, NFA * NFB, 1>(abf, abcd, abU);          // [a][b][c][d]
+        // c2s on each index with l >= 2 (s, p are identities)
+        double s1[DA * NFB * NFC * NFD];
+        if constexpr (LA >= 2) c2s_reg<LA, 1, NFB * NFC * NFD>(abcd, s1);
+        double *p1 = (LA >= 2) ? s1 : abcd;
+        double s2[DA * DB * NFC * NFD];
+        if constexpr (LB >= 2) c2s_reg<LB, DA, NFC * NFD>(p1, s2);
+        double *p2 = (LB >= 2) ? s2 : p1;
+        double s3[DA * DB * DC * NFD];
+        if constexpr (LC >= 2) c2s_reg<LC, DA * DB, NFD>(p2, s3);
+        double *p3 = (LC >= 2) ? s3 : p2;
+        double s4[DA * DB * DC * DD];
+        if constexpr (LD >= 2) c2s_reg<LD, DA * DB * DC, 1>(p3, s4);
+        double *p4 = (LD >= 2) ? s4 : p3;
+
+        const int ca = ct % nca_t, cb = ct / nca_t, cc = cu % nca_u, cd = cu / nca_u;
+        double *dst = obase + (long long)ca * DA * sa + (long long)cb * DB * sb + cc * DC * sc + cd * DD * sd;
+        static_for<DD>([&](auto MD) {
+            static_for<DC>([&](auto MC) {
+                static_for<DB>([&](auto MB) {
+                    static_for<DA>([&](auto MA) {
+                        constexpr int ma = decltype(MA)::value, mb = decltype(MB)::value;
+                        constexpr int mc = decltype(MC)::value, md = decltype(MD)::value;
+                        dst[ma * sa + mb * sb + mc * sc + md * sd] = p4[((ma * DB + mb) * DC + mc) * DD + md];
+                    });
+                });
+            });
+        });
+    }
+}

@@ -22,4 +22,11 @@ int generic_setup_constants();
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
                  int cart, long long ntasks, const int *c2s_off_table);
 int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLaunch &L, const Task *tasks,
-                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream);
+                   long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream,
+                   const TileParams *tile = nullptr, const long long *uprefix = nullptr);
+
+// register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
+typedef void (*RegKernelFn)(const TileParams);
+RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu);
+int rys_tab_nint(int nroots);
+int reg_kernel_launch(RegKernelFn fn, int nroots, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);

@@ -59,3 +59,36 @@ struct EngineParams {          // passed by value to kernels
     double omega;              // env[PTR_RANGE_OMEGA]; > 0 long range, 0 plain Coulomb
     int cart;                  // 1: Cartesian output (int2e_cart), 0: real spherical
 };
+
+// ----------------------------------------------------------------------------- tile description
+struct TileParams {
+    // T side (per-thread pairs): structure-of-arrays tables of one pair class
+    const double *tprim;       // [6 + NCT][Q][NT]: aij, 1/aij, px, py, pz, kij, cc[NCT]
+    const double *tgeom;       // [6][NT]: ra[3], ab[3]
+    const long long *trow;     // [NT] global row offset of the pair's block
+    const int *tstride;        // [2][NT] sa, sb (elements)
+    const int *tI;             // [NT] larger shell index of the pair (sorted ascending)
+    const int *tpair;          // [NT] pair ids (for the generic kernel's tile mode)
+    int NT, Q;                 // pairs in class, primitives per pair (padded)
+    int t_begin, t_end;        // range of this chunk inside the class list
+    int nca_t;                 // contraction count of shell a (T side), for block offsets
+    // U side (block-uniform pairs)
+    const int *upair;          // [NU] pair ids (AoS tables in EngineParams), sorted by larger shell index
+    const int *uK;             // [NU] larger shell index
+    const long long *ucol;     // [NU] column offset of the pair's block (this rank's numbering)
+    const int *ustride;        // [2][NU] sc, sd (in columns)
+    int NU;                    // kets of this launch (this rank's share among the first NU_valid)
+    int NU_all;                // length of the class list (second row of ustride starts here)
+    int u_step, u_first;       // rank sharding: u = u_first + u_step * blockIdx.y
+    int nca_u;
+    int tri;                   // 1: only quartets with K(u) <= I(t) (reference benchmark loop)
+    // output tile
+    double *out;
+    long long row0;            // global row of the chunk's first row
+    long long ld;              // rows of the chunk buffer
+    // engine tables
+    const PairHdr *pairs;
+    const PrimPair *prims;
+    const double *pcoef;
+    const double *rys;         // table of this class' nroots
+};

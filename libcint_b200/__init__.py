@@ -54,6 +54,10 @@ def load_library():
         lib.cintb200_debug_pair_offsets.restype = ci
         lib.cintb200_debug_force_generic.argtypes = [vp, ci]
         lib.cintb200_debug_force_generic.restype = None
+        lib.cintb200_debug_profile.argtypes = [vp, ci]
+        lib.cintb200_debug_profile.restype = None
+        lib.cintb200_debug_profile_rows.argtypes = [vp, vp, ci]
+        lib.cintb200_debug_profile_rows.restype = ci
     for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
@@ -166,6 +170,18 @@ class Context:
             raise B200Error(self.lib.cintb200_last_error().decode())
         return out.reshape((ld, ncols), order="F"), dict(i0=int(geom[0]), i1=int(geom[1]), row0=int(geom[2]),
                                                          ld=ld, ncols=ncols, nchunks=int(geom[5]))
+
+    def profile(self, **kw):
+        """Run the whole job once with per-launch CUDA events; returns (stats, rows[n,12]) -- see driver.cu."""
+        self.lib.cintb200_debug_profile(self.handle, 1)
+        try:
+            st = self.all_unique(**kw)
+        finally:
+            self.lib.cintb200_debug_profile(self.handle, 0)
+        n = self.lib.cintb200_debug_profile_rows(self.handle, None, 0)
+        rows = np.zeros((n, 12))
+        self.lib.cintb200_debug_profile_rows(self.handle, _p(rows), n)
+        return st, rows
 
     def pair_offsets(self, i, j):
         """(global row offset, this rank's column offset or -1) of the block of shell pair (i, j), i >= j."""

@@ -245,10 +245,13 @@ struct LaunchRec {
     int chunk;
     TileParams P;               // out / row0 / ld filled per run (buffer alternates)
     RegKernelFn fn;             // nullptr -> generic kernel
+    int coop; CoopInfo ci;      // fn is a cooperative kernel
     int nroots, ncu, gx, gy;
     GenericClass GC; GenericLaunch GL;
     long long ntasks;           // generic: number of quartets
     size_t uprefix_off;         // generic: offset into plan->d_uprefix
+    int key[6];                 // la lb lc ld nct ncu
+    double quartets, prim, flops;
 };
 
 static int build_launches(CINTOpt *c, JobPlan *plan)
@@ -308,9 +311,16 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 plan->st_quartets += q_here; plan->st_integrals += q_here * blk; plan->st_prim += prim_here;
                 plan->st_flops += prim_here * fp + q_here * fq;
                 L.ntasks = uprefix[nu_mine];
+                L.key[0] = T.la; L.key[1] = T.lb; L.key[2] = U.la; L.key[3] = U.lb; L.key[4] = T.nca * T.ncb; L.key[5] = U.nca * U.ncb;
+                L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq;
                 L.fn = c->force_generic ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
+                if (!L.fn && !c->force_generic) {
+                    L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci);
+                    L.coop = L.fn != nullptr;
+                }
                 if (L.fn) {
-                    L.gx = (t_end - t_begin + 127) / 128;
+                    const int qpb = L.coop ? 128 / L.ci.fs : 128;
+                    L.gx = (t_end - t_begin + qpb - 1) / qpb;
                     for (int y0 = 0; y0 < nu_mine; y0 += 65535) {
                         LaunchRec L2 = L;
                         L2.P.u_first = rank + nranks * y0;
@@ -374,7 +384,15 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         }
         return 0;
     };
+    const bool prof = c->profile != 0;
+    std::vector<cudaEvent_t> pev;
+    if (prof) {
+        pev.resize(plan->launches.size() + 1);
+        for (auto &e : pev) CU_OK(cudaEventCreate(&e));
+    }
+    size_t li = 0;
     for (LaunchRec &L : plan->launches) {
+        if (prof) CU_OK(cudaEventRecord(pev[li++], st));
         if (L.chunk != cur_chunk) {
             if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; buf ^= 1; }
             cur_chunk = L.chunk;
@@ -382,7 +400,8 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         }
         L.P.out = plan->d_out[buf];
         if (L.fn) {
-            if (reg_kernel_launch(L.fn, L.nroots, L.ncu, L.P, L.gx, L.gy, st))
+            if (L.coop ? coop_kernel_launch(L.fn, L.ci, L.ncu, L.P, L.gx, L.gy, st)
+                       : reg_kernel_launch(L.fn, L.nroots, L.ncu, L.P, L.gx, L.gy, st))
                 return b200_fail(CINTB200_ENODEV, "register kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             reg_launches++;
         } else {
@@ -392,6 +411,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         }
         nlaunch++;
     }
+    if (prof) CU_OK(cudaEventRecord(pev[li], st));
     if (cur_chunk >= 0 && finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV;
     CU_OK(cudaEventRecord(plan->ev_t1, st));
     CU_OK(cudaStreamSynchronize(st));
@@ -400,6 +420,26 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
     if (le != cudaSuccess) return b200_fail(CINTB200_ENODEV, "kernel execution failed: %s", cudaGetErrorString(le));
     float ms = 0;
     CU_OK(cudaEventElapsedTime(&ms, plan->ev_t0, plan->ev_t1));
+    if (prof) {
+        // aggregate launch durations by kernel class: rows of 12 doubles
+        std::map<std::vector<int>, std::vector<double>> agg;
+        for (size_t k = 0; k < plan->launches.size(); k++) {
+            const LaunchRec &L = plan->launches[k];
+            float dt = 0;
+            cudaEventElapsedTime(&dt, pev[k], pev[k + 1]);
+            std::vector<int> key(L.key, L.key + 6);
+            key.push_back(L.fn ? (L.coop ? 2 : 1) : 0);
+            std::vector<double> &a = agg[key];
+            if (a.empty()) a.assign(5, 0.0);
+            a[0] += dt; a[1] += L.quartets; a[2] += L.prim; a[3] += L.flops; a[4] += 1;
+        }
+        c->profile_rows.clear();
+        for (auto &kv : agg) {
+            for (int v : kv.first) c->profile_rows.push_back(v);
+            for (double v : kv.second) c->profile_rows.push_back(v);
+        }
+        for (auto &e : pev) cudaEventDestroy(e);
+    }
     if (stats) {
         stats[0] = plan->st_quartets; stats[1] = plan->st_integrals; stats[2] = plan->st_prim; stats[3] = 0;
         stats[4] = (double)nlaunch; stats[5] = d2h; stats[6] = plan->st_flops; stats[7] = ms;
@@ -447,4 +487,15 @@ extern "C" int cintb200_debug_pair_offsets(cintb200_ctx *c, int i, int j, long l
     *row = plan->rowoff[p];
     *col_owner_rank = plan->colof[p];       // -1: another rank owns this ket
     return 0;
+}
+
+// Per-class profile of the last cintb200_int2e_sph_all_unique run made with profiling on: rows of
+// 12 doubles {la, lb, lc, ld, nct, ncu, is_register_kernel, ms, quartets, primitive quartets, model flops, launches}.
+extern "C" void cintb200_debug_profile(cintb200_ctx *c, int on) { if (c && c->magic == B200_CTX_MAGIC) c->profile = on; }
+extern "C" int cintb200_debug_profile_rows(cintb200_ctx *c, double *rows, int max_rows)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return -1;
+    const int n = (int)(c->profile_rows.size() / 12);
+    if (rows) memcpy(rows, c->profile_rows.data(), sizeof(double) * 12 * std::min(n, max_rows));
+    return n;
 }

@@ -40,6 +40,8 @@ struct CINTOpt {
     unsigned long long *d_counters = nullptr;
     long long launches = 0;
     struct JobPlan *plan = nullptr;     // cached whole-job plan (driver.cu)
+    int profile = 0;                    // record per-launch events in the whole-job driver
+    std::vector<double> profile_rows;
     int force_generic = 0;              // tests: route every class through the generic kernel
     std::mutex mtx;
 };

@@ -30,3 +30,8 @@ typedef void (*RegKernelFn)(const TileParams);
 RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu);
 int rys_tab_nint(int nroots);
 int reg_kernel_launch(RegKernelFn fn, int nroots, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);
+
+// cooperative kernels (kern_coop_inst*.cu): FS lanes per quartet
+struct CoopInfo { int fs, xsz, nroots; };
+RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info);
+int coop_kernel_launch(RegKernelFn fn, const CoopInfo &info, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);

@@ -75,6 +75,10 @@ size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, i
 int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
                                   double *host_sink, double *stats);
 
+/* Measured FP64 FMA peak of the device in TFLOP/s (DFMA-chain microbenchmark run for about `seconds`);
+ * the roofline denominator of bench.py, since MEASURED_PEAKS.json has no FP64 entry. */
+int cintb200_fp64_peak(int device, double seconds, double *tflops);
+
 /* Last error text of the calling thread ("" if none). */
 const char *cintb200_last_error(void);
 

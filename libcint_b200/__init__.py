@@ -44,6 +44,8 @@ def load_library():
     lib.cintb200_block_size.argtypes = [vp, ci, vp, ci]
     lib.cintb200_block_size.restype = sz
     lib.cintb200_last_error.restype = ctypes.c_char_p
+    lib.cintb200_fp64_peak.argtypes = [ci, cd, vp]
+    lib.cintb200_fp64_peak.restype = ci
     if hasattr(lib, "cintb200_int2e_sph_all_unique"):
         lib.cintb200_int2e_sph_all_unique.argtypes = [vp, ci, ci, sz, vp, vp]
         lib.cintb200_int2e_sph_all_unique.restype = ci
@@ -220,6 +222,15 @@ def int3c2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
 
 def int3c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int3c2e_cart", 3, shls, atm, bas, env, opt, dims, out, cart=True)
+
+
+def fp64_peak_tflops(device=-1, seconds=0.5):
+    """DFMA-chain microbenchmark: the FP64 roofline denominator (TFLOP/s)."""
+    lib = load_library()
+    v = ctypes.c_double()
+    if lib.cintb200_fp64_peak(device, seconds, ctypes.byref(v)) != 0:
+        raise B200Error(lib.cintb200_last_error().decode())
+    return v.value
 
 
 def load_fixture(name):

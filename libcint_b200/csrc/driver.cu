@@ -56,6 +56,9 @@ struct JobPlan {
     std::vector<struct LaunchRec> launches;
     double st_quartets = 0, st_integrals = 0, st_prim = 0, st_flops = 0;
     cudaStream_t copy_stream = nullptr;
+    static const int NS = 8;                // concurrent launch streams (independent classes overlap)
+    cudaStream_t streams[NS] = {nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NS] = {nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
 };
 
@@ -68,6 +71,8 @@ void jobplan_free(JobPlan *p)
     }
     cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
+    for (int k = 0; k < JobPlan::NS; k++) { if (p->streams[k]) cudaStreamDestroy(p->streams[k]); if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     for (int b = 0; b < 2; b++) {
         if (p->ev_done[b]) cudaEventDestroy(p->ev_done[b]);
         if (p->ev_copied[b]) cudaEventDestroy(p->ev_copied[b]);
@@ -236,6 +241,11 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
         CU_OK(cudaEventCreateWithFlags(&plan->ev_done[b], cudaEventDisableTiming));
         CU_OK(cudaEventCreateWithFlags(&plan->ev_copied[b], cudaEventDisableTiming));
     }
+    for (int k = 0; k < JobPlan::NS; k++) {
+        CU_OK(cudaStreamCreateWithFlags(&plan->streams[k], cudaStreamNonBlocking));
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_join[k], cudaEventDisableTiming));
+    }
+    CU_OK(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
     CU_OK(cudaEventCreate(&plan->ev_t0));
     CU_OK(cudaEventCreate(&plan->ev_t1));
     return 0;
@@ -363,16 +373,36 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         if (rc) { jobplan_free(plan); return rc; }
         c->plan = plan;
     }
+    if (host_sink && plan->out_doubles * sizeof(double) > chunk_bytes)
+        return b200_fail(CINTB200_EINVAL, "host_sink mode: the largest tile (one bra shell x all kets) needs %zu bytes, "
+                         "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
     EngineParams EP;
     EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
     EP.expcutoff = c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
 
     double d2h = 0;
     long long nlaunch = 0, reg_launches = 0;
+    const bool prof = c->profile != 0;
     cudaStream_t st = c->stream;
     CU_OK(cudaEventRecord(plan->ev_t0, st));
     int buf = 0, cur_chunk = -1;
+    const int NS = prof ? 1 : JobPlan::NS;
+    auto fork = [&]() -> int {                 // side streams start after everything queued on the main stream
+        if (NS == 1) return 0;
+        CU_OK(cudaEventRecord(plan->ev_fork, st));
+        for (int k = 0; k < NS; k++) CU_OK(cudaStreamWaitEvent(plan->streams[k], plan->ev_fork, 0));
+        return 0;
+    };
+    auto join = [&]() -> int {                 // main stream continues after all side streams drained
+        if (NS == 1) return 0;
+        for (int k = 0; k < NS; k++) {
+            CU_OK(cudaEventRecord(plan->ev_join[k], plan->streams[k]));
+            CU_OK(cudaStreamWaitEvent(st, plan->ev_join[k], 0));
+        }
+        return 0;
+    };
     auto finish_chunk = [&](int ch, int b) -> int {
+        if (join()) return CINTB200_ENODEV;
         CU_OK(cudaEventRecord(plan->ev_done[b], st));
         if (host_sink) {
             const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
@@ -384,7 +414,6 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         }
         return 0;
     };
-    const bool prof = c->profile != 0;
     std::vector<cudaEvent_t> pev;
     if (prof) {
         pev.resize(plan->launches.size() + 1);
@@ -392,21 +421,24 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
     }
     size_t li = 0;
     for (LaunchRec &L : plan->launches) {
-        if (prof) CU_OK(cudaEventRecord(pev[li++], st));
         if (L.chunk != cur_chunk) {
             if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; buf ^= 1; }
             cur_chunk = L.chunk;
             if (host_sink) CU_OK(cudaStreamWaitEvent(st, plan->ev_copied[buf], 0));   // buffer drained?
+            if (fork()) return CINTB200_ENODEV;
         }
         L.P.out = plan->d_out[buf];
+        cudaStream_t ls = (NS == 1) ? st : plan->streams[nlaunch % NS];
+        if (prof) CU_OK(cudaEventRecord(pev[li++], st));
         if (L.fn) {
-            if (L.coop ? coop_kernel_launch(L.fn, L.ci, L.ncu, L.P, L.gx, L.gy, st)
-                       : reg_kernel_launch(L.fn, L.nroots, L.ncu, L.P, L.gx, L.gy, st))
+            if (L.coop ? coop_kernel_launch(L.fn, L.ci, L.ncu, L.P, L.gx, L.gy, ls)
+                       : reg_kernel_launch(L.fn, L.nroots, L.ncu, L.P, L.gx, L.gy, ls))
                 return b200_fail(CINTB200_ENODEV, "register kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             reg_launches++;
         } else {
             L.GC.scratch = plan->d_scratch;
-            if (generic_launch(EP, L.GC, L.GL, nullptr, L.ntasks, plan->d_out[buf], nullptr, nullptr, st, &L.P, plan->d_uprefix + L.uprefix_off))
+            ls = st;            // generic launches share one scratch area: keep them ordered on the main stream
+            if (generic_launch(EP, L.GC, L.GL, nullptr, L.ntasks, plan->d_out[buf], nullptr, nullptr, ls, &L.P, plan->d_uprefix + L.uprefix_off))
                 return b200_fail(CINTB200_ENODEV, "generic kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         nlaunch++;

@@ -575,3 +575,48 @@ extern "C" void cintb200_debug_force_generic(cintb200_ctx *c, int on) { if (c &&
 
 int rys_tab_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_NINT[nroots] : 0; }
 int rys_tab_off(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_OFF[nroots] : 0; }
+
+// ------------------------------------------------------------------ FP64 roofline denominator
+// MEASURED_PEAKS.json carries no FP64 entry, so the bench measures the DFMA peak itself: 8 independent
+// FMA chains per thread, 2 flops per FMA, enough resident warps to saturate the FP64 pipes.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
+{
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; i++) {
+        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+
+extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
+{
+    if (device >= 0) CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double *buf;
+    CUDA_OK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_OK(cudaEventCreate(&e0));
+    CUDA_OK(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);      // warm-up
+    CUDA_OK(cudaDeviceSynchronize());
+    double best = 0, spent = 0;
+    while (spent < seconds) {
+        CUDA_OK(cudaEventRecord(e0));
+        dfma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999999, 1e-9);
+        CUDA_OK(cudaEventRecord(e1));
+        CUDA_OK(cudaEventSynchronize(e1));
+        float ms;
+        CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+        spent += ms * 1e-3;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops = best;
+    return 0;
+}

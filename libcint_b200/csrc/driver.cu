@@ -35,7 +35,8 @@ struct PairClass {
     std::vector<long long> npp_prefix;      // prefix sums of npp over the list
     double *d_tprim = nullptr, *d_tgeom = nullptr;
     long long *d_trow = nullptr, *d_ucol = nullptr;
-    int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr;
+    int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr, *d_tnpp = nullptr;
+    std::vector<int> chunk_lo;              // first list index of every chunk (+ end)
 };
 
 struct LaunchRec;
@@ -47,6 +48,7 @@ struct JobPlan {
     std::vector<long long> rows_before;     // [nbas+1] rows of pairs with I < i
     std::vector<long long> cols_before;     // [nbas+1] this rank's columns of kets with K < i
     std::vector<std::pair<int, int>> chunks;
+    std::vector<long long> chunk_cols;      // this rank's columns needed by chunk k (kets with K < i1)
     double *d_out[2] = {nullptr, nullptr};
     size_t out_doubles = 0;
     long long *d_uprefix = nullptr; size_t cap_uprefix = 0;
@@ -67,7 +69,7 @@ void jobplan_free(JobPlan *p)
     if (!p) return;
     for (PairClass &c : p->classes) {
         cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
-        cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride);
+        cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
     }
     cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -80,13 +82,6 @@ void jobplan_free(JobPlan *p)
     if (p->ev_t0) cudaEventDestroy(p->ev_t0);
     if (p->ev_t1) cudaEventDestroy(p->ev_t1);
     delete p;
-}
-
-static int bucket_q(int npp)
-{
-    static const int b[] = {1, 2, 3, 4, 6, 8, 9, 12, 16, 24, 32, 48, 64};
-    for (int v : b) if (npp <= v) return v;
-    return (npp + 15) / 16 * 16;
 }
 
 template <class T>
@@ -119,64 +114,108 @@ static void model_flops(int li, int lj, int lk, int ll, int nc, double *per_prim
 
 static int build_plan(CINTOpt *c, JobPlan *plan)
 {
-    const int nbas = c->nbas;
+    const int nbas = c->nbas, nranks = plan->nranks, rank = plan->rank;
     const size_t npair = (size_t)nbas * (nbas + 1) / 2;
+    auto pair_dim = [&](int i, int j) {
+        const ShellInfo &si = c->shells[i], &sj = c->shells[j];
+        return (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
+    };
+    // 1. pair classes (la, lb, nca, ncb), lists in enumeration order = sorted by the larger shell index
     std::map<std::vector<int>, int> key2class;
-    std::vector<int> cls_of(npair), idx_in_cls(npair);
     plan->rowoff.resize(npair);
     plan->rows_before.assign(nbas + 1, 0);
-    plan->cols_before.assign(nbas + 1, 0);
-    long long rows = 0;
+    std::vector<long long> tcols_before(nbas + 1, 0);
+    long long rows = 0, maxdim = 1;
     for (int i = 0; i < nbas; i++) {
         plan->rows_before[i] = rows;
         for (int j = 0; j <= i; j++) {
             const size_t p = (size_t)i * (i + 1) / 2 + j;
             const PairHdr &h = c->pairs[p];
-            const int q = bucket_q(std::max(1, h.npp));
-            std::vector<int> key = {h.la, h.lb, h.nca, h.ncb, q};
+            std::vector<int> key = {h.la, h.lb, h.nca, h.ncb};
             auto it = key2class.find(key);
             int ci;
             if (it == key2class.end()) {
                 ci = (int)plan->classes.size();
                 key2class[key] = ci;
                 PairClass pc;
-                pc.la = h.la; pc.lb = h.lb; pc.nca = h.nca; pc.ncb = h.ncb; pc.Q = q;
+                pc.la = h.la; pc.lb = h.lb; pc.nca = h.nca; pc.ncb = h.ncb; pc.Q = 1;
                 plan->classes.push_back(pc);
             } else ci = it->second;
             PairClass &pc = plan->classes[ci];
-            cls_of[p] = ci;
-            idx_in_cls[p] = (int)pc.ids.size();
             pc.ids.push_back((int)p);
             pc.I.push_back(i);
             pc.npp.push_back(h.npp);
+            pc.Q = std::max(pc.Q, h.npp);
             plan->rowoff[p] = rows;
-            const ShellInfo &si = c->shells[i], &sj = c->shells[j];
-            rows += (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
+            rows += pair_dim(i, j);
+            maxdim = std::max(maxdim, pair_dim(i, j));
         }
     }
     plan->rows_before[nbas] = rows;
-    // this rank's column numbering: kets dealt round-robin inside each class list
+    for (int i = 0; i <= nbas; i++) tcols_before[i] = plan->rows_before[i];      // same numbering before sharding
+    // 2. chunks: ranges of i; column need estimated as total/nranks + slack (exact numbering comes after the
+    //    per-chunk reordering, the buffer is then sized from the exact maximum)
+    const size_t cap = plan->chunk_bytes / sizeof(double);
+    const long long slack = maxdim * (long long)plan->classes.size() * 2;
+    auto est_cols = [&](int i1) { return (size_t)(tcols_before[i1] / nranks + slack); };
+    int i0 = 0;
+    while (i0 < nbas) {
+        int i1 = i0 + 1;
+        while (i1 < nbas) {
+            size_t r = (size_t)(plan->rows_before[i1 + 1] - plan->rows_before[i0]);
+            if (r * est_cols(i1 + 1) > cap) break;
+            i1++;
+        }
+        plan->chunks.push_back({i0, i1});
+        i0 = i1;
+    }
+    // 3. inside every chunk range, order each class list by descending primitive count: a block's first
+    //    quartet then carries the block's loop bound and neighbouring threads do equal work
+    for (PairClass &pc : plan->classes) {
+        std::vector<int> order(pc.ids.size());
+        for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
+        for (auto &ch : plan->chunks) {
+            auto b = std::lower_bound(pc.I.begin(), pc.I.end(), ch.first) - pc.I.begin();
+            auto e = std::lower_bound(pc.I.begin(), pc.I.end(), ch.second) - pc.I.begin();
+            std::stable_sort(order.begin() + b, order.begin() + e, [&](int x, int y) { return pc.npp[x] > pc.npp[y]; });
+        }
+        pc.chunk_lo.clear();
+        for (auto &ch : plan->chunks) pc.chunk_lo.push_back((int)(std::lower_bound(pc.I.begin(), pc.I.end(), ch.first) - pc.I.begin()));
+        pc.chunk_lo.push_back((int)pc.ids.size());
+        std::vector<int> ids(order.size()), I(order.size()), npp(order.size());
+        for (size_t k = 0; k < order.size(); k++) { ids[k] = pc.ids[order[k]]; I[k] = pc.I[order[k]]; npp[k] = pc.npp[order[k]]; }
+        pc.ids.swap(ids); pc.I.swap(I); pc.npp.swap(npp);
+    }
+    // 4. this rank's kets: index in the final class order modulo nranks; columns numbered chunk by chunk so that
+    //    the kets with K < i1 always occupy the first cols_before[i1] columns
     std::vector<long long> &colof = plan->colof;
     colof.assign(npair, -1);
+    plan->cols_before.assign(nbas + 1, 0);
     long long cols = 0;
-    for (int i = 0; i < nbas; i++) {
-        plan->cols_before[i] = cols;
-        for (int j = 0; j <= i; j++) {
-            const size_t p = (size_t)i * (i + 1) / 2 + j;
-            if (idx_in_cls[p] % plan->nranks != plan->rank) continue;
-            colof[p] = cols;
-            const ShellInfo &si = c->shells[i], &sj = c->shells[j];
-            cols += (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
-        }
+    size_t need = 1;
+    for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
+        for (int i = plan->chunks[ch].first; i < plan->chunks[ch].second; i++) plan->cols_before[i] = cols;   // lower bound only
+        for (PairClass &pc : plan->classes)
+            for (int k = pc.chunk_lo[ch]; k < pc.chunk_lo[ch + 1]; k++) {
+                if (k % nranks != rank) continue;
+                const int p = pc.ids[k];
+                colof[p] = cols;
+                const int i = pc.I[k], j = p - i * (i + 1) / 2;
+                cols += pair_dim(i, j);
+            }
+        plan->chunk_cols.push_back(cols);
+        const size_t r = (size_t)(plan->rows_before[plan->chunks[ch].second] - plan->rows_before[plan->chunks[ch].first]);
+        need = std::max(need, r * (size_t)std::max<long long>(cols, 1));
     }
     plan->cols_before[nbas] = cols;
-
+    plan->out_doubles = need;
+    // 5. device tables per class
     for (PairClass &pc : plan->classes) {
         const size_t NT = pc.ids.size();
         const int nct = pc.nca * pc.ncb, Q = pc.Q;
         std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
         std::vector<long long> trow(NT), ucol(NT);
-        std::vector<int> tstride(2 * NT), ustride(2 * NT);
+        std::vector<int> tstride(2 * NT);
         pc.npp_prefix.assign(NT + 1, 0);
         for (size_t n = 0; n < NT; n++) {
             const int p = pc.ids[n];
@@ -200,39 +239,20 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
             }
             // strides of the canonical indices inside the (i,j) block: i fastest
             const int i = pc.I[n];
-            const int j = (h.sh_a == i) ? h.sh_b : h.sh_a;
             const ShellInfo &si = c->shells[i];
             const int di = (2 * si.l + 1) * si.nctr;
             const bool a_is_i = (h.sh_a == i);
-            (void)j;
             tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
-            ustride[n] = a_is_i ? 1 : di;  ustride[NT + n] = a_is_i ? di : 1;
             trow[n] = plan->rowoff[p];
             ucol[n] = colof[p];
         }
+        std::vector<int> nppc(pc.npp);
+        for (int &v : nppc) v = std::max(v, 1);       // dead pairs still run one zero-weight primitive
         if (upload(&pc.d_tprim, tprim) || upload(&pc.d_tgeom, tgeom) || upload(&pc.d_trow, trow) || upload(&pc.d_ucol, ucol) ||
-            upload(&pc.d_tstride, tstride) || upload(&pc.d_ustride, ustride) || upload(&pc.d_tI, pc.I) || upload(&pc.d_tpair, pc.ids))
+            upload(&pc.d_tstride, tstride) || upload(&pc.d_ustride, tstride) || upload(&pc.d_tI, pc.I) || upload(&pc.d_tpair, pc.ids) ||
+            upload(&pc.d_tnpp, nppc))
             return CINTB200_ENOMEM;
     }
-    // chunks: ranges of i with rows(i0..i1) * cols(K < i1) * 8 <= chunk_bytes
-    const size_t cap = plan->chunk_bytes / sizeof(double);
-    int i0 = 0;
-    size_t need = 1;
-    while (i0 < nbas) {
-        int i1 = i0 + 1;
-        while (i1 < nbas) {
-            size_t r = (size_t)(plan->rows_before[i1 + 1] - plan->rows_before[i0]);
-            size_t cc = (size_t)plan->cols_before[i1 + 1];
-            if (r * cc > cap) break;
-            i1++;
-        }
-        size_t r = (size_t)(plan->rows_before[i1] - plan->rows_before[i0]);
-        size_t cc = (size_t)plan->cols_before[i1];
-        need = std::max(need, r * std::max<size_t>(cc, 1));
-        plan->chunks.push_back({i0, i1});
-        i0 = i1;
-    }
-    plan->out_doubles = need;
     for (int b = 0; b < 2; b++)
         if (cudaMalloc((void **)&plan->d_out[b], sizeof(double) * need) != cudaSuccess)
             return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
@@ -266,35 +286,32 @@ struct LaunchRec {
 
 static int build_launches(CINTOpt *c, JobPlan *plan)
 {
-    const int rank = plan->rank, nranks = plan->nranks, nbas = c->nbas;
-    std::vector<long long> uprefix_all;
+    const int rank = plan->rank, nranks = plan->nranks;
     size_t scratch_need = 0;
     plan->st_quartets = plan->st_integrals = plan->st_prim = plan->st_flops = 0;
-    // first T index with I >= k, per class
-    std::vector<std::vector<int>> first_t(plan->classes.size(), std::vector<int>(nbas + 1));
-    for (size_t ci = 0; ci < plan->classes.size(); ci++) {
-        const PairClass &T = plan->classes[ci];
-        for (int k = 0; k <= nbas; k++) first_t[ci][k] = (int)(std::lower_bound(T.I.begin(), T.I.end(), k) - T.I.begin());
-    }
     for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
         const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
         const long long row0 = plan->rows_before[i0];
         const long long ld = plan->rows_before[i1] - row0;
-        if (ld == 0 || plan->cols_before[i1] == 0) continue;
+        if (ld == 0 || plan->chunk_cols[ch] == 0) continue;
         for (size_t ct = 0; ct < plan->classes.size(); ct++) {
             PairClass &T = plan->classes[ct];
-            const int t_begin = first_t[ct][i0], t_end = first_t[ct][i1];
+            const int t_begin = T.chunk_lo[ch], t_end = T.chunk_lo[ch + 1];
             if (t_end <= t_begin) continue;
+            // per bra shell index inside this chunk: number of T pairs / primitives with I >= i
+            std::vector<double> cnt_ge(i1 - i0 + 1, 0.0), npp_ge(i1 - i0 + 1, 0.0);
+            for (int t = t_begin; t < t_end; t++) { cnt_ge[T.I[t] - i0] += 1; npp_ge[T.I[t] - i0] += T.npp[t]; }
+            for (int k = i1 - i0 - 1; k >= 0; k--) { cnt_ge[k] += cnt_ge[k + 1]; npp_ge[k] += npp_ge[k + 1]; }
             for (size_t cu = 0; cu < plan->classes.size(); cu++) {
                 PairClass &U = plan->classes[cu];
-                const int nu_valid = first_t[cu][i1];
+                const int nu_valid = U.chunk_lo[ch + 1];
                 if (nu_valid <= rank) continue;
                 const int nu_mine = (nu_valid - rank + nranks - 1) / nranks;
                 LaunchRec L;
                 memset(&L, 0, sizeof L);
                 TileParams &P = L.P;
                 P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
-                P.tI = T.d_tI; P.tpair = T.d_tpair;
+                P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp;
                 P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
                 P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = rank; P.nca_u = U.nca;
@@ -305,22 +322,20 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 L.nroots = (T.la + T.lb + U.la + U.lb) / 2 + 1;
                 L.ncu = U.nca * U.ncb;
                 P.rys = c->d_rys + rys_tab_off(L.nroots);
-                std::vector<long long> uprefix(nu_mine + 1, 0);
-                double prim_here = 0;
+                double q_here = 0, prim_here = 0;
                 for (int j = 0; j < nu_mine; j++) {
                     const int u = rank + nranks * j;
-                    const int tl = std::max(t_begin, std::min(t_end, first_t[ct][U.I[u]]));
-                    uprefix[j + 1] = uprefix[j] + (t_end - tl);
-                    prim_here += (double)U.npp[u] * (double)(T.npp_prefix[t_end] - T.npp_prefix[tl]);
+                    const int kk = std::max(U.I[u], i0) - i0;          // K < i0: every T pair of the chunk is valid
+                    q_here += cnt_ge[kk];
+                    prim_here += (double)U.npp[u] * npp_ge[kk];
                 }
-                const double q_here = (double)uprefix[nu_mine];
                 if (q_here == 0) continue;
                 const double blk = (double)(2 * T.la + 1) * (2 * T.lb + 1) * T.nca * T.ncb * (2 * U.la + 1) * (2 * U.lb + 1) * U.nca * U.ncb;
                 double fp, fq;
                 model_flops(T.la, T.lb, U.la, U.lb, T.nca * T.ncb * U.nca * U.ncb, &fp, &fq);
                 plan->st_quartets += q_here; plan->st_integrals += q_here * blk; plan->st_prim += prim_here;
                 plan->st_flops += prim_here * fp + q_here * fq;
-                L.ntasks = uprefix[nu_mine];
+                L.ntasks = (long long)(t_end - t_begin) * nu_mine;      // generic: rectangle, invalid quartets skipped in-kernel
                 L.key[0] = T.la; L.key[1] = T.lb; L.key[2] = U.la; L.key[3] = U.lb; L.key[4] = T.nca * T.ncb; L.key[5] = U.nca * U.ncb;
                 L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq;
                 L.fn = c->force_generic ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
@@ -341,14 +356,11 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off()))
                         return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits", T.la, T.lb, U.la, U.lb);
                     scratch_need = std::max(scratch_need, L.GC.scratch_per_block * (size_t)L.GL.grid);
-                    L.uprefix_off = uprefix_all.size();
-                    uprefix_all.insert(uprefix_all.end(), uprefix.begin(), uprefix.end());
                     plan->launches.push_back(L);
                 }
             }
         }
     }
-    if (upload(&plan->d_uprefix, uprefix_all)) return CINTB200_ENOMEM;
     if (scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate generic-kernel scratch");
     return 0;
@@ -406,7 +418,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         CU_OK(cudaEventRecord(plan->ev_done[b], st));
         if (host_sink) {
             const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
-            const size_t bytes = sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->cols_before[i1];
+            const size_t bytes = sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->chunk_cols[ch];
             CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_done[b], 0));
             CU_OK(cudaMemcpyAsync(host_sink, plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
             CU_OK(cudaEventRecord(plan->ev_copied[b], plan->copy_stream));
@@ -438,7 +450,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         } else {
             L.GC.scratch = plan->d_scratch;
             ls = st;            // generic launches share one scratch area: keep them ordered on the main stream
-            if (generic_launch(EP, L.GC, L.GL, nullptr, L.ntasks, plan->d_out[buf], nullptr, nullptr, ls, &L.P, plan->d_uprefix + L.uprefix_off))
+            if (generic_launch(EP, L.GC, L.GL, nullptr, L.ntasks, plan->d_out[buf], nullptr, nullptr, ls, &L.P, nullptr))
                 return b200_fail(CINTB200_ENODEV, "generic kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         nlaunch++;
@@ -492,7 +504,7 @@ extern "C" int cintb200_debug_chunk(cintb200_ctx *c, int chunk, double *host_out
     const int i0 = plan->chunks[chunk].first, i1 = plan->chunks[chunk].second;
     geom[0] = i0; geom[1] = i1;
     geom[2] = plan->rows_before[i0]; geom[3] = plan->rows_before[i1] - plan->rows_before[i0];
-    geom[4] = plan->cols_before[i1];
+    geom[4] = plan->chunk_cols[chunk];
     geom[5] = (long long)plan->chunks.size();
     const size_t n = (size_t)geom[3] * (size_t)geom[4];
     if (!host_out) return 0;
@@ -501,7 +513,7 @@ extern "C" int cintb200_debug_chunk(cintb200_ctx *c, int chunk, double *host_out
     int buf = 0;
     for (int k = 0; k < chunk; k++) {
         const long long ld = plan->rows_before[plan->chunks[k].second] - plan->rows_before[plan->chunks[k].first];
-        if (ld == 0 || plan->cols_before[plan->chunks[k].second] == 0) continue;
+        if (ld == 0 || plan->chunk_cols[k] == 0) continue;
         buf ^= 1;
     }
     CU_OK(cudaSetDevice(c->device));

@@ -17,7 +17,14 @@
 #pragma once
 #include "kern_reg.cuh"
 
-__host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * (nmax + 1) * (mmax + 1); }
+// per-(root,axis) G block padded to an odd number of doubles so the 3N lanes that write them hit distinct banks
+__host__ __device__ constexpr int coop_g_task(int nmax, int mmax) { return ((nmax + 1) * (mmax + 1)) | 1; }
+__host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * coop_g_task(nmax, mmax); }
+__host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, int nab)
+{
+    int a = nf * nab, b = coop_g_size(n, nmax, mmax) + 2 * n;
+    return (a > b ? a : b) | 1;
+}
 
 template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T>
 __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams P)
@@ -32,7 +39,8 @@ __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams 
     constexpr int NCT = REG_IS_T ? NCR : NCL, NCU = REG_IS_T ? NCL : NCR;
     constexpr int USTR = 9 + NCU;
     constexpr int GSZ = coop_g_size(N, NMAX, MMAX);
-    constexpr int XSZ = (NF * NAB > GSZ + 2 * N) ? NF * NAB : GSZ + 2 * N;   // per-quartet smem (G + roots, reused for the exchange)
+    constexpr int GT = coop_g_task(NMAX, MMAX);
+    constexpr int XSZ = coop_xsz(N, NMAX, MMAX, NF, NAB);       // per-quartet smem (G + roots, reused for the exchange)
     constexpr int MS = MMAX + 1;
     static_assert(NF <= FS, "lane side has more components than lanes");
     static_assert(FS <= 32 && (FS & (FS - 1)) == 0, "FS must be a power of two within a warp");
@@ -43,17 +51,12 @@ __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams 
     const int q = tid / FS, lane = tid % FS;
 
     const int K = P.uK[u];
-    int t_lo = P.t_begin;
-    if (P.tri) {
-        int lo = P.t_begin, hi = P.t_end;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
-        t_lo = lo;
-    }
-    const int t0 = t_lo + blockIdx.x * QPB;
-    if (t0 >= P.t_end) return;
+    const int t0 = P.t_begin + blockIdx.x * QPB;
     const int t = t0 + q;
-    const bool active = t < P.t_end;
-    const int tt = active ? t : P.t_end - 1;
+    const int tt = t < P.t_end ? t : P.t_end - 1;
+    const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);      // see kern_reg.cuh
+    if (!__syncthreads_or(active)) return;
+    const int Qb = P.tnpp[t0];
 
     // --- smem carve-up: Rys table | U primitives | per-quartet work areas ---
     double *s_rys = smem;
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams 
     for (int i = 0; i < NCOMB * NE; i++) acc[i] = 0.0;
 
     const int nppu = hu.npp;
-    for (int tq = 0; tq < P.Q; tq++) {
+    for (int tq = 0; tq < Qb; tq++) {
         const size_t o = (size_t)tq * NT + tt;
         const size_t F = (size_t)P.Q * NT;
         const double aT = P.tprim[o], iaT = P.tprim[F + o];
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams 
                         g[n][m + 1] = v;
                     });
                 });
-                double *dst = s_q + (size_t)task * (NMAX + 1) * MS;
+                double *dst = s_q + (size_t)task * GT;
                 static_for<NMAX + 1>([&](auto NN) {
                     static_for<MMAX + 1>([&](auto MM) {
                         dst[decltype(NN)::value * MS + decltype(MM)::value] = g[decltype(NN)::value][decltype(MM)::value];
@@ -201,9 +204,9 @@ __global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams 
             for (int e = 0; e < NE; e++) val[e] = 0.0;
             static_for<N>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
-                const double *gx = s_q + (size_t)(3 * r) * (NMAX + 1) * MS + fx;
-                const double *gy = s_q + (size_t)(3 * r + 1) * (NMAX + 1) * MS + fy;
-                const double *gz = s_q + (size_t)(3 * r + 2) * (NMAX + 1) * MS + fz;
+                const double *gx = s_q + (size_t)(3 * r) * GT + fx;
+                const double *gy = s_q + (size_t)(3 * r + 1) * GT + fy;
+                const double *gz = s_q + (size_t)(3 * r + 2) * GT + fz;
                 double cx[NMAX + 1], cy[NMAX + 1], cz[NMAX + 1];
 #pragma unroll
                 for (int n = 0; n <= NMAX; n++) { cx[n] = gx[n * MS]; cy[n] = gy[n * MS]; cz[n] = gz[n * MS]; }

@@ -80,26 +80,16 @@ __device__ void c2s_index(const double *in, double *out, int pre, int post, int 
     }
 }
 
-// tile mode: work item w -> (u, t) through the prefix array of valid T counts per U pair
-__device__ __forceinline__ Task tile_task(const TileParams &T, const long long *__restrict__ uprefix, long long w)
+// tile mode: work item w -> (u, t) of the rectangle (this rank's kets) x (T pairs of the chunk);
+// returns bra = -1 for quartets outside the reference loop bound k <= i
+__device__ __forceinline__ Task tile_task(const TileParams &T, long long w)
 {
-    int lo = 0, hi = T.NU;                       // last j with uprefix[j] <= w
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (uprefix[mid] <= w) lo = mid; else hi = mid;
-    }
-    const int j = lo;
+    const int nT = T.t_end - T.t_begin;
+    const int j = (int)(w / nT);
+    const int t = T.t_begin + (int)(w - (long long)j * nT);
     const int u = T.u_first + T.u_step * j;
-    int t_lo = T.t_begin;
-    if (T.tri) {
-        int a = T.t_begin, b = T.t_end;
-        const int K = T.uK[u];
-        while (a < b) { int mid = (a + b) >> 1; if (T.tI[mid] < K) a = mid + 1; else b = mid; }
-        t_lo = a;
-    }
-    const int t = t_lo + (int)(w - uprefix[j]);
     Task k;
-    k.bra = T.tpair[t];
+    k.bra = (T.tri && T.tI[t] < T.uK[u]) ? -1 : T.tpair[t];
     k.ket = T.upair[u];
     k.sa = T.tstride[t];
     k.sb = T.tstride[T.NT + t];
@@ -151,7 +141,8 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
         * (la < 2 ? fsp[la] : 1.0) * (lb < 2 ? fsp[lb] : 1.0) * (lc < 2 ? fsp[lc] : 1.0) * (ld < 2 ? fsp[ld] : 1.0);
 
     for (long long t = blockIdx.x; t < ntasks; t += gridDim.x) {
-        const Task task = tasks ? tasks[t] : tile_task(TP, uprefix, t);
+        const Task task = tasks ? tasks[t] : tile_task(TP, t);
+        if (task.bra < 0) continue;          // block-uniform
         const PairHdr hb = P.pairs[task.bra];
         const PairHdr hk = P.pairs[task.ket];
         __syncthreads();

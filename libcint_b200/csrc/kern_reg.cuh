@@ -222,20 +222,14 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const TileParams P
 
     // --- which T pairs does this block cover? ---
     const int K = P.uK[u];
-    int t_lo = P.t_begin;
-    if (P.tri) {                       // first T pair with I >= K (lists are sorted by I)
-        int lo = P.t_begin, hi = P.t_end;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
-        }
-        t_lo = lo;
-    }
-    const int t0 = t_lo + blockIdx.x * REG_THREADS;
-    if (t0 >= P.t_end) return;          // block-uniform
+    const int t0 = P.t_begin + blockIdx.x * REG_THREADS;
     const int t = t0 + tid;
-    const bool active = t < P.t_end;
-    const int tt = active ? t : P.t_end - 1;
+    const int tt = t < P.t_end ? t : P.t_end - 1;
+    // reference loop bound k <= i (examples/time_c60.c:206): only the kets of the chunk's own shell range
+    // can fail it; the lists are not sorted by shell index inside a chunk, so it is a per-thread predicate
+    const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);
+    if (!__syncthreads_or(active)) return;
+    const int Qb = P.tnpp[t0];          // lists are sorted by descending primitive count inside a chunk
 
     // --- stage the Rys table of N roots and the U pair's primitives ---
     const int nint = c_rys_meta.nint[N];
@@ -280,7 +274,7 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const TileParams P
     for (int i = 0; i < NACC; i++) acc[i] = 0.0;
 
     const int nppu = hu.npp;
-    for (int tq = 0; tq < P.Q; tq++) {
+    for (int tq = 0; tq < Qb; tq++) {
         const size_t o = (size_t)tq * NT + tt;
         const size_t F = (size_t)P.Q * NT;
         const double aT = P.tprim[o], iaT = P.tprim[F + o];

@@ -67,8 +67,9 @@ struct TileParams {
     const double *tgeom;       // [6][NT]: ra[3], ab[3]
     const long long *trow;     // [NT] global row offset of the pair's block
     const int *tstride;        // [2][NT] sa, sb (elements)
-    const int *tI;             // [NT] larger shell index of the pair (sorted ascending)
+    const int *tI;             // [NT] larger shell index of the pair
     const int *tpair;          // [NT] pair ids (for the generic kernel's tile mode)
+    const int *tnpp;           // [NT] primitive pairs per T pair (>= 1); lists are sorted by descending count inside a chunk
     int NT, Q;                 // pairs in class, primitives per pair (padded)
     int t_begin, t_end;        // range of this chunk inside the class list
     int nca_t;                 // contraction count of shell a (T side), for block offsets

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcint_b200.so")
+LIB_PATH = os.environ.get("CINTB200_LIB", os.path.join(_HERE, "libcint_b200.so"))     # override: kernel-variant experiments
 DATA_DIR = os.path.join(_HERE, "data")
 
 SPH, CART = 0, 1

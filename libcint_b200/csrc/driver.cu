@@ -338,8 +338,10 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 L.ntasks = (long long)(t_end - t_begin) * nu_mine;      // generic: rectangle, invalid quartets skipped in-kernel
                 L.key[0] = T.la; L.key[1] = T.lb; L.key[2] = U.la; L.key[3] = U.lb; L.key[4] = T.nca * T.ncb; L.key[5] = U.nca * U.ncb;
                 L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq;
-                L.fn = c->force_generic ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
-                if (!L.fn && !c->force_generic) {
+                // the specialised kernels implement the plain Coulomb operator; range-separated runs use the generic kernel
+                const bool generic_only = c->force_generic || c->omega != 0;
+                L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
+                if (!L.fn && !generic_only) {
                     L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci);
                     L.coop = L.fn != nullptr;
                 }

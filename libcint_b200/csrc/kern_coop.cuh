@@ -27,7 +27,7 @@ __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, in
 }
 
 template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T>
-__global__ void __launch_bounds__(REG_THREADS) eri_coop_kernel(const TileParams P)
+__global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;

@@ -94,6 +94,12 @@ __host__ __device__ constexpr int cx_hrr_off(int l0, int le, int j)   // offset 
 
 
 #define REG_THREADS 128
+#ifndef REG_UQ_UNROLL
+#define REG_UQ_UNROLL 1          // unroll factor of the inner (U) primitive loop
+#endif
+#ifndef REG_MIN_BLOCKS
+#define REG_MIN_BLOCKS 2          // register cap 255; see profiles/ for the occupancy experiments
+#endif
 #define REG_MAXU 64            // most primitive pairs of a U pair (8 x 8)
 
 // row stride (doubles) of the smem copy of the Rys table: odd, so rows fall on distinct 8-byte bank pairs
@@ -103,8 +109,8 @@ template <int N>
 __device__ __forceinline__ void rys_roots_smem(const double *tab, double x, double (&t2)[N], double (&w)[N])
 {
     if (x >= 35.0 + 5.0 * N) {
-        const double ix = 1.0 / x;
-        const double isx = sqrt(ix);
+        const double isx = rsqrt(x);            // t^2 = r/x, w = v/sqrt(x)
+        const double ix = isx * isx;
 #pragma unroll
         for (int k = 0; k < N; k++) {
             t2[k] = c_rys_lx_r[N * (N - 1) / 2 + k] * ix;
@@ -116,16 +122,22 @@ __device__ __forceinline__ void rys_roots_smem(const double *tab, double x, doub
     double y;
     rys_locate(x, idx, y);
     const double *c = tab + idx * rys_smem_stride(N);
-    double v[2 * N];
+    static_assert(RYS_DEG == 9, "Estrin scheme below is written for degree 9");
+    // Estrin evaluation: depth 4 instead of Horner's 9 dependent FMAs -- these kernels stall on fixed-latency
+    // dependencies (ncu: warp "wait" stalls dominate), not on FP64 issue bandwidth
+    const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
 #pragma unroll
-    for (int p = 0; p < 2 * N; p++) v[p] = c[RYS_DEG * 2 * N + p];
-#pragma unroll
-    for (int j = RYS_DEG - 1; j >= 0; j--) {
-#pragma unroll
-        for (int p = 0; p < 2 * N; p++) v[p] = fma(v[p], y, c[j * 2 * N + p]);
+    for (int p = 0; p < 2 * N; p++) {
+        const double p01 = fma(c[1 * 2 * N + p], y, c[0 * 2 * N + p]);
+        const double p23 = fma(c[3 * 2 * N + p], y, c[2 * 2 * N + p]);
+        const double p45 = fma(c[5 * 2 * N + p], y, c[4 * 2 * N + p]);
+        const double p67 = fma(c[7 * 2 * N + p], y, c[6 * 2 * N + p]);
+        const double p89 = fma(c[9 * 2 * N + p], y, c[8 * 2 * N + p]);
+        const double q0 = fma(p23, y2, p01), q1 = fma(p67, y2, p45);
+        const double r0 = fma(q1, y4, q0);
+        const double v = fma(p89, y8, r0);
+        if (p & 1) w[p >> 1] = v; else t2[p >> 1] = v;
     }
-#pragma unroll
-    for (int k = 0; k < N; k++) { t2[k] = v[2 * k]; w[k] = v[2 * k + 1]; }
 }
 
 // ----------------------------------------------------------------------------- HRR in registers
@@ -206,7 +218,7 @@ template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart
 
 // ----------------------------------------------------------------------------- the kernel
 template <int LA, int LB, int LC, int LD, int NCT, int NCU>
-__global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const TileParams P)
+__global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
@@ -293,7 +305,8 @@ __global__ void __launch_bounds__(REG_THREADS) eri_reg_kernel(const TileParams P
 #pragma unroll
             for (int i = 0; i < NCU * NEF; i++) accu[i] = 0.0;
         }
-#pragma unroll 1
+        constexpr int UQ_UNROLL = REG_UQ_UNROLL;
+#pragma unroll UQ_UNROLL
         for (int uq = 0; uq < nppu; uq++) {
             const double *su = s_u + uq * USTR;
             const double aU = su[0], iaU = su[1];

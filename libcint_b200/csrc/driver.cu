@@ -355,7 +355,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                         plan->launches.push_back(L2);
                     }
                 } else {
-                    if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off()))
+                    if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off(), c->omega < 0))
                         return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits", T.la, T.lb, U.la, U.lb);
                     scratch_need = std::max(scratch_need, L.GC.scratch_per_block * (size_t)L.GL.grid);
                     plan->launches.push_back(L);
@@ -373,7 +373,6 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (nranks < 1 || rank < 0 || rank >= nranks) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
-    if (c->omega < 0) return b200_fail(CINTB200_ENOSUP, "short-range Coulomb not implemented in this build");
     std::lock_guard<std::mutex> lock(c->mtx);
     CU_OK(cudaSetDevice(c->device));
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;

@@ -356,8 +356,6 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (n == 0) return 0;
     if (!shls || !out) return b200_fail(CINTB200_EINVAL, "NULL shls/out");
-    if (c->omega < 0)
-        return b200_fail(CINTB200_ENOSUP, "short-range Coulomb (env[PTR_RANGE_OMEGA] < 0) is not implemented in this build");
     const int cart = (kind == CINTB200_CART);
     std::lock_guard<std::mutex> lock(c->mtx);
     CUDA_OK(cudaSetDevice(c->device));
@@ -423,7 +421,7 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         while (end < n && !(k0 < keys[order[end]]) && !(keys[order[end]] < k0)) end++;
         GenericClass C;
         GenericLaunch L;
-        if (generic_plan(&C, &L, k0.la, k0.lb, k0.lc, k0.ld, k0.ncab, k0.nccd, cart, (long long)(end - start), C2S_OFF))
+        if (generic_plan(&C, &L, k0.la, k0.lb, k0.lc, k0.ld, k0.ncab, k0.nccd, cart, (long long)(end - start), C2S_OFF, c->omega < 0))
             return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits (nroots <= %d)",
                              k0.la, k0.lb, k0.lc, k0.ld, RYS_NMAX);
         if (C.scratch_per_block) {

@@ -107,13 +107,17 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
     const int tid = threadIdx.x;
     const int la = C.la, lb = C.lb, lc = C.lc, ld = C.ld;
     const int nmax = la + lb, mmax = lc + ld, nroots = C.nroots;
+    // short-range Coulomb (omega < 0): erfc = 1 - erf, evaluated as the full-Coulomb rule plus the long-range rule
+    // with negated weights, i.e. 2*nroots quadrature points.  The reference does the same for order <= 3
+    // (src/g2e.c:4455-4476) and switches to dedicated erfc roots above; the combined rule is exact for every order.
+    const int nreff = C.nreff;
     const int nE = C.nE, nF = C.nF, nEF = nE * nF;
     const int ncomb = C.ncab * C.nccd;
     const int gstride_r = (nmax + 1) * (mmax + 1);
 
     double *s_rw = sm;                                   // [2*nroots]  t2,w interleaved as p
-    double *s_g = s_rw + 2 * nroots;                     // [3][nroots][nmax+1][mmax+1]
-    int *s_ecomp = (int *)(s_g + 3 * nroots * gstride_r);   // [nE], [nF] packed exponents
+    double *s_g = s_rw + 2 * nreff;                      // [3][nreff][nmax+1][mmax+1]
+    int *s_ecomp = (int *)(s_g + 3 * nreff * gstride_r);   // [nE], [nF] packed exponents
     int *s_fcomp = s_ecomp + nE;
     double *s_dyn = (double *)(s_fcomp + nF + ((nE + nF) & 1));
     double *gscratch = C.scratch + (size_t)blockIdx.x * C.scratch_per_block;
@@ -164,17 +168,22 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
                 double x = a0 * (dx * dx + dy * dy + dz * dz);
                 double fac1 = common * pb.kij * pk.kij * sqrt(a0 / (a1 * a1 * a1));
                 double theta = 1.0;
-                if (P.omega > 0) {              // long-range attenuation, src/g2e.c:4477-4492
-                    theta = P.omega * P.omega / (P.omega * P.omega + a0);
+                const bool lr = P.omega > 0, sr = P.omega < 0;
+                if (P.omega != 0) theta = P.omega * P.omega / (P.omega * P.omega + a0);
+                if (lr) {                       // long-range attenuation, src/g2e.c:4477-4492
                     x *= theta;
                     fac1 *= sqrt(theta);
                 }
                 __syncthreads();                // previous primitive's G fully consumed
                 if (tid < 2 * nroots) s_rw[tid] = rys_value(P.rys_coef, nroots, x, tid);
+                else if (sr && tid < 4 * nroots) s_rw[tid] = rys_value(P.rys_coef, nroots, x * theta, tid - 2 * nroots);
                 __syncthreads();
-                if (tid < 3 * nroots) {
+                if (tid < 3 * nreff) {
                     const int r = tid / 3, xyz = tid - 3 * r;
-                    const double s = s_rw[2 * r] * theta;          // t^2 (LR: theta t^2)
+                    const bool second = r >= nroots;                       // long-range half of the SR rule
+                    const double sc = (lr || second) ? theta : 1.0;
+                    const double s = s_rw[2 * r] * sc;                      // t^2 (LR: theta t^2)
+                    const double wgt = second ? -sqrt(theta) * s_rw[2 * r + 1] : s_rw[2 * r + 1];
                     const double sa = s * akl / asum, sk = s * aij / asum;
                     const double b00 = 0.5 * s / asum;
                     const double b10 = 0.5 * (1.0 - sa) / aij;
@@ -184,9 +193,9 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
                     const double qc = (xyz == 0 ? pk.px : (xyz == 1 ? pk.py : pk.pz)) - hk.ra[xyz];
                     const double c00 = pa - sa * pq;
                     const double c0p = qc + sk * pq;
-                    double *g = s_g + (size_t)(xyz * nroots + r) * gstride_r;
+                    double *g = s_g + (size_t)(xyz * nreff + r) * gstride_r;
                     const int ms = mmax + 1;
-                    g[0] = (xyz == 2) ? s_rw[2 * r + 1] * fac1 : 1.0;
+                    g[0] = (xyz == 2) ? wgt * fac1 : 1.0;
                     if (nmax > 0) g[ms] = c00 * g[0];
                     for (int n = 1; n < nmax; n++) g[(n + 1) * ms] = c00 * g[n * ms] + n * b10 * g[(n - 1) * ms];
                     for (int m = 0; m < mmax; m++)
@@ -207,10 +216,10 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
                     const int ox = (ec & 255) * ms + (fc & 255);
                     const int oy = ((ec >> 8) & 255) * ms + ((fc >> 8) & 255);
                     const int oz = ((ec >> 16) & 255) * ms + ((fc >> 16) & 255);
-                    const double *gx = s_g + ox, *gy = s_g + (size_t)nroots * gstride_r + oy,
-                                 *gz = s_g + (size_t)2 * nroots * gstride_r + oz;
+                    const double *gx = s_g + ox, *gy = s_g + (size_t)nreff * gstride_r + oy,
+                                 *gz = s_g + (size_t)2 * nreff * gstride_r + oz;
                     double v = 0;
-                    for (int r = 0; r < nroots; r++)
+                    for (int r = 0; r < nreff; r++)
                         v = fma(gx[r * gstride_r] * gy[r * gstride_r], gz[r * gstride_r], v);
                     for (int ck = 0; ck < C.nccd; ck++) {
                         const double vk = v * __ldg(cck + ck);
@@ -320,12 +329,13 @@ int generic_setup_constants()
 
 // Plan a launch for one class; returns 0 on success.  scratch is (re)allocated by the caller.
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
-                 int cart, long long ntasks, const int *c2s_off_table)
+                 int cart, long long ntasks, const int *c2s_off_table, int short_range)
 {
     memset(C, 0, sizeof *C);
     C->la = la; C->lb = lb; C->lc = lc; C->ld = ld;
     C->nroots = (la + lb + lc + ld) / 2 + 1;
     if (C->nroots > RYS_NMAX) return -1;
+    C->nreff = short_range ? 2 * C->nroots : C->nroots;
     C->ncab = ncab; C->nccd = nccd;
     C->nE = sum_ncart(la, la + lb);
     C->nF = sum_ncart(lc, lc + ld);
@@ -334,7 +344,7 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     C->c2s_off[2] = c2s_off_table[lc]; C->c2s_off[3] = c2s_off_table[ld];
     const size_t nEF = (size_t)C->nE * C->nF;
     const int nmax = la + lb, mmax = lc + ld;
-    size_t fixed = sizeof(double) * (2 * C->nroots + (size_t)3 * C->nroots * (nmax + 1) * (mmax + 1))
+    size_t fixed = sizeof(double) * (2 * C->nreff + (size_t)3 * C->nreff * (nmax + 1) * (mmax + 1))
                  + sizeof(int) * (C->nE + C->nF + 2);
     size_t acc_b = sizeof(double) * nEF * ncab * nccd;
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
@@ -347,7 +357,7 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     if (smem > 200 * 1024) return -1;
     C->scratch_per_block = (C->acc_in_smem ? 0 : nEF * ncab * nccd) + (C->work_in_smem ? 0 : 2 * (size_t)C->work_size);
     int threads = (int)((nEF + 31) / 32 * 32);
-    if (threads < 64) threads = 64;        // >= 3 * nroots for nroots <= 13 needs 39 threads
+    if (threads < 96) threads = 96;        // >= 3 * nreff (<= 66 quadrature points x 3 axes handled by tid < 3*nreff)
     if (threads > 256) threads = 256;
     L->threads = threads;
     L->smem = smem;

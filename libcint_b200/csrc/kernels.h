@@ -7,6 +7,7 @@
 struct GenericClass {           // uniform per launch of eri_generic_kernel
     int la, lb, lc, ld;
     int nroots;
+    int nreff;                  // quadrature points actually summed (2*nroots for short-range Coulomb)
     int ncab, nccd;             // contraction combinations of the bra / ket pair
     int nE, nF;                 // Cartesian components of [e0| (e = la..la+lb) and |f0]
     int acc_in_smem, work_in_smem;
@@ -20,7 +21,7 @@ struct GenericLaunch { int grid, threads; size_t smem; };
 
 int generic_setup_constants();
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
-                 int cart, long long ntasks, const int *c2s_off_table);
+                 int cart, long long ntasks, const int *c2s_off_table, int short_range = 0);
 int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLaunch &L, const Task *tasks,
                    long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream,
                    const TileParams *tile = nullptr, const long long *uprefix = nullptr);

@@ -194,3 +194,44 @@ def test_symmetry_properties():
         c = v2[o2[n]:o2[n] + s2[n]].reshape([d[2], d[3], d[0], d[1]], order="F")
         assert np.abs(a - b.transpose(1, 0, 2, 3)).max() < 1e-13
         assert np.abs(a - c.transpose(2, 3, 0, 1)).max() < 1e-13
+
+
+def test_range_separated_coulomb():
+    # config 5: env[PTR_RANGE_OMEGA] = +omega (erf, long range) / -omega (erfc, short range).
+    # Properties from testsuite/test_cint.py:258-302 (LR + SR == full, checked there to 1e-9) plus element-wise
+    # parity with the oracle.  Our SR is evaluated as full - LR with one 2N-point rule, so its absolute error
+    # scales with the FULL integral: tolerance 1e-12 * max(1, |full| of the block).
+    which, _ = ou.best()
+    cases = [("testbasis", reference_test_basis()), ("c2h6_ccpvtz", cb.load_fixture("c2h6_ccpvtz"))]
+    for name, (atm, bas, env) in cases:
+        nb = len(bas)
+        rng = np.random.default_rng(17)
+        q = rng.integers(0, nb, (250, 4)).astype(np.int32)
+        full, o, s, _ = cb.Context(atm, bas, env).int2e_batch(q)
+        for omega in (0.3, 0.8):
+            env_lr, env_sr = env.copy(), env.copy()
+            env_lr[8], env_sr[8] = omega, -omega
+            lr, _, _, _ = cb.Context(atm, bas, env_lr).int2e_batch(q)
+            sr, _, _, _ = cb.Context(atm, bas, env_sr).int2e_batch(q)
+            assert np.abs(lr + sr - full).max() < 1e-11, (name, omega)
+            want_lr = ou.eval_many(which, "int2e_sph", q[:120], atm, bas, env_lr)
+            want_sr = ou.eval_many("port", "int2e_sph", q[:120], atm, bas, env_sr)
+            for n in range(120):
+                blk = slice(o[n], o[n] + s[n])
+                scale = max(1.0, np.abs(full[blk]).max())
+                assert np.abs(lr[blk] - want_lr[n]).max() <= 1e-12 * scale, (name, omega, "lr", tuple(q[n]))
+                assert np.abs(sr[blk] - want_sr[n]).max() <= 1e-12 * scale, (name, omega, "sr", tuple(q[n]))
+    # whole-job driver with omega != 0 goes through the generic kernel in tile mode
+    atm, bas, env = cb.load_fixture("c2h6_631g")
+    env = env.copy()
+    env[8] = -0.5
+    ctx = cb.Context(atm, bas, env)
+    ctx.all_unique(chunk_bytes=1 << 30)
+    tile, g = ctx.chunk(0)
+    for (i, j, k, l) in [(5, 3, 4, 1), (21, 20, 7, 7), (10, 0, 10, 0)]:
+        r, _ = ctx.pair_offsets(i, j)
+        _, c = ctx.pair_offsets(k, l)
+        want, _ = ou.eval_tuple("port", "int2e_sph", (i, j, k, l), atm, bas, env)
+        d = ou.dims_of(bas, (i, j, k, l))
+        got = tile[r:r + d[0] * d[1], c:c + d[2] * d[3]]
+        assert np.abs(got - want.reshape(got.shape, order="F")).max() < 1e-12

@@ -75,6 +75,13 @@ size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, i
 int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
                                   double *host_sink, double *stats);
 
+/* Host-only planning of the whole job for `rank` of `nranks` (no GPU needed): the static sharding that
+ * cintb200_int2e_sph_all_unique will execute.  out[0] shell quartets, out[1] integrals, out[2] primitive quartets,
+ * out[3] model FLOPs, out[4] tile columns owned by this rank, out[5] tile rows (all pairs), out[6] chunks,
+ * out[7] kernel launches, out[8] bytes of one tile buffer. */
+int cintb200_plan_summary(const int *atm, int natm, const int *bas, int nbas, const double *env,
+                          int rank, int nranks, size_t chunk_bytes, double *out);
+
 /* Measured FP64 FMA peak of the device in TFLOP/s (DFMA-chain microbenchmark run for about `seconds`);
  * the roofline denominator of bench.py, since MEASURED_PEAKS.json has no FP64 entry. */
 int cintb200_fp64_peak(int device, double seconds, double *tflops);

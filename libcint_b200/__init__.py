@@ -224,6 +224,20 @@ def int3c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int3c2e_cart", 3, shls, atm, bas, env, opt, dims, out, cart=True)
 
 
+def plan_summary(atm, bas, env, rank=0, nranks=1, chunk_bytes=0):
+    """Static sharding of the whole job (host only, no GPU): dict of counts for `rank` of `nranks`."""
+    lib = load_library()
+    atm, bas, env = _as_basis(atm, bas, env)
+    out = np.zeros(16)
+    lib.cintb200_plan_summary.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+    rc = lib.cintb200_plan_summary(_p(atm), len(atm), _p(bas), len(bas), _p(env), rank, nranks, chunk_bytes, _p(out))
+    if rc != 0:
+        raise B200Error(lib.cintb200_last_error().decode())
+    keys = ("quartets", "integrals", "prim_quartets", "model_flops", "columns", "rows", "chunks", "launches", "tile_bytes")
+    return dict(zip(keys, out[:9]))
+
+
 def fp64_peak_tflops(device=-1, seconds=0.5):
     """DFMA-chain microbenchmark: the FP64 roofline denominator (TFLOP/s)."""
     lib = load_library()

@@ -54,6 +54,7 @@ struct JobPlan {
     long long *d_uprefix = nullptr; size_t cap_uprefix = 0;
     double *d_scratch = nullptr; size_t cap_scratch = 0;
     int force_generic = 0;
+    int host_only = 0;                      // planning without a device (cintb200_plan_summary)
     std::vector<long long> colof;           // per pair id: this rank's column offset or -1
     std::vector<struct LaunchRec> launches;
     double st_quartets = 0, st_integrals = 0, st_prim = 0, st_flops = 0;
@@ -211,6 +212,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     plan->out_doubles = need;
     // 5. device tables per class
     for (PairClass &pc : plan->classes) {
+        if (plan->host_only) { pc.npp_prefix.assign(1, 0); continue; }
         const size_t NT = pc.ids.size();
         const int nct = pc.nca * pc.ncb, Q = pc.Q;
         std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
@@ -253,6 +255,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
             upload(&pc.d_tnpp, nppc))
             return CINTB200_ENOMEM;
     }
+    if (plan->host_only) return 0;
     for (int b = 0; b < 2; b++)
         if (cudaMalloc((void **)&plan->d_out[b], sizeof(double) * need) != cudaSuccess)
             return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
@@ -363,7 +366,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
             }
         }
     }
-    if (scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
+    if (!plan->host_only && scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate generic-kernel scratch");
     return 0;
 }
@@ -543,4 +546,31 @@ extern "C" int cintb200_debug_profile_rows(cintb200_ctx *c, double *rows, int ma
     const int n = (int)(c->profile_rows.size() / 12);
     if (rows) memcpy(rows, c->profile_rows.data(), sizeof(double) * 12 * std::min(n, max_rows));
     return n;
+}
+
+// Host-only planning: the static sharding of the whole job for `rank` of `nranks`, no GPU needed.
+//   out[0] shell quartets   out[1] integrals   out[2] primitive quartets   out[3] model flops
+//   out[4] columns owned    out[5] total rows  out[6] chunks               out[7] kernel launches
+//   out[8] tile buffer bytes
+extern "C" int cintb200_plan_summary(const int *atm, int natm, const int *bas, int nbas, const double *env,
+                                     int rank, int nranks, size_t chunk_bytes, double *out)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || !out) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
+    CINTOpt *c = nullptr;
+    int rc = ctx_new_host(&c, atm, natm, bas, nbas, env);
+    if (rc) return rc;
+    JobPlan *plan = new JobPlan();
+    plan->rank = rank; plan->nranks = nranks; plan->host_only = 1;
+    plan->chunk_bytes = chunk_bytes ? chunk_bytes : (size_t)16 << 30;
+    rc = build_plan(c, plan);
+    if (!rc) rc = build_launches(c, plan);
+    if (!rc) {
+        out[0] = plan->st_quartets; out[1] = plan->st_integrals; out[2] = plan->st_prim; out[3] = plan->st_flops;
+        out[4] = (double)plan->cols_before[nbas]; out[5] = (double)plan->rows_before[nbas];
+        out[6] = (double)plan->chunks.size(); out[7] = (double)plan->launches.size();
+        out[8] = (double)plan->out_doubles * 8;
+    }
+    jobplan_free(plan);
+    cintb200_destroy(c);
+    return rc;
 }

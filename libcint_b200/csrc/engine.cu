@@ -261,29 +261,20 @@ static int ctx_upload(CINTOpt *c)
     return 0;
 }
 
-extern "C" int cintb200_create(cintb200_ctx **out, const int *atm, int natm, const int *bas, int nbas,
-                               const double *env, int device)
+// host-only part of context construction (validation, copies of the arrays, shell-pair tables)
+int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env)
 {
     if (!out || !atm || !bas || !env || natm <= 0 || nbas <= 0) return b200_fail(CINTB200_EINVAL, "cintb200_create: bad arguments");
     *out = NULL;
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
-        return b200_fail(CINTB200_ENODEV, "no CUDA device available (%s); this library has no CPU path",
-                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    if (device < 0) CUDA_OK(cudaGetDevice(&device));
-    if (device >= ndev) return b200_fail(CINTB200_EINVAL, "device %d out of range (%d devices)", device, ndev);
-    CUDA_OK(cudaSetDevice(device));
     for (int i = 0; i < nbas; i++) {
         if (bas(ANG_OF, i) < 0 || bas(ANG_OF, i) > B200_LMAX)
             return b200_fail(CINTB200_EINVAL, "shell %d: angular momentum %d outside 0..%d", i, bas(ANG_OF, i), B200_LMAX);
         if (bas(NPRIM_OF, i) < 1 || bas(NCTR_OF, i) < 1 || bas(ATOM_OF, i) < 0 || bas(ATOM_OF, i) >= natm)
             return b200_fail(CINTB200_EINVAL, "shell %d: malformed bas entry", i);
     }
-    if (setup_device_constants(device)) return CINTB200_ENODEV;
     CINTOpt *c = new CINTOpt();
     c->magic = B200_CTX_MAGIC;
-    c->device = device;
+    c->device = -1;
     c->natm = natm; c->nbas = nbas;
     c->atm.assign(atm, atm + (size_t)natm * ATM_SLOTS);
     c->bas.assign(bas, bas + (size_t)nbas * BAS_SLOTS);
@@ -295,7 +286,29 @@ extern "C" int cintb200_create(cintb200_ctx **out, const int *atm, int natm, con
     c->expcutoff3 = (e0 == 0) ? 60.0 : std::max(40.0, e0);
     c->omega = env[PTR_RANGE_OMEGA];
     build_pairs(c);
-    int rc = ctx_upload(c);
+    *out = c;
+    return 0;
+}
+
+extern "C" int cintb200_create(cintb200_ctx **out, const int *atm, int natm, const int *bas, int nbas,
+                               const double *env, int device)
+{
+    if (!out) return b200_fail(CINTB200_EINVAL, "cintb200_create: bad arguments");
+    *out = NULL;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return b200_fail(CINTB200_ENODEV, "no CUDA device available (%s); this library has no CPU path",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    if (device >= ndev) return b200_fail(CINTB200_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    if (setup_device_constants(device)) return CINTB200_ENODEV;
+    CINTOpt *c = NULL;
+    int rc = ctx_new_host(&c, atm, natm, bas, nbas, env);
+    if (rc) return rc;
+    c->device = device;
+    rc = ctx_upload(c);
     if (rc) { cintb200_destroy(c); return rc; }
     *out = c;
     return 0;
@@ -304,6 +317,12 @@ extern "C" int cintb200_create(cintb200_ctx **out, const int *atm, int natm, con
 extern "C" void cintb200_destroy(cintb200_ctx *c)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return;
+    if (c->device < 0) {            // host-only context (planning without a GPU)
+        if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
+        c->magic = 0;
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_c2s);

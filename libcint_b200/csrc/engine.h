@@ -48,5 +48,6 @@ struct CINTOpt {
 
 struct JobPlan;
 void jobplan_free(JobPlan *p);
+int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);
 int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_host);

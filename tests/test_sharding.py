@@ -1,0 +1,84 @@
+"""CPU tests of the multi-GPU host logic (no GPU): static sharding of the whole job across ranks.
+World-size-2 run over torch.distributed `gloo`, rendezvous on 127.0.0.1 -- the same reduction of per-rank
+counts that bench.py performs over NCCL."""
+import os
+import socket
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import libcint_b200 as cb
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    atm, bas, env = cb.load_fixture(name)
+    s = cb.plan_summary(atm, bas, env, rank=rank, nranks=world)
+    t = torch.tensor([s["quartets"], s["integrals"], s["prim_quartets"], s["model_flops"], s["columns"]], dtype=torch.float64)
+    mx = t.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        q.put((t.tolist(), mx.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c60_ccpvdz", "c2h6_ccpvtz"])
+def test_two_rank_sharding_gloo(name):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    tot, mx = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    atm, bas, env = cb.load_fixture(name)
+    one = cb.plan_summary(atm, bas, env)
+    # the shards partition the job exactly ...
+    assert tot[0] == one["quartets"] and tot[1] == one["integrals"] and tot[2] == one["prim_quartets"]
+    assert tot[4] == one["columns"]
+    assert abs(tot[3] - one["model_flops"]) <= 1e-9 * one["model_flops"]
+    # ... and evenly: round-robin dealing inside lists sorted by primitive count slightly favours rank 0 on tiny
+    # molecules (few pairs per class); on the benchmark molecule the slowest rank stays within 0.5% of the mean
+    assert mx[3] / one["model_flops"] < (0.505 if name == "c60_ccpvdz" else 0.53)
+    nbas = len(bas)
+    assert one["quartets"] == sum((i + 1) * (i + 1) * (i + 2) // 2 for i in range(nbas))
+
+
+def test_sharding_balance_up_to_8_ranks():
+    atm, bas, env = cb.load_fixture("c60_ccpvdz")
+    one = cb.plan_summary(atm, bas, env)
+    assert one["quartets"] == 1023783775          # examples/time_c60.c:200-207
+    assert one["integrals"] == 63085726860        # integrals actually produced by the loop
+    for n in (2, 4, 8):
+        parts = [cb.plan_summary(atm, bas, env, rank=r, nranks=n) for r in range(n)]
+        assert sum(p["quartets"] for p in parts) == one["quartets"]
+        assert sum(p["columns"] for p in parts) == one["columns"]
+        worst = max(p["model_flops"] for p in parts) * n / one["model_flops"]
+        assert worst < 1.02, (n, worst)           # static, cost-balanced: < 2% above the mean
+
+
+def test_chunking_respects_budget():
+    atm, bas, env = cb.load_fixture("c2h6_ccpvdz")
+    big = cb.plan_summary(atm, bas, env, chunk_bytes=1 << 30)
+    small = cb.plan_summary(atm, bas, env, chunk_bytes=200_000)
+    assert big["chunks"] == 1 and small["chunks"] > 5
+    assert small["quartets"] == big["quartets"] and small["integrals"] == big["integrals"]
+    # a chunk never holds less than one bra shell, so the buffer may exceed a tiny budget, but not by much
+    assert small["tile_bytes"] < 4 * 200_000

@@ -80,5 +80,6 @@ def test_chunking_respects_budget():
     small = cb.plan_summary(atm, bas, env, chunk_bytes=200_000)
     assert big["chunks"] == 1 and small["chunks"] > 5
     assert small["quartets"] == big["quartets"] and small["integrals"] == big["integrals"]
-    # a chunk never holds less than one bra shell, so the buffer may exceed a tiny budget, but not by much
-    assert small["tile_bytes"] < 4 * 200_000
+    # a chunk never holds less than one bra shell x all kets, so a tiny budget is exceeded -- but the buffer
+    # shrinks to that minimum
+    assert small["tile_bytes"] < big["tile_bytes"] / 5

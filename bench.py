@@ -155,7 +155,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each moves ~505/N GB to the host)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--chunk-gb", type=float, default=16.0)
+    ap.add_argument("--chunk-gb", type=float, default=80.0, help="device-resident tile buffer (one buffer)")
+    ap.add_argument("--e2e-chunk-gb", type=float, default=16.0, help="tile / pinned sink size of the end-to-end mode (two device buffers)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -254,7 +255,7 @@ def main():
     # ---------------- end to end: host arrays in, every integral delivered to pinned host memory ----------------
     e2e = None
     if not args.no_e2e:
-        e2e_chunk = chunk          # one bra shell x all kets of C60 needs 11.9 GB, so the sink is a full chunk
+        e2e_chunk = int(args.e2e_chunk_gb * (1 << 30))          # one bra shell x all kets of C60 needs 11.9 GB
         sink = torch.empty(e2e_chunk // 8, dtype=torch.float64, pin_memory=True)
         h2d = atm.nbytes + bas.nbytes + env.nbytes
 

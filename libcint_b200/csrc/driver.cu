@@ -256,9 +256,9 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
             return CINTB200_ENOMEM;
     }
     if (plan->host_only) return 0;
-    for (int b = 0; b < 2; b++)
-        if (cudaMalloc((void **)&plan->d_out[b], sizeof(double) * need) != cudaSuccess)
-            return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
+    // one tile buffer; the second one (overlap of D2H with the next chunk's kernels) is allocated on first use of a host sink
+    if (cudaMalloc((void **)&plan->d_out[0], sizeof(double) * need) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
     CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
         CU_OK(cudaEventCreateWithFlags(&plan->ev_done[b], cudaEventDisableTiming));
@@ -389,6 +389,8 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
         if (rc) { jobplan_free(plan); return rc; }
         c->plan = plan;
     }
+    if (host_sink && !plan->d_out[1] && cudaMalloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cannot allocate the second %zu-byte tile buffer", sizeof(double) * plan->out_doubles);
     if (host_sink && plan->out_doubles * sizeof(double) > chunk_bytes)
         return b200_fail(CINTB200_EINVAL, "host_sink mode: the largest tile (one bra shell x all kets) needs %zu bytes, "
                          "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
@@ -438,7 +440,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
     size_t li = 0;
     for (LaunchRec &L : plan->launches) {
         if (L.chunk != cur_chunk) {
-            if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; buf ^= 1; }
+            if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; if (host_sink) buf ^= 1; }
             cur_chunk = L.chunk;
             if (host_sink) CU_OK(cudaStreamWaitEvent(st, plan->ev_copied[buf], 0));   // buffer drained?
             if (fork()) return CINTB200_ENODEV;
@@ -514,12 +516,9 @@ extern "C" int cintb200_debug_chunk(cintb200_ctx *c, int chunk, double *host_out
     if (!host_out) return 0;
     if (n > host_cap) return b200_fail(CINTB200_EINVAL, "host buffer too small");
     // chunks alternate between the two buffers in evaluation order
-    int buf = 0;
-    for (int k = 0; k < chunk; k++) {
-        const long long ld = plan->rows_before[plan->chunks[k].second] - plan->rows_before[plan->chunks[k].first];
-        if (ld == 0 || plan->chunk_cols[k] == 0) continue;
-        buf ^= 1;
-    }
+    // without a host sink every chunk is evaluated into buffer 0, so only the LAST chunk is still resident
+    const int buf = 0;
+    if (chunk != (int)plan->chunks.size() - 1) return b200_fail(CINTB200_EINVAL, "only the last chunk stays resident");
     CU_OK(cudaSetDevice(c->device));
     CU_OK(cudaMemcpy(host_out, plan->d_out[buf], sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;

@@ -100,3 +100,51 @@ def unique_quartets(nbas):
                 for l in range(k + 1):
                     out.append((i, j, k, l))
     return np.array(out, np.int32)
+
+
+def c60_df_basis(max_atoms=60, aux_lmax=4):
+    """Config 3 stand-in (SURVEY 8d / hard part 7): C60 geometry of examples/time_c60.c with the carbon cc-pVTZ
+    shells of examples/time_c2h6.c (taken from the committed fixtures) as orbital basis, plus an EVEN-TEMPERED
+    auxiliary basis per atom (the def2-universal-JKFIT exponents are not available offline):
+    l = 0..aux_lmax, exponents 0.25 * 2.2^k, k = 0..(5 - l), one uncontracted primitive per shell.
+    Returns atm, bas, env, n_orbital_shells."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+    c60 = np.load(os.path.join(here, "c60_ccpvdz.npz"))
+    tz = np.load(os.path.join(here, "c2h6_ccpvtz.npz"))
+    atm60, env60 = c60["atm"], c60["env"]
+    tbas, tenv = tz["bas"], tz["env"]
+    cshells = [b for b in tbas if b[0] == 0]              # shells of the first carbon atom
+    natm = min(max_atoms, 60)
+    atm = np.zeros((natm, 6), np.int32)
+    env = [0.0] * PTR_ENV_START
+    for i in range(natm):
+        atm[i, 0] = 6
+        atm[i, 1] = len(env)
+        env += list(env60[atm60[i, 1]:atm60[i, 1] + 3])
+    bas = []
+    ptr = {}
+    for b in cshells:                                     # share exponent/coefficient storage between atoms
+        key = (int(b[5]), int(b[6]))
+        if key not in ptr:
+            pe = len(env)
+            env += list(tenv[b[5]:b[5] + b[2]])
+            pc = len(env)
+            env += list(tenv[b[6]:b[6] + b[2] * b[3]])
+            ptr[key] = (pe, pc)
+    for i in range(natm):
+        for b in cshells:
+            pe, pc = ptr[(int(b[5]), int(b[6]))]
+            bas.append([i, int(b[1]), int(b[2]), int(b[3]), 0, pe, pc, 0])
+    norb = len(bas)
+    aux = {}
+    for l in range(aux_lmax + 1):
+        for k in range(6 - l):
+            a = 0.25 * 2.2 ** k
+            pe = len(env)
+            env += [a, gto_norm(l, a)]
+            aux[(l, k)] = (pe, pe + 1)
+    for i in range(natm):
+        for (l, k), (pe, pc) in aux.items():
+            bas.append([i, l, 1, 1, 0, pe, pc, 0])
+    return atm, np.array(bas, np.int32), np.array(env), norb

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(c
             const double *su = s_u + uq * USTR;
             const double aU = su[0], iaU = su[1];
             const double asum = aT + aU;
-            const double rs = rsqrt(asum);
+            const double rs = fast_rsqrt(asum);
             const double inv = rs * rs;
             // register side = "bra" of the recurrences, lane side = "ket"
             const double aR = REG_IS_T ? aT : aU, aL = REG_IS_T ? aU : aT;

@@ -94,6 +94,9 @@ __host__ __device__ constexpr int cx_hrr_off(int l0, int le, int j)   // offset 
 
 
 #define REG_THREADS 128
+#ifndef REG_ACC_SMEM_MAX
+#define REG_ACC_SMEM_MAX 0       // >0: keep outer accumulators of contracted-T classes in smem (measured: no gain, off)
+#endif
 #ifndef REG_UQ_UNROLL
 #define REG_UQ_UNROLL 1          // unroll factor of the inner (U) primitive loop
 #endif
@@ -106,25 +109,22 @@ __host__ __device__ constexpr int cx_hrr_off(int l0, int le, int j)   // offset 
 __host__ __device__ constexpr int rys_smem_stride(int n) { return (RYS_DEG + 1) * 2 * n + 1; }
 
 template <int N>
-__device__ __forceinline__ void rys_roots_smem(const double *tab, double x, double (&t2)[N], double (&w)[N])
+__device__ __forceinline__ void rys_roots_smem(const double *tab, int nint, double x, double (&t2)[N], double (&w)[N])
 {
-    if (x >= 35.0 + 5.0 * N) {
-        const double isx = rsqrt(x);            // t^2 = r/x, w = v/sqrt(x)
-        const double ix = isx * isx;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            t2[k] = c_rys_lx_r[N * (N - 1) / 2 + k] * ix;
-            w[k] = c_rys_lx_v[N * (N - 1) / 2 + k] * isx;
-        }
-        return;
-    }
+    // BRANCH-FREE on purpose: the table polynomials and the large-x form are both evaluated and selected, so the
+    // primitive loop body stays one basic block and the scheduler can overlap this latency-bound chain with the
+    // VRR / quadrature arithmetic of the neighbouring iteration (ncu: these kernels stall on fixed-latency
+    // dependencies, not on FP64 issue bandwidth).  Cost: one rsqrt and 2N multiplies per primitive quartet.
+    const bool large = x >= 35.0 + 5.0 * N;
+    const double isx = fast_rsqrt(large ? x : 1.0);          // t^2 = r/x, w = v/sqrt(x)
+    const double ix = isx * isx;
     int idx;
     double y;
-    rys_locate(x, idx, y);
+    rys_locate(large ? 0.0 : x, idx, y);
+    (void)nint;
     const double *c = tab + idx * rys_smem_stride(N);
     static_assert(RYS_DEG == 9, "Estrin scheme below is written for degree 9");
-    // Estrin evaluation: depth 4 instead of Horner's 9 dependent FMAs -- these kernels stall on fixed-latency
-    // dependencies (ncu: warp "wait" stalls dominate), not on FP64 issue bandwidth
+    // Estrin evaluation: depth 4 instead of Horner's 9 dependent FMAs
     const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
 #pragma unroll
     for (int p = 0; p < 2 * N; p++) {
@@ -136,7 +136,8 @@ __device__ __forceinline__ void rys_roots_smem(const double *tab, double x, doub
         const double q0 = fma(p23, y2, p01), q1 = fma(p67, y2, p45);
         const double r0 = fma(q1, y4, q0);
         const double v = fma(p89, y8, r0);
-        if (p & 1) w[p >> 1] = v; else t2[p >> 1] = v;
+        if (p & 1) w[p >> 1] = large ? c_rys_lx_v[N * (N - 1) / 2 + (p >> 1)] * isx : v;
+        else t2[p >> 1] = large ? c_rys_lx_r[N * (N - 1) / 2 + (p >> 1)] * ix : v;
     }
 }
 
@@ -217,8 +218,14 @@ __device__ __forceinline__ void c2s_reg(const double *in, double *out)
 template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart(L) : 2 * L + 1; };
 
 // ----------------------------------------------------------------------------- the kernel
+// Classes whose T pair is generally contracted (NCT > 1) update the outer accumulators only once per T primitive:
+// they are kept in SHARED memory (layout [i][thread], conflict-free) when small enough, which frees 2*NACC registers
+// and lets three blocks share an SM instead of two.
+__host__ __device__ constexpr bool reg_acc_in_smem(int nct, int nacc) { return nct > 1 && nacc <= REG_ACC_SMEM_MAX; }
+
 template <int LA, int LB, int LC, int LD, int NCT, int NCU>
-__global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(const TileParams P)
+__global__ void __launch_bounds__(REG_THREADS, reg_acc_in_smem(NCT, NCT * NCU * cx_nrange(LA, LA + LB) * cx_nrange(LC, LC + LD)) ? 3 : REG_MIN_BLOCKS)
+eri_reg_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
@@ -281,9 +288,16 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(co
         * (LC == 0 ? fsp0 : LC == 1 ? fsp1 : 1.0) * (LD == 0 ? fsp0 : LD == 1 ? fsp1 : 1.0);
 
     constexpr int NACC = NCT * NCU * NEF;
-    double acc[NACC];
+    constexpr bool ACC_SMEM = reg_acc_in_smem(NCT, NACC);
+    double acc[ACC_SMEM ? 1 : NACC];
+    double *s_acc = s_u + REG_MAXU * USTR + tid;         // [NACC][REG_THREADS]
+    if constexpr (ACC_SMEM) {
 #pragma unroll
-    for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+        for (int i = 0; i < NACC; i++) s_acc[i * REG_THREADS] = 0.0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NACC; i++) acc[i] = 0.0;
+    }
 
     const int nppu = hu.npp;
     for (int tq = 0; tq < Qb; tq++) {
@@ -311,7 +325,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(co
             const double *su = s_u + uq * USTR;
             const double aU = su[0], iaU = su[1];
             const double asum = aT + aU;
-            const double rs = rsqrt(asum);
+            const double rs = fast_rsqrt(asum);
             const double inv = rs * rs;
             const double pq[3] = {ptx - su[2], pty - su[3], ptz - su[4]};
             const double qc[3] = {su[5], su[6], su[7]};
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(co
             const double x = a0 * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
             const double fac = common * kT * su[8] * iaT * iaU * rs;
             double t2[N], w[N];
-            rys_roots_smem<N>(s_rys, x, t2, w);
+            rys_roots_smem<N>(s_rys, nint, x, t2, w);
             const double rho_u = aU * inv, rho_t = aT * inv;
             double val[(NCU == 1) ? 1 : NEF];
             if constexpr (NCU > 1) {
@@ -389,7 +403,10 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(co
 #pragma unroll
             for (int ct = 0; ct < NCT; ct++)
 #pragma unroll
-                for (int i = 0; i < NCU * NEF; i++) acc[ct * NCU * NEF + i] = fma(ccT[ct], accu[i], acc[ct * NCU * NEF + i]);
+                for (int i = 0; i < NCU * NEF; i++) {
+                    if constexpr (ACC_SMEM) s_acc[(ct * NCU * NEF + i) * REG_THREADS] = fma(ccT[ct], accu[i], s_acc[(ct * NCU * NEF + i) * REG_THREADS]);
+                    else acc[ct * NCU * NEF + i] = fma(ccT[ct], accu[i], acc[ct * NCU * NEF + i]);
+                }
         }
     }
     if (!active) return;
@@ -404,13 +421,18 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_reg_kernel(co
         const int ct = comb / NCU, cu = comb - ct * NCU;
         // select the accumulator block of this combination (dynamic index -> predicated copies)
         double ef[NEF];
-        static_for<NCT * NCU>([&](auto CI) {
-            constexpr int ci = decltype(CI)::value;
-            if (comb == ci) {
+        if constexpr (ACC_SMEM) {
 #pragma unroll
-                for (int i = 0; i < NEF; i++) ef[i] = acc[ci * NEF + i];
-            }
-        });
+            for (int i = 0; i < NEF; i++) ef[i] = s_acc[(comb * NEF + i) * REG_THREADS];
+        } else {
+            static_for<NCT * NCU>([&](auto CI) {
+                constexpr int ci = decltype(CI)::value;
+                if (comb == ci) {
+#pragma unroll
+                    for (int i = 0; i < NEF; i++) ef[i] = acc[ci * NEF + i];
+                }
+            });
+        }
         double abf[NFA * NFB * NF];
         hrr_pair_reg<LA, LB, 1, NF>(ef, abf, abT);                   // [ab][F]
         double abcd[NFA * NFB * NFC * NFD];

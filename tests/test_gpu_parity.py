@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import oracle_util as ou
 import libcint_b200 as cb
-from libcint_b200.basis import reference_test_basis, class_sweep_basis, unique_quartets
+from libcint_b200.basis import reference_test_basis, class_sweep_basis, unique_quartets, c60_df_basis
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -235,3 +235,44 @@ def test_range_separated_coulomb():
         d = ou.dims_of(bas, (i, j, k, l))
         got = tile[r:r + d[0] * d[1], c:c + d[2] * d[3]]
         assert np.abs(got - want.reshape(got.shape, order="F")).max() < 1e-12
+
+
+def test_class_sweep_with_h_shells():
+    # config 4 upper end: classes containing h shells (nroots up to 11), contracted 3 prim x 2 ctr
+    atm, bas, env = class_sweep_basis(lmax=5)
+    nsh = 6
+    q = np.array([[5, 6 + 0, 12 + 5, 18 + 0],      # (hs|hs)  nroots 6
+                  [5, 6 + 5, 12 + 0, 18 + 0],      # (hh|ss)  nroots 6
+                  [5, 6 + 1, 12 + 2, 18 + 2],      # (hp|dd)  nroots 6
+                  [5, 6 + 4, 12 + 3, 18 + 5],      # (hg|fh)  nroots 9
+                  [4, 6 + 5, 12 + 5, 18 + 4]],     # (gh|hg)  nroots 10
+                 np.int32)
+    ctx = cb.Context(atm, bas, env)
+    v, o, s, nz = ctx.int2e_batch(q)
+    want = ou.eval_many("port", "int2e_sph", q, atm, bas, env)       # extended-precision roots: tight tolerance
+    assert_blocks_close(split(v, o, s), want, q, tol=TOL, what="h classes vs port")
+    if ou.ref() is not None:                                          # the reference's roots: ~1e-11 for nroots >= 7
+        wantr = ou.eval_many("ref", "int2e_sph", q, atm, bas, env)
+        assert_blocks_close(split(v, o, s), wantr, q, tol=1e-10, what="h classes vs reference")
+    # one uncontracted (hh|hh) quartet: nroots 11, 14641 spherical integrals
+    atm1, bas1, env1 = class_sweep_basis(lmax=5, nprim=1, nctr=1)
+    q1 = np.array([[5, 11, 17, 23]], np.int32)
+    v1, o1, s1, _ = cb.Context(atm1, bas1, env1).int2e_batch(q1)
+    w1 = ou.eval_many("port", "int2e_sph", q1, atm1, bas1, env1)
+    assert_blocks_close(split(v1, o1, s1), w1, q1, tol=TOL, what="(hh|hh)")
+
+
+def test_int3c2e_density_fitting_sample():
+    # config 3 stand-in: C60 geometry, carbon cc-pVTZ orbital shells, even-tempered s..g auxiliary shells
+    which, _ = ou.best()
+    atm, bas, env, norb = c60_df_basis(max_atoms=12)
+    naux = len(bas) - norb
+    rng = np.random.default_rng(33)
+    t = np.stack([rng.integers(0, norb, 400), rng.integers(0, norb, 400), norb + rng.integers(0, naux, 400)], 1).astype(np.int32)
+    ctx = cb.Context(atm, bas, env)
+    v, o, s, nz = ctx.int3c2e_batch(t)
+    want = ou.eval_many(which, "int3c2e_sph", t, atm, bas, env)
+    assert_blocks_close(split(v, o, s), want, t, tol=1e-11 if which == "ref" else TOL, what="int3c2e df")
+    v, o, s, nz = ctx.int3c2e_batch(t[:100], kind=cb.CART)
+    want = ou.eval_many(which, "int3c2e_cart", t[:100], atm, bas, env)
+    assert_blocks_close(split(v, o, s), want, t[:100], tol=1e-11 if which == "ref" else TOL, what="int3c2e cart")

@@ -245,7 +245,8 @@ def main():
             "kernel_share_of_step": top[7] / tot_ms,
             "kernel_ms_per_step": top[7], "kernel_launches_per_step": int(top[11]),
             "flop_model": "SURVEY.md 8(d): F(class) per executed primitive quartet + 4 nf nc per contracted quartet",
-            "whole_job": {"achieved": flops / (step_ms * 1e-3) / 1e12, "frac": flops / (step_ms * 1e-3) / 1e12 / peak,
+            "whole_job": {"achieved": flops / (step_ms * 1e-3) / 1e12, "frac": flops / (step_ms * 1e-3) / 1e12 / (peak * world),
+                          "peak": peak * world,
                           "model_flops_per_step": flops, "primitive_quartets": prim},
             "hbm_store": {"achieved_gbs": 8 * produced / (step_ms * 1e-3) / 1e9 / world, "peak_gbs": hbm,
                           "frac": 8 * produced / (step_ms * 1e-3) / 1e9 / world / hbm,

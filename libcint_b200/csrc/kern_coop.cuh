@@ -18,16 +18,20 @@
 #include "kern_reg.cuh"
 
 // per-(root,axis) G block padded to an odd number of doubles so the 3N lanes that write them hit distinct banks
+// resident blocks per SM the compiler must allow, by accumulator count per lane (measured per class on C60:
+// small-accumulator classes gain 20-25% from 3-4 blocks, the (dd|x) classes with 62 accumulators lose from spills)
+__host__ __device__ constexpr int coop_min_blocks(int nacc) { return nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2; }
+
 __host__ __device__ constexpr int coop_g_task(int nmax, int mmax) { return ((nmax + 1) * (mmax + 1)) | 1; }
 __host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * coop_g_task(nmax, mmax); }
 __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, int nab)
 {
-    int a = nf * nab, b = coop_g_size(n, nmax, mmax) + 2 * n;
+    int a = (nf | 1) * nab, b = coop_g_size(n, nmax, mmax) + 2 * n;
     return (a > b ? a : b) | 1;
 }
 
 template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T>
-__global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(const TileParams P)
+__global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
@@ -42,6 +46,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(c
     constexpr int GT = coop_g_task(NMAX, MMAX);
     constexpr int XSZ = coop_xsz(N, NMAX, MMAX, NF, NAB);       // per-quartet smem (G + roots, reused for the exchange)
     constexpr int MS = MMAX + 1;
+    constexpr int NFP = NF | 1;                                 // odd row stride of the exchange buffer (bank conflicts)
     static_assert(NF <= FS, "lane side has more components than lanes");
     static_assert(FS <= 32 && (FS & (FS - 1)) == 0, "FS must be a power of two within a warp");
 
@@ -271,7 +276,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(c
         // exchange: X[mab][f]
         if (lane < NF) {
 #pragma unroll
-            for (int i = 0; i < NAB; i++) s_q[i * NF + lane] = p2[i];
+            for (int i = 0; i < NAB; i++) s_q[i * NFP + lane] = p2[i];
         }
         __syncwarp();
         const int ca = cr % nca_r, cb = cr / nca_r, cc = cl % nca_l, cd = cl / nca_l;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(REG_THREADS, REG_MIN_BLOCKS) eri_coop_kernel(c
         for (int mab = lane; mab < NAB; mab += FS) {
             double fr[NF];
 #pragma unroll
-            for (int f = 0; f < NF; f++) fr[f] = s_q[mab * NF + f];
+            for (int f = 0; f < NF; f++) fr[f] = s_q[mab * NFP + f];
             double cdc[NFC * NFD];
             hrr_pair_reg<LC, LD, 1, 1>(fr, cdc, abL);
             double s3[DC * NFD];

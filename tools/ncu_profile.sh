@@ -12,7 +12,7 @@ import libcint_b200 as cb
 atm, bas, env = cb.load_fixture("c60_ccpvdz")
 ctx = cb.Context(atm, bas, env)
 ctx.lib.cintb200_debug_profile(ctx.handle, 1)      # single stream: launches serialised like the timed profile pass
-st = ctx.all_unique(chunk_bytes=16 << 30)
+st = ctx.all_unique(chunk_bytes=80 << 30)
 print("gpu ms", st[7], "launches", st[4])
 PY
 for what in "$@"; do
@@ -27,9 +27,10 @@ full)
     ncu -i /tmp/prof_$1.ncu-rep --page source --csv > gpurun_out/prof_$1_${ROUND}_source.csv 2>/dev/null
     ncu -i /tmp/prof_$1.ncu-rep --page details > gpurun_out/prof_$1_${ROUND}_details.txt 2>/dev/null
   }
-  capture reg_psps eri_reg_kernelILi1ELi0ELi1ELi0ELi2ELi2E 300
-  capture coop_dpdp eri_coop_kernelILi2ELi1ELi2ELi1E 60
-  capture reg_ssss eri_reg_kernelILi0ELi0ELi0ELi0ELi4ELi4E 300
+  capture reg_psps eri_reg_kernelILi1ELi0ELi1ELi0ELi2ELi2E 4
+  capture coop_ppdp eri_coop_kernelILi2ELi1ELi1ELi1ELi1ELi1ELi16ELb0E 3
+  capture coop_dpdp eri_coop_kernelILi2ELi1ELi2ELi1E 3
+  capture reg_sssp eri_reg_kernelILi0ELi0ELi1ELi0ELi4ELi2E 4
   ;;
 esac
 done

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     const int tt = t < P.t_end ? t : P.t_end - 1;
     const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);      // see kern_reg.cuh
     if (!__syncthreads_or(active)) return;
-    const int Qb = P.tnpp[t0];
+    const int Qb = __shfl_sync(0xffffffffu, P.tnpp[tt], 0);      // warp-uniform bound, see kern_reg.cuh
 
     // --- smem carve-up: Rys table | U primitives | per-quartet work areas ---
     double *s_rys = smem;

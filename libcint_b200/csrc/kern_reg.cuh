@@ -248,7 +248,9 @@ eri_reg_kernel(const TileParams P)
     // can fail it; the lists are not sorted by shell index inside a chunk, so it is a per-thread predicate
     const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);
     if (!__syncthreads_or(active)) return;
-    const int Qb = P.tnpp[t0];          // lists are sorted by descending primitive count inside a chunk
+    // lists are sorted by descending primitive count inside a chunk: lane 0 of every WARP carries the warp's loop
+    // bound (a chunk often holds fewer T pairs of a class than one block, so a block-wide bound would pad heavily)
+    const int Qb = __shfl_sync(0xffffffffu, P.tnpp[tt], 0);
 
     // --- stage the Rys table of N roots and the U pair's primitives ---
     const int nint = c_rys_meta.nint[N];

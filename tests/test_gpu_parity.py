@@ -133,6 +133,17 @@ def test_c2h6_full_unique_tensor():
         assert_blocks_close(split(v, o, s), want, q, what=name)
 
 
+def test_c2h6_large_bases_sampled():
+    # config 1, larger bases of examples/time_c2h6.c: 6-311G**, cc-pVTZ (f), cc-pVQZ (g), sampled quartets
+    which, _ = ou.best()
+    for name, n in (("c2h6_6311gss", 4000), ("c2h6_ccpvtz", 4000), ("c2h6_ccpvqz", 3000)):
+        atm, bas, env = cb.load_fixture(name)
+        q = np.random.default_rng(4).integers(0, len(bas), (n, 4)).astype(np.int32)
+        v, o, s, nz = cb.Context(atm, bas, env).int2e_batch(q)
+        want = ou.eval_many(which, "int2e_sph", q, atm, bas, env)
+        assert_blocks_close(split(v, o, s), want, q, what=name)
+
+
 def test_class_sweep_s_to_g():
     # config 4: contracted (3 prim x 2 ctr) quartets over l = 0..4 on four centres
     which, _ = ou.best()

@@ -71,6 +71,11 @@ def test_tiles_two_and_three_ranks():
     check_job("c2h6_631g", nranks=3)
 
 
+def test_tiles_c2h6_ccpvtz_mixed_kernels():
+    # f shells: the s/p/d classes use the specialised kernels, everything with an f shell the generic kernel
+    check_job("c2h6_ccpvtz", max_quartets=6000)
+
+
 def test_tiles_multi_chunk():
     # tiny chunk budget -> many chunks; the last two are verified, the quartet count covers all of them
     check_job("c2h6_ccpvdz", chunk_bytes=200_000)

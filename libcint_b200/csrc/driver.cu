@@ -37,6 +37,12 @@ struct PairClass {
     long long *d_trow = nullptr, *d_ucol = nullptr;
     int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr, *d_tnpp = nullptr;
     std::vector<int> chunk_lo;              // first list index of every chunk (+ end)
+    // second ordering of the same pairs for the DIAGONAL kets of a chunk (K inside the chunk's bra shell range):
+    // sorted by the larger shell index (then by primitive count), so the valid bras of a ket are a suffix
+    std::vector<int> idsB, IB, nppB;
+    double *dB_tprim = nullptr, *dB_tgeom = nullptr;
+    long long *dB_trow = nullptr;
+    int *dB_tstride = nullptr, *dB_tI = nullptr, *dB_tpair = nullptr, *dB_tnpp = nullptr;
 };
 
 struct LaunchRec;
@@ -71,6 +77,7 @@ void jobplan_free(JobPlan *p)
     for (PairClass &c : p->classes) {
         cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
+        cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
     }
     cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -173,6 +180,13 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     // 3. inside every chunk range, order each class list by descending primitive count: a block's first
     //    quartet then carries the block's loop bound and neighbouring threads do equal work
     for (PairClass &pc : plan->classes) {
+        {
+            std::vector<int> ob(pc.ids.size());
+            for (size_t k = 0; k < ob.size(); k++) ob[k] = (int)k;
+            std::stable_sort(ob.begin(), ob.end(), [&](int x, int y) { return pc.I[x] != pc.I[y] ? pc.I[x] < pc.I[y] : pc.npp[x] > pc.npp[y]; });
+            pc.idsB.resize(ob.size()); pc.IB.resize(ob.size()); pc.nppB.resize(ob.size());
+            for (size_t k = 0; k < ob.size(); k++) { pc.idsB[k] = pc.ids[ob[k]]; pc.IB[k] = pc.I[ob[k]]; pc.nppB[k] = pc.npp[ob[k]]; }
+        }
         std::vector<int> order(pc.ids.size());
         for (size_t k = 0; k < order.size(); k++) order[k] = (int)k;
         for (auto &ch : plan->chunks) {
@@ -210,49 +224,59 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     }
     plan->cols_before[nbas] = cols;
     plan->out_doubles = need;
-    // 5. device tables per class
+    // 5. device tables per class, for both orderings
     for (PairClass &pc : plan->classes) {
-        if (plan->host_only) { pc.npp_prefix.assign(1, 0); continue; }
         const size_t NT = pc.ids.size();
-        const int nct = pc.nca * pc.ncb, Q = pc.Q;
-        std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
-        std::vector<long long> trow(NT), ucol(NT);
-        std::vector<int> tstride(2 * NT);
         pc.npp_prefix.assign(NT + 1, 0);
-        for (size_t n = 0; n < NT; n++) {
-            const int p = pc.ids[n];
-            const PairHdr &h = c->pairs[p];
-            pc.npp_prefix[n + 1] = pc.npp_prefix[n] + h.npp;
-            for (int d = 0; d < 3; d++) { tgeom[d * NT + n] = h.ra[d]; tgeom[(3 + d) * NT + n] = h.ab[d]; }
-            for (int q = 0; q < Q; q++) {
-                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
-                if (q < h.npp) {
-                    const PrimPair &pp = c->prims[h.pp_off + q];
-                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
-                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
-                    tprim[5 * F + o] = pp.kij;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
-                } else {            // zero-weight padding primitive
-                    tprim[o] = 1.0; tprim[F + o] = 1.0;
-                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
-                    tprim[5 * F + o] = 0.0;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+        for (size_t n = 0; n < NT; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
+        if (plan->host_only) continue;
+        const int nct = pc.nca * pc.ncb, Q = pc.Q;
+        auto build = [&](const std::vector<int> &ids, const std::vector<int> &I, const std::vector<int> &npp,
+                         double **d_tprim, double **d_tgeom, long long **d_trow, int **d_tstride, int **d_tI,
+                         int **d_tpair, int **d_tnpp, long long **d_ucol, int **d_ustride) -> int {
+            std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
+            std::vector<long long> trow(NT), ucol(NT);
+            std::vector<int> tstride(2 * NT);
+            for (size_t n = 0; n < NT; n++) {
+                const int p = ids[n];
+                const PairHdr &h = c->pairs[p];
+                for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
+                for (int q = 0; q < Q; q++) {
+                    const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
+                    if (q < h.npp) {
+                        const PrimPair &pp = c->prims[h.pp_off + q];
+                        tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
+                        tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
+                        tprim[5 * F + o] = pp.kij;
+                        for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
+                    } else {            // zero-weight padding primitive
+                        tprim[o] = 1.0; tprim[F + o] = 1.0;
+                        tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
+                        tprim[5 * F + o] = 0.0;
+                        for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+                    }
                 }
+                // strides of the canonical indices inside the (i,j) block: i fastest
+                const int i = I[n];
+                const ShellInfo &si = c->shells[i];
+                const int di = (2 * si.l + 1) * si.nctr;
+                const bool a_is_i = (h.sh_a == i);
+                tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
+                trow[n] = plan->rowoff[p];
+                ucol[n] = colof[p];
             }
-            // strides of the canonical indices inside the (i,j) block: i fastest
-            const int i = pc.I[n];
-            const ShellInfo &si = c->shells[i];
-            const int di = (2 * si.l + 1) * si.nctr;
-            const bool a_is_i = (h.sh_a == i);
-            tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
-            trow[n] = plan->rowoff[p];
-            ucol[n] = colof[p];
-        }
-        std::vector<int> nppc(pc.npp);
-        for (int &v : nppc) v = std::max(v, 1);       // dead pairs still run one zero-weight primitive
-        if (upload(&pc.d_tprim, tprim) || upload(&pc.d_tgeom, tgeom) || upload(&pc.d_trow, trow) || upload(&pc.d_ucol, ucol) ||
-            upload(&pc.d_tstride, tstride) || upload(&pc.d_ustride, tstride) || upload(&pc.d_tI, pc.I) || upload(&pc.d_tpair, pc.ids) ||
-            upload(&pc.d_tnpp, nppc))
+            std::vector<int> nppc(npp);
+            for (int &v : nppc) v = std::max(v, 1);       // dead pairs still run one zero-weight primitive
+            if (upload(d_tprim, tprim) || upload(d_tgeom, tgeom) || upload(d_trow, trow) || upload(d_tstride, tstride) ||
+                upload(d_tI, I) || upload(d_tpair, ids) || upload(d_tnpp, nppc))
+                return CINTB200_ENOMEM;
+            if (d_ucol && (upload(d_ucol, ucol) || upload(d_ustride, tstride))) return CINTB200_ENOMEM;
+            return 0;
+        };
+        if (build(pc.ids, pc.I, pc.npp, &pc.d_tprim, &pc.d_tgeom, &pc.d_trow, &pc.d_tstride, &pc.d_tI, &pc.d_tpair, &pc.d_tnpp,
+                  &pc.d_ucol, &pc.d_ustride) ||
+            build(pc.idsB, pc.IB, pc.nppB, &pc.dB_tprim, &pc.dB_tgeom, &pc.dB_trow, &pc.dB_tstride, &pc.dB_tI, &pc.dB_tpair, &pc.dB_tnpp,
+                  nullptr, nullptr))
             return CINTB200_ENOMEM;
     }
     if (plan->host_only) return 0;
@@ -306,19 +330,29 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
             for (int t = t_begin; t < t_end; t++) { cnt_ge[T.I[t] - i0] += 1; npp_ge[T.I[t] - i0] += T.npp[t]; }
             for (int k = i1 - i0 - 1; k >= 0; k--) { cnt_ge[k] += cnt_ge[k + 1]; npp_ge[k] += npp_ge[k + 1]; }
             for (size_t cu = 0; cu < plan->classes.size(); cu++) {
-                PairClass &U = plan->classes[cu];
-                const int nu_valid = U.chunk_lo[ch + 1];
-                if (nu_valid <= rank) continue;
-                const int nu_mine = (nu_valid - rank + nranks - 1) / nranks;
+              PairClass &U = plan->classes[cu];
+              // part 0: kets below the chunk's shell range (every bra of the chunk is valid; bras sorted by primitive count)
+              // part 1: kets inside it (valid bras = those with I >= K: a suffix of the shell-sorted ordering B)
+              for (int part = 0; part < 2; part++) {
+                const int u_lo = part == 0 ? 0 : U.chunk_lo[ch], u_hi = part == 0 ? U.chunk_lo[ch] : U.chunk_lo[ch + 1];
+                // this rank's kets in [u_lo, u_hi): indices congruent to rank modulo nranks
+                int u_first = u_lo + ((rank - u_lo) % nranks + nranks) % nranks;
+                if (u_first >= u_hi) continue;
+                const int nu_mine = (u_hi - u_first + nranks - 1) / nranks;
                 LaunchRec L;
                 memset(&L, 0, sizeof L);
                 TileParams &P = L.P;
-                P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
-                P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp;
+                if (part == 0) {
+                    P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
+                    P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp;
+                } else {
+                    P.tprim = T.dB_tprim; P.tgeom = T.dB_tgeom; P.trow = T.dB_trow; P.tstride = T.dB_tstride;
+                    P.tI = T.dB_tI; P.tpair = T.dB_tpair; P.tnpp = T.dB_tnpp;
+                }
                 P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
-                P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = rank; P.nca_u = U.nca;
-                P.tri = 1;
+                P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca;
+                P.tri = part;
                 P.row0 = row0; P.ld = ld;
                 P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
                 L.chunk = (int)ch;
@@ -327,7 +361,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 P.rys = c->d_rys + rys_tab_off(L.nroots);
                 double q_here = 0, prim_here = 0;
                 for (int j = 0; j < nu_mine; j++) {
-                    const int u = rank + nranks * j;
+                    const int u = u_first + nranks * j;
                     const int kk = std::max(U.I[u], i0) - i0;          // K < i0: every T pair of the chunk is valid
                     q_here += cnt_ge[kk];
                     prim_here += (double)U.npp[u] * npp_ge[kk];
@@ -353,7 +387,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     L.gx = (t_end - t_begin + qpb - 1) / qpb;
                     for (int y0 = 0; y0 < nu_mine; y0 += 65535) {
                         LaunchRec L2 = L;
-                        L2.P.u_first = rank + nranks * y0;
+                        L2.P.u_first = u_first + nranks * y0;
                         L2.gy = std::min(65535, nu_mine - y0);
                         plan->launches.push_back(L2);
                     }
@@ -363,6 +397,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     scratch_need = std::max(scratch_need, L.GC.scratch_per_block * (size_t)L.GL.grid);
                     plan->launches.push_back(L);
                 }
+              }
             }
         }
     }

@@ -55,13 +55,19 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     const int tid = threadIdx.x;
     const int q = tid / FS, lane = tid % FS;
 
-    const int K = P.uK[u];
-    const int t0 = P.t_begin + blockIdx.x * QPB;
+    int t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings
+    if (P.tri) {
+        const int K = P.uK[u];
+        int lo = P.t_begin, hi = P.t_end;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
+        t_lo = lo;
+    }
+    const int t0 = t_lo + blockIdx.x * QPB;
+    if (t0 >= P.t_end) return;
     const int t = t0 + q;
-    const int tt = t < P.t_end ? t : P.t_end - 1;
-    const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);      // see kern_reg.cuh
-    if (!__syncthreads_or(active)) return;
-    const int Qb = __shfl_sync(0xffffffffu, P.tnpp[tt], 0);      // warp-uniform bound, see kern_reg.cuh
+    const bool active = t < P.t_end;
+    const int tt = active ? t : P.t_end - 1;
+    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     // --- smem carve-up: Rys table | U primitives | per-quartet work areas ---
     double *s_rys = smem;

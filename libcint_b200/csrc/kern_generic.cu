@@ -89,7 +89,7 @@ __device__ __forceinline__ Task tile_task(const TileParams &T, long long w)
     const int t = T.t_begin + (int)(w - (long long)j * nT);
     const int u = T.u_first + T.u_step * j;
     Task k;
-    k.bra = (T.tri && T.tI[t] < T.uK[u]) ? -1 : T.tpair[t];
+    k.bra = (T.tri && T.tI[t] < T.uK[u]) ? -1 : T.tpair[t];      // tri = 1 lists are shell-sorted; a predicate is enough here
     k.ket = T.upair[u];
     k.sa = T.tstride[t];
     k.sb = T.tstride[T.NT + t];

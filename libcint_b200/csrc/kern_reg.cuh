@@ -240,17 +240,27 @@ eri_reg_kernel(const TileParams P)
     const int tid = threadIdx.x;
 
     // --- which T pairs does this block cover? ---
-    const int K = P.uK[u];
-    const int t0 = P.t_begin + blockIdx.x * REG_THREADS;
+    // reference loop bound k <= i (examples/time_c60.c:206).  tri = 0: this ket lies below the chunk's bra shells,
+    // every T pair is valid (list sorted by primitive count).  tri = 1: the list is sorted by the bra's larger
+    // shell index and the valid T pairs are the suffix starting at the first pair with I >= K.
+    int t_lo = P.t_begin;
+    if (P.tri) {
+        const int K = P.uK[u];
+        int lo = P.t_begin, hi = P.t_end;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+        }
+        t_lo = lo;
+    }
+    const int t0 = t_lo + blockIdx.x * REG_THREADS;
+    if (t0 >= P.t_end) return;          // block-uniform
     const int t = t0 + tid;
-    const int tt = t < P.t_end ? t : P.t_end - 1;
-    // reference loop bound k <= i (examples/time_c60.c:206): only the kets of the chunk's own shell range
-    // can fail it; the lists are not sorted by shell index inside a chunk, so it is a per-thread predicate
-    const bool active = (t < P.t_end) && (!P.tri || P.tI[tt] >= K);
-    if (!__syncthreads_or(active)) return;
-    // lists are sorted by descending primitive count inside a chunk: lane 0 of every WARP carries the warp's loop
-    // bound (a chunk often holds fewer T pairs of a class than one block, so a block-wide bound would pad heavily)
-    const int Qb = __shfl_sync(0xffffffffu, P.tnpp[tt], 0);
+    const bool active = t < P.t_end;
+    const int tt = active ? t : P.t_end - 1;
+    // warp-uniform primitive loop bound: the largest count among the warp's T pairs (shorter pairs are padded with
+    // zero-weight primitives; neighbouring list entries have similar counts by construction)
+    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     // --- stage the Rys table of N roots and the U pair's primitives ---
     const int nint = c_rys_meta.nint[N];

@@ -58,6 +58,7 @@ struct JobPlan {
     double *d_out[2] = {nullptr, nullptr};
     size_t out_doubles = 0;
     long long *d_uprefix = nullptr; size_t cap_uprefix = 0;
+    unsigned int *d_counters = nullptr;     // one work-item counter per launch
     double *d_scratch = nullptr; size_t cap_scratch = 0;
     int force_generic = 0;
     int host_only = 0;                      // planning without a device (cintb200_plan_summary)
@@ -79,7 +80,7 @@ void jobplan_free(JobPlan *p)
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
         cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
     }
-    cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch);
+    cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (int k = 0; k < JobPlan::NS; k++) { if (p->streams[k]) cudaStreamDestroy(p->streams[k]); if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -385,12 +386,13 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 if (L.fn) {
                     const int qpb = L.coop ? 128 / L.ci.fs : 128;
                     L.gx = (t_end - t_begin + qpb - 1) / qpb;
-                    for (int y0 = 0; y0 < nu_mine; y0 += 65535) {
-                        LaunchRec L2 = L;
-                        L2.P.u_first = u_first + nranks * y0;
-                        L2.gy = std::min(65535, nu_mine - y0);
-                        plan->launches.push_back(L2);
+                    L.gy = nu_mine;
+                    L.P.gx = L.gx;
+                    {
+                        const long long items = (long long)L.gx * nu_mine;
+                        L.P.batch = (int)std::max<long long>(1, std::min<long long>(16, items / (148 * 8 * 4)));
                     }
+                    plan->launches.push_back(L);
                 } else {
                     if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off(), c->omega < 0))
                         return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits", T.la, T.lb, U.la, U.lb);
@@ -400,6 +402,11 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
               }
             }
         }
+    }
+    if (!plan->host_only) {
+        if (cudaMalloc((void **)&plan->d_counters, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size())) != cudaSuccess)
+            return b200_fail(CINTB200_ENOMEM, "cannot allocate launch counters");
+        for (size_t k = 0; k < plan->launches.size(); k++) plan->launches[k].P.counter = plan->d_counters + k;
     }
     if (!plan->host_only && scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate generic-kernel scratch");
@@ -438,6 +445,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
     const bool prof = c->profile != 0;
     cudaStream_t st = c->stream;
     CU_OK(cudaEventRecord(plan->ev_t0, st));
+    CU_OK(cudaMemsetAsync(plan->d_counters, 0, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size()), st));
     int buf = 0, cur_chunk = -1;
     const int NS = prof ? 1 : JobPlan::NS;
     auto fork = [&]() -> int {                 // side streams start after everything queued on the main stream

@@ -51,25 +51,11 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     static_assert(FS <= 32 && (FS & (FS - 1)) == 0, "FS must be a power of two within a warp");
 
     extern __shared__ double smem[];
-    const int u = P.u_first + P.u_step * blockIdx.y;
     const int tid = threadIdx.x;
     const int q = tid / FS, lane = tid % FS;
 
-    int t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings
-    if (P.tri) {
-        const int K = P.uK[u];
-        int lo = P.t_begin, hi = P.t_end;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
-        t_lo = lo;
-    }
-    const int t0 = t_lo + blockIdx.x * QPB;
-    if (t0 >= P.t_end) return;
-    const int t = t0 + q;
-    const bool active = t < P.t_end;
-    const int tt = active ? t : P.t_end - 1;
-    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
-
-    // --- smem carve-up: Rys table | U primitives | per-quartet work areas ---
+    // --- smem carve-up: Rys table | U primitives | per-quartet work areas; the table is staged once per block and the
+    //     block walks a contiguous range of work items (one ket x QPB bras), see kern_reg.cuh ---
     double *s_rys = smem;
     const int nint = c_rys_meta.nint[N];
     {
@@ -80,18 +66,51 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
         }
     }
     double *s_u = s_rys + nint * rys_smem_stride(N);
-    const PairHdr hu = P.pairs[P.upair[u]];
-    for (int i = tid; i < hu.npp; i += REG_THREADS) {
-        const PrimPair pp = P.prims[hu.pp_off + i];
-        double *d = s_u + i * USTR;
-        d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
-        d[5] = pp.px - hu.ra[0]; d[6] = pp.py - hu.ra[1]; d[7] = pp.pz - hu.ra[2];
-        d[8] = pp.kij;
-        for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
-    }
     double *s_q = s_u + REG_MAXU * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
+    const long long total = (long long)P.gx * P.NU;
+    int cur_by = -1;
+    PairHdr hu;
+    // dynamic scheduling: blocks grab batches of P.batch consecutive work items from a per-launch counter (consecutive items
+    // share the ket, and the heavy first items of every ket are spread over all blocks)
+    __shared__ long long s_item;
+    for (;;) {
     __syncthreads();
+    if (tid == 0) s_item = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
+    __syncthreads();
+    const long long item0 = s_item;
+    if (item0 >= total) break;
+    const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
+    for (long long item = item0; item < item1; item++) {
+    const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
+    const int u = P.u_first + P.u_step * by;
+    if (by != cur_by) {
+        __syncthreads();
+        hu = P.pairs[P.upair[u]];
+        for (int i = tid; i < hu.npp; i += REG_THREADS) {
+            const PrimPair pp = P.prims[hu.pp_off + i];
+            double *d = s_u + i * USTR;
+            d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
+            d[5] = pp.px - hu.ra[0]; d[6] = pp.py - hu.ra[1]; d[7] = pp.pz - hu.ra[2];
+            d[8] = pp.kij;
+            for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
+        }
+        __syncthreads();
+        cur_by = by;
+    }
+    int t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings
+    if (P.tri) {
+        const int K = P.uK[u];
+        int lo = P.t_begin, hi = P.t_end;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
+        t_lo = lo;
+    }
+    const int t0 = t_lo + bx * QPB;
+    if (t0 >= P.t_end) continue;
+    const int t = t0 + q;
+    const bool active = t < P.t_end;
+    const int tt = active ? t : P.t_end - 1;
+    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     const size_t NT = P.NT;
     double raT[3], abT[3];
@@ -312,4 +331,6 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
         }
         __syncwarp();
     }
+    }   // work items
+    }   // batches
 }

@@ -236,10 +236,56 @@ eri_reg_kernel(const TileParams P)
 
     extern __shared__ double smem[];
     double *s_rys = smem;                                       // [nint][stride]
-    const int u = P.u_first + P.u_step * blockIdx.y;
     const int tid = threadIdx.x;
 
-    // --- which T pairs does this block cover? ---
+    // --- stage the Rys table of N roots ONCE per block; the block then walks a contiguous range of work items
+    //     (item = one ket x one group of REG_THREADS bras), so the table and the ket's primitives are reused ---
+    const int nint = c_rys_meta.nint[N];
+    {
+        constexpr int ROW = (RYS_DEG + 1) * 2 * N;
+        for (int i = tid; i < nint * ROW; i += REG_THREADS) {
+            int r = i / ROW, c = i - r * ROW;
+            s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
+        }
+    }
+    double *s_u = s_rys + nint * rys_smem_stride(N);           // [nppu][USTR]
+    const long long total = (long long)P.gx * P.NU;
+    int cur_by = -1;
+    PairHdr hu;
+    // dynamic scheduling: blocks grab batches of P.batch consecutive work items from a per-launch counter (consecutive items
+    // share the ket, and the heavy first items of every ket are spread over all blocks)
+    __shared__ long long s_item;
+    for (;;) {
+    __syncthreads();
+    if (tid == 0) s_item = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
+    __syncthreads();
+    const long long item0 = s_item;
+    if (item0 >= total) break;
+    const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
+    for (long long item = item0; item < item1; item++) {
+    const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
+    const int u = P.u_first + P.u_step * by;
+    if (by != cur_by) {
+        __syncthreads();                // previous ket's primitives no longer in use (and the table is staged)
+        hu = P.pairs[P.upair[u]];
+        for (int i = tid; i < hu.npp; i += REG_THREADS) {
+            const PrimPair pp = P.prims[hu.pp_off + i];
+            double *d = s_u + i * USTR;
+            d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
+            d[5] = pp.px - hu.ra[0]; d[6] = pp.py - hu.ra[1]; d[7] = pp.pz - hu.ra[2];
+            if constexpr (NCU == 1) {
+                d[8] = pp.kij * P.pcoef[hu.cc_off + i];
+                d[9] = 1.0;
+            } else {
+                d[8] = pp.kij;
+                for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
+            }
+        }
+        __syncthreads();
+        cur_by = by;
+    }
+
+    // --- which T pairs does this item cover? ---
     // reference loop bound k <= i (examples/time_c60.c:206).  tri = 0: this ket lies below the chunk's bra shells,
     // every T pair is valid (list sorted by primitive count).  tri = 1: the list is sorted by the bra's larger
     // shell index and the valid T pairs are the suffix starting at the first pair with I >= K.
@@ -253,40 +299,14 @@ eri_reg_kernel(const TileParams P)
         }
         t_lo = lo;
     }
-    const int t0 = t_lo + blockIdx.x * REG_THREADS;
-    if (t0 >= P.t_end) return;          // block-uniform
+    const int t0 = t_lo + bx * REG_THREADS;
+    if (t0 >= P.t_end) continue;        // block-uniform
     const int t = t0 + tid;
     const bool active = t < P.t_end;
     const int tt = active ? t : P.t_end - 1;
     // warp-uniform primitive loop bound: the largest count among the warp's T pairs (shorter pairs are padded with
     // zero-weight primitives; neighbouring list entries have similar counts by construction)
     const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
-
-    // --- stage the Rys table of N roots and the U pair's primitives ---
-    const int nint = c_rys_meta.nint[N];
-    {
-        constexpr int ROW = (RYS_DEG + 1) * 2 * N;
-        for (int i = tid; i < nint * ROW; i += REG_THREADS) {
-            int r = i / ROW, c = i - r * ROW;
-            s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
-        }
-    }
-    double *s_u = s_rys + nint * rys_smem_stride(N);           // [nppu][USTR]
-    const PairHdr hu = P.pairs[P.upair[u]];
-    for (int i = tid; i < hu.npp; i += REG_THREADS) {
-        const PrimPair pp = P.prims[hu.pp_off + i];
-        double *d = s_u + i * USTR;
-        d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
-        d[5] = pp.px - hu.ra[0]; d[6] = pp.py - hu.ra[1]; d[7] = pp.pz - hu.ra[2];
-        if constexpr (NCU == 1) {
-            d[8] = pp.kij * P.pcoef[hu.cc_off + i];
-            d[9] = 1.0;
-        } else {
-            d[8] = pp.kij;
-            for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
-        }
-    }
-    __syncthreads();
 
     // --- per-thread (T pair) constants ---
     const size_t NT = P.NT;
@@ -421,7 +441,7 @@ eri_reg_kernel(const TileParams P)
                 }
         }
     }
-    if (!active) return;
+    if (!active) continue;
 
     // --- epilogue: HRR, c2s, store ---
     const int sa = P.tstride[tt], sb = P.tstride[NT + tt];
@@ -477,4 +497,6 @@ eri_reg_kernel(const TileParams P)
             });
         });
     }
+    }   // work items
+    }   // batches
 }

@@ -26,6 +26,8 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
                    long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream,
                    const TileParams *tile = nullptr, const long long *uprefix = nullptr);
 
+#define B200_PERSISTENT_BLOCKS (148 * 16)      // blocks per launch of the tile kernels (each walks many work items)
+
 // register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
 typedef void (*RegKernelFn)(const TileParams);
 RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu);

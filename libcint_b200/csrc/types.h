@@ -72,6 +72,9 @@ struct TileParams {
     const int *tnpp;           // [NT] primitive pairs per T pair (>= 1); lists are sorted by descending count inside a chunk
     int NT, Q;                 // pairs in class, primitives per pair (padded)
     int t_begin, t_end;        // range of this chunk inside the class list
+    unsigned int *counter;     // per-launch work-item counter (zeroed before every job)
+    int batch;                 // work items fetched per atomic (sized on the host so that every launch has >= ~8 batches per SM)
+    int gx;                    // work items per ket = ceil((t_end - t_begin) / pairs per block)
     int nca_t;                 // contraction count of shell a (T side), for block offsets
     // U side (block-uniform pairs)
     const int *upair;          // [NU] pair ids (AoS tables in EngineParams), sorted by larger shell index

@@ -384,13 +384,13 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     L.coop = L.fn != nullptr;
                 }
                 if (L.fn) {
-                    const int qpb = L.coop ? 128 / L.ci.fs : 128;
+                    const int qpb = L.coop ? 32 / L.ci.fs : 32;       // bras per work item (one warp)
                     L.gx = (t_end - t_begin + qpb - 1) / qpb;
                     L.gy = nu_mine;
                     L.P.gx = L.gx;
                     {
                         const long long items = (long long)L.gx * nu_mine;
-                        L.P.batch = (int)std::max<long long>(1, std::min<long long>(16, items / (148 * 8 * 4)));
+                        L.P.batch = (int)std::max<long long>(1, std::min<long long>(16, items / (148 * 32 * 4)));
                     }
                     plan->launches.push_back(L);
                 } else {

@@ -65,29 +65,28 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
             s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
         }
     }
-    double *s_u = s_rys + nint * rys_smem_stride(N);
-    double *s_q = s_u + REG_MAXU * USTR + (size_t)q * XSZ;      // this quartet's area
+    constexpr int NWARP = REG_THREADS / 32, QPW = 32 / FS;     // quartets per warp
+    const int warp = tid >> 5, wl = tid & 31;
+    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * REG_MAXU * USTR;        // this WARP's ket primitives
+    double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * REG_MAXU * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
     const long long total = (long long)P.gx * P.NU;
     int cur_by = -1;
     PairHdr hu;
-    // dynamic scheduling: blocks grab batches of P.batch consecutive work items from a per-launch counter (consecutive items
-    // share the ket, and the heavy first items of every ket are spread over all blocks)
-    __shared__ long long s_item;
+    __syncthreads();                    // table staged; warps are independent from here on (see kern_reg.cuh)
     for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
-    __syncthreads();
-    const long long item0 = s_item;
+    long long item0 = 0;
+    if (wl == 0) item0 = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
+    item0 = __shfl_sync(0xffffffffu, item0, 0);
     if (item0 >= total) break;
     const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
     for (long long item = item0; item < item1; item++) {
     const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
     const int u = P.u_first + P.u_step * by;
     if (by != cur_by) {
-        __syncthreads();
+        __syncwarp();
         hu = P.pairs[P.upair[u]];
-        for (int i = tid; i < hu.npp; i += REG_THREADS) {
+        for (int i = wl; i < hu.npp; i += 32) {
             const PrimPair pp = P.prims[hu.pp_off + i];
             double *d = s_u + i * USTR;
             d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
             d[8] = pp.kij;
             for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
         }
-        __syncthreads();
+        __syncwarp();
         cur_by = by;
     }
     int t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings
@@ -105,9 +104,9 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
         t_lo = lo;
     }
-    const int t0 = t_lo + bx * QPB;
-    if (t0 >= P.t_end) continue;
-    const int t = t0 + q;
+    const int t0 = t_lo + bx * QPW;
+    if (t0 >= P.t_end) continue;         // warp-uniform
+    const int t = t0 + (q - warp * QPW);
     const bool active = t < P.t_end;
     const int tt = active ? t : P.t_end - 1;
     const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);

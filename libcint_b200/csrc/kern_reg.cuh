@@ -239,7 +239,7 @@ eri_reg_kernel(const TileParams P)
     const int tid = threadIdx.x;
 
     // --- stage the Rys table of N roots ONCE per block; the block then walks a contiguous range of work items
-    //     (item = one ket x one group of REG_THREADS bras), so the table and the ket's primitives are reused ---
+    //     (item = one ket x 32 bras, one WARP each), so the table and the ket's primitives are reused ---
     const int nint = c_rys_meta.nint[N];
     {
         constexpr int ROW = (RYS_DEG + 1) * 2 * N;
@@ -248,27 +248,28 @@ eri_reg_kernel(const TileParams P)
             s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
         }
     }
-    double *s_u = s_rys + nint * rys_smem_stride(N);           // [nppu][USTR]
+    constexpr int NWARP = REG_THREADS / 32;
+    const int warp = tid >> 5, lane = tid & 31;
+    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * REG_MAXU * USTR;     // this WARP's ket primitives [nppu][USTR]
     const long long total = (long long)P.gx * P.NU;
     int cur_by = -1;
     PairHdr hu;
-    // dynamic scheduling: blocks grab batches of P.batch consecutive work items from a per-launch counter (consecutive items
-    // share the ket, and the heavy first items of every ket are spread over all blocks)
-    __shared__ long long s_item;
+    __syncthreads();                    // table staged; from here on the warps run independently (no block barriers)
+    // dynamic scheduling per WARP: a warp grabs batches of P.batch consecutive work items (item = one ket x 32 bras)
+    // from the per-launch counter; consecutive items share the ket, whose primitives sit in the warp's own smem slice
     for (;;) {
-    __syncthreads();
-    if (tid == 0) s_item = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
-    __syncthreads();
-    const long long item0 = s_item;
+    long long item0 = 0;
+    if (lane == 0) item0 = (long long)atomicAdd(P.counter, (unsigned int)P.batch);
+    item0 = __shfl_sync(0xffffffffu, item0, 0);
     if (item0 >= total) break;
     const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
     for (long long item = item0; item < item1; item++) {
     const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
     const int u = P.u_first + P.u_step * by;
     if (by != cur_by) {
-        __syncthreads();                // previous ket's primitives no longer in use (and the table is staged)
+        __syncwarp();                   // previous ket's primitives no longer in use by this warp
         hu = P.pairs[P.upair[u]];
-        for (int i = tid; i < hu.npp; i += REG_THREADS) {
+        for (int i = lane; i < hu.npp; i += 32) {
             const PrimPair pp = P.prims[hu.pp_off + i];
             double *d = s_u + i * USTR;
             d[0] = pp.aij; d[1] = pp.inv_aij; d[2] = pp.px; d[3] = pp.py; d[4] = pp.pz;
@@ -281,7 +282,7 @@ eri_reg_kernel(const TileParams P)
                 for (int c = 0; c < NCU; c++) d[9 + c] = P.pcoef[hu.cc_off + i * NCU + c];
             }
         }
-        __syncthreads();
+        __syncwarp();
         cur_by = by;
     }
 
@@ -299,9 +300,9 @@ eri_reg_kernel(const TileParams P)
         }
         t_lo = lo;
     }
-    const int t0 = t_lo + bx * REG_THREADS;
-    if (t0 >= P.t_end) continue;        // block-uniform
-    const int t = t0 + tid;
+    const int t0 = t_lo + bx * 32;
+    if (t0 >= P.t_end) continue;        // warp-uniform
+    const int t = t0 + lane;
     const bool active = t < P.t_end;
     const int tt = active ? t : P.t_end - 1;
     // warp-uniform primitive loop bound: the largest count among the warp's T pairs (shorter pairs are padded with
@@ -322,7 +323,7 @@ eri_reg_kernel(const TileParams P)
     constexpr int NACC = NCT * NCU * NEF;
     constexpr bool ACC_SMEM = reg_acc_in_smem(NCT, NACC);
     double acc[ACC_SMEM ? 1 : NACC];
-    double *s_acc = s_u + REG_MAXU * USTR + tid;         // [NACC][REG_THREADS]
+    double *s_acc = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * REG_MAXU * USTR + tid;         // [NACC][REG_THREADS]
     if constexpr (ACC_SMEM) {
 #pragma unroll
         for (int i = 0; i < NACC; i++) s_acc[i * REG_THREADS] = 0.0;

@@ -403,6 +403,9 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
             }
         }
     }
+    // longest kernels first inside every chunk: the short ones then fill the tail on the other streams
+    std::stable_sort(plan->launches.begin(), plan->launches.end(), [](const LaunchRec &a, const LaunchRec &b) {
+        return a.chunk != b.chunk ? a.chunk < b.chunk : a.flops > b.flops; });
     if (!plan->host_only) {
         if (cudaMalloc((void **)&plan->d_counters, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size())) != cudaSuccess)
             return b200_fail(CINTB200_ENOMEM, "cannot allocate launch counters");

@@ -27,10 +27,9 @@ full)
     ncu -i /tmp/prof_$1.ncu-rep --page source --csv > gpurun_out/prof_$1_${ROUND}_source.csv 2>/dev/null
     ncu -i /tmp/prof_$1.ncu-rep --page details > gpurun_out/prof_$1_${ROUND}_details.txt 2>/dev/null
   }
-  capture reg_psps eri_reg_kernelILi1ELi0ELi1ELi0ELi2ELi2E 4
-  capture coop_ppdp eri_coop_kernelILi2ELi1ELi1ELi1ELi1ELi1ELi16ELb0E 3
-  capture coop_dpdp eri_coop_kernelILi2ELi1ELi2ELi1E 3
-  capture reg_sssp eri_reg_kernelILi0ELi0ELi1ELi0ELi4ELi2E 4
+  capture reg_psps eri_reg_kernelILi1ELi0ELi1ELi0ELi2ELi2E 8
+  capture coop_dpdp eri_coop_kernelILi2ELi1ELi2ELi1E 8
+  capture reg_sssp eri_reg_kernelILi0ELi0ELi1ELi0ELi4ELi2E 8
   ;;
 esac
 done

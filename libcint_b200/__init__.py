@@ -185,6 +185,17 @@ class Context:
         self.lib.cintb200_debug_profile_rows(self.handle, _p(rows), n)
         return st, rows
 
+    def launch_rows(self):
+        """Launch list of the cached whole-job plan in execution order (see driver.cu)."""
+        f = self.lib.cintb200_debug_launch_rows
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        f.restype = ctypes.c_int
+        n = f(self.handle, None, 0)
+        rows = np.zeros((max(n, 0), 12))
+        if n > 0:
+            f(self.handle, _p(rows), n)
+        return rows
+
     def pair_offsets(self, i, j):
         """(global row offset, this rank's column offset or -1) of the block of shell pair (i, j), i >= j."""
         r = ctypes.c_longlong()

@@ -309,7 +309,8 @@ struct LaunchRec {
     long long ntasks;           // generic: number of quartets
     size_t uprefix_off;         // generic: offset into plan->d_uprefix
     int key[6];                 // la lb lc ld nct ncu
-    double quartets, prim, flops;
+    double quartets, prim, flops, integrals;
+    int part;                   // 0: kets below the chunk's bra shells, 1: the chunk's own kets
 };
 
 static int build_launches(CINTOpt *c, JobPlan *plan)
@@ -352,7 +353,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 }
                 P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
-                P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca;
+                P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca; P.umax = std::max(1, U.Q);
                 P.tri = part;
                 P.row0 = row0; P.ld = ld;
                 P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
@@ -375,7 +376,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 plan->st_flops += prim_here * fp + q_here * fq;
                 L.ntasks = (long long)(t_end - t_begin) * nu_mine;      // generic: rectangle, invalid quartets skipped in-kernel
                 L.key[0] = T.la; L.key[1] = T.lb; L.key[2] = U.la; L.key[3] = U.lb; L.key[4] = T.nca * T.ncb; L.key[5] = U.nca * U.ncb;
-                L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq;
+                L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq; L.integrals = q_here * blk; L.part = part;
                 // the specialised kernels implement the plain Coulomb operator; range-separated runs use the generic kernel
                 const bool generic_only = c->force_generic || c->omega != 0;
                 L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
@@ -618,4 +619,20 @@ extern "C" int cintb200_plan_summary(const int *atm, int natm, const int *bas, i
     jobplan_free(plan);
     cintb200_destroy(c);
     return rc;
+}
+
+// Launch list of the cached plan in execution order: rows of 12 doubles
+// {chunk, la, lb, lc, ld, nct, ncu, kind (0 generic, 1 register, 2 cooperative), part, quartets, integrals, model flops}.
+extern "C" int cintb200_debug_launch_rows(cintb200_ctx *c, double *rows, int max_rows)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan) return -1;
+    const int n = (int)c->plan->launches.size();
+    for (int k = 0; k < n && k < max_rows && rows; k++) {
+        const LaunchRec &L = c->plan->launches[k];
+        double *r = rows + 12 * k;
+        r[0] = L.chunk;
+        for (int j = 0; j < 6; j++) r[1 + j] = L.key[j];
+        r[7] = L.fn ? (L.coop ? 2 : 1) : 0; r[8] = L.part; r[9] = L.quartets; r[10] = L.integrals; r[11] = L.flops;
+    }
+    return n;
 }

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     }
     constexpr int NWARP = REG_THREADS / 32, QPW = 32 / FS;     // quartets per warp
     const int warp = tid >> 5, wl = tid & 31;
-    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * REG_MAXU * USTR;        // this WARP's ket primitives
-    double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * REG_MAXU * USTR + (size_t)q * XSZ;      // this quartet's area
+    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;        // this WARP's ket primitives [nppu <= umax]
+    double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
     const long long total = (long long)P.gx * P.NU;
     int cur_by = -1;

@@ -250,7 +250,7 @@ eri_reg_kernel(const TileParams P)
     }
     constexpr int NWARP = REG_THREADS / 32;
     const int warp = tid >> 5, lane = tid & 31;
-    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * REG_MAXU * USTR;     // this WARP's ket primitives [nppu][USTR]
+    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;     // this WARP's ket primitives [nppu <= umax][USTR]
     const long long total = (long long)P.gx * P.NU;
     int cur_by = -1;
     PairHdr hu;
@@ -323,7 +323,7 @@ eri_reg_kernel(const TileParams P)
     constexpr int NACC = NCT * NCU * NEF;
     constexpr bool ACC_SMEM = reg_acc_in_smem(NCT, NACC);
     double acc[ACC_SMEM ? 1 : NACC];
-    double *s_acc = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * REG_MAXU * USTR + tid;         // [NACC][REG_THREADS]
+    double *s_acc = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + tid;         // [NACC][REG_THREADS]
     if constexpr (ACC_SMEM) {
 #pragma unroll
         for (int i = 0; i < NACC; i++) s_acc[i * REG_THREADS] = 0.0;

@@ -85,6 +85,7 @@ struct TileParams {
     int NU_all;                // length of the class list (second row of ustride starts here)
     int u_step, u_first;       // rank sharding: u = u_first + u_step * blockIdx.y
     int nca_u;
+    int umax;                  // most primitive pairs of any ket of this launch (sizes the per-warp smem slice)
     int tri;                   // 1: only quartets with K(u) <= I(t) (reference benchmark loop)
     // output tile
     double *out;

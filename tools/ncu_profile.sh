@@ -14,6 +14,8 @@ ctx = cb.Context(atm, bas, env)
 ctx.lib.cintb200_debug_profile(ctx.handle, 1)      # single stream: launches serialised like the timed profile pass
 st = ctx.all_unique(chunk_bytes=80 << 30)
 print("gpu ms", st[7], "launches", st[4])
+import numpy as np, os
+np.save(os.path.join("gpurun_out", "launch_rows.npy"), ctx.launch_rows())
 PY
 for what in "$@"; do
 case $what in

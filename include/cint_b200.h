@@ -75,6 +75,13 @@ size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, i
 int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
                                   double *host_sink, double *stats);
 
+/* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
+ * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity
+ * tolerance by construction); 0 switches it off.  The bounds are evaluated on the device on first use.
+ * cintb200_schwarz_bounds copies them (one per shell pair i >= j, index i(i+1)/2 + j; q may be NULL) and returns their number. */
+int cintb200_set_schwarz_threshold(cintb200_ctx *ctx, double thr);
+int cintb200_schwarz_bounds(cintb200_ctx *ctx, double *q);
+
 /* Host-only planning of the whole job for `rank` of `nranks` (no GPU needed): the static sharding that
  * cintb200_int2e_sph_all_unique will execute.  out[0] shell quartets, out[1] integrals, out[2] primitive quartets,
  * out[3] model FLOPs, out[4] tile columns owned by this rank, out[5] tile rows (all pairs), out[6] chunks,

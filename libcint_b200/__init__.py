@@ -185,6 +185,22 @@ class Context:
         self.lib.cintb200_debug_profile_rows(self.handle, _p(rows), n)
         return st, rows
 
+    def set_schwarz_threshold(self, thr):
+        self.lib.cintb200_set_schwarz_threshold.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        self.lib.cintb200_set_schwarz_threshold(self.handle, thr)
+
+    def schwarz_bounds(self):
+        """sqrt(max|(ij|ij)|) per shell pair i >= j (index i(i+1)/2 + j), evaluated on the device."""
+        f = self.lib.cintb200_schwarz_bounds
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        n = f(self.handle, None)
+        if n < 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        q = np.zeros(n)
+        f(self.handle, _p(q))
+        return q
+
     def launch_rows(self):
         """Launch list of the cached whole-job plan in execution order (see driver.cu)."""
         f = self.lib.cintb200_debug_launch_rows

@@ -43,6 +43,7 @@ struct PairClass {
     double *dB_tprim = nullptr, *dB_tgeom = nullptr;
     long long *dB_trow = nullptr;
     int *dB_tstride = nullptr, *dB_tI = nullptr, *dB_tpair = nullptr, *dB_tnpp = nullptr;
+    double *d_tq = nullptr, *dB_tq = nullptr;   // Schwarz bounds in both orderings
 };
 
 struct LaunchRec;
@@ -61,12 +62,16 @@ struct JobPlan {
     unsigned int *d_counters = nullptr;     // one work-item counter per launch
     double *d_scratch = nullptr; size_t cap_scratch = 0;
     int force_generic = 0;
+    double schwarz_thr = 0;
     int host_only = 0;                      // planning without a device (cintb200_plan_summary)
     std::vector<long long> colof;           // per pair id: this rank's column offset or -1
     std::vector<struct LaunchRec> launches;
     double st_quartets = 0, st_integrals = 0, st_prim = 0, st_flops = 0;
     cudaStream_t copy_stream = nullptr;
-    static const int NS = 8;                // concurrent launch streams (independent classes overlap)
+#ifndef B200_NSTREAMS
+#define B200_NSTREAMS 8
+#endif
+    static const int NS = B200_NSTREAMS;    // concurrent launch streams (independent classes overlap)
     cudaStream_t streams[NS] = {nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NS] = {nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -78,7 +83,7 @@ void jobplan_free(JobPlan *p)
     for (PairClass &c : p->classes) {
         cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
-        cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
+        cudaFree(c.d_tq); cudaFree(c.dB_tq); cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
     }
     cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -279,6 +284,11 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
             build(pc.idsB, pc.IB, pc.nppB, &pc.dB_tprim, &pc.dB_tgeom, &pc.dB_trow, &pc.dB_tstride, &pc.dB_tI, &pc.dB_tpair, &pc.dB_tnpp,
                   nullptr, nullptr))
             return CINTB200_ENOMEM;
+        if (!c->schwarz.empty()) {
+            std::vector<double> qa(NT), qb(NT);
+            for (size_t n = 0; n < NT; n++) { qa[n] = c->schwarz[pc.ids[n]]; qb[n] = c->schwarz[pc.idsB[n]]; }
+            if (upload(&pc.d_tq, qa) || upload(&pc.dB_tq, qb)) return CINTB200_ENOMEM;
+        }
     }
     if (plan->host_only) return 0;
     // one tile buffer; the second one (overlap of D2H with the next chunk's kernels) is allocated on first use of a host sink
@@ -346,15 +356,16 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 TileParams &P = L.P;
                 if (part == 0) {
                     P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
-                    P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp;
+                    P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp; P.tq = T.d_tq;
                 } else {
                     P.tprim = T.dB_tprim; P.tgeom = T.dB_tgeom; P.trow = T.dB_trow; P.tstride = T.dB_tstride;
-                    P.tI = T.dB_tI; P.tpair = T.dB_tpair; P.tnpp = T.dB_tnpp;
+                    P.tI = T.dB_tI; P.tpair = T.dB_tpair; P.tnpp = T.dB_tnpp; P.tq = T.dB_tq;
                 }
                 P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
                 P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca; P.umax = std::max(1, U.Q);
                 P.tri = part;
+                P.uq = U.d_tq; P.schwarz_thr = (T.d_tq && U.d_tq) ? c->schwarz_thr : 0.0;
                 P.row0 = row0; P.ld = ld;
                 P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
                 L.chunk = (int)ch;
@@ -422,14 +433,15 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (nranks < 1 || rank < 0 || rank >= nranks) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (c->schwarz_thr > 0 && c->omega == 0 && !c->force_generic && ctx_compute_schwarz(c)) return CINTB200_ENODEV;
     std::lock_guard<std::mutex> lock(c->mtx);
     CU_OK(cudaSetDevice(c->device));
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
     JobPlan *plan = c->plan;
-    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic) {
+    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic || plan->schwarz_thr != c->schwarz_thr) {
         if (plan) { cudaDeviceSynchronize(); jobplan_free(plan); c->plan = nullptr; }
         plan = new JobPlan();
-        plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic;
+        plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic; plan->schwarz_thr = c->schwarz_thr;
         int rc = build_plan(c, plan);
         if (!rc) rc = build_launches(c, plan);
         if (rc) { jobplan_free(plan); return rc; }

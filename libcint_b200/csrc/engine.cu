@@ -487,6 +487,77 @@ extern "C" long cintb200_int3c2e_batch(cintb200_ctx *c, int kind, const int *shl
                                        double *out, int on_device, int *nonzero)
 { return run_batch(c, 3, kind, shls, n, out_off, out, on_device, nonzero); }
 
+// ------------------------------------------------------------------ Schwarz bounds (device)
+// q[p] = sqrt(max |(ij|ij)|) over the block of shell pair p: |(ij|kl)| <= q[ij] q[kl].  The reference has no
+// shell-quartet screening (its callers do it); the whole-job driver uses these bounds to skip work items
+// whose 32 quartets are all below the threshold (their blocks are zero-filled, like the reference's empty blocks).
+__global__ void block_maxabs_kernel(const double *__restrict__ v, const size_t *__restrict__ off, const size_t *__restrict__ len,
+                                    double *__restrict__ q, size_t n)
+{
+    const size_t p = blockIdx.x;
+    if (p >= n) return;
+    double m = 0;
+    for (size_t i = threadIdx.x; i < len[p]; i += blockDim.x) m = fmax(m, fabs(v[off[p] + i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmax(m, sm[w]);
+        q[p] = sqrt(m);
+    }
+}
+
+static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
+                      double *out, int on_device, int *nonzero);
+
+int ctx_compute_schwarz(CINTOpt *c)
+{
+    if (!c->schwarz.empty()) return 0;
+    const size_t np = (size_t)c->nbas * (c->nbas + 1) / 2;
+    std::vector<int> shls(4 * np);
+    std::vector<size_t> off(np), len(np);
+    size_t total = 0;
+    for (int i = 0, p = 0; i < c->nbas; i++)
+        for (int j = 0; j <= i; j++, p++) {
+            shls[4 * p] = i; shls[4 * p + 1] = j; shls[4 * p + 2] = i; shls[4 * p + 3] = j;
+            const size_t d = (size_t)(2 * c->shells[i].l + 1) * c->shells[i].nctr * (2 * c->shells[j].l + 1) * c->shells[j].nctr;
+            off[p] = total; len[p] = d * d; total += d * d;
+        }
+    double *d_v = nullptr, *d_q = nullptr;
+    size_t *d_off = nullptr, *d_len = nullptr;
+    CUDA_OK(cudaSetDevice(c->device));
+    CUDA_OK(cudaMalloc(&d_v, sizeof(double) * total));
+    CUDA_OK(cudaMalloc(&d_q, sizeof(double) * np));
+    CUDA_OK(cudaMalloc(&d_off, sizeof(size_t) * np));
+    CUDA_OK(cudaMalloc(&d_len, sizeof(size_t) * np));
+    long rc = run_batch(c, 4, CINTB200_SPH, shls.data(), np, off.data(), d_v, 1, nullptr);
+    if (rc >= 0) {
+        cudaMemcpy(d_off, off.data(), sizeof(size_t) * np, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_len, len.data(), sizeof(size_t) * np, cudaMemcpyHostToDevice);
+        block_maxabs_kernel<<<(unsigned)np, 128>>>(d_v, d_off, d_len, d_q, np);
+        c->schwarz.resize(np);
+        if (cudaMemcpy(c->schwarz.data(), d_q, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess) { c->schwarz.clear(); rc = -1; }
+    }
+    cudaFree(d_v); cudaFree(d_q); cudaFree(d_off); cudaFree(d_len);
+    return rc < 0 ? b200_fail(CINTB200_ENODEV, "Schwarz bound evaluation failed") : 0;
+}
+
+extern "C" int cintb200_set_schwarz_threshold(cintb200_ctx *c, double thr)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    c->schwarz_thr = thr;
+    return 0;
+}
+
+extern "C" int cintb200_schwarz_bounds(cintb200_ctx *c, double *q)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    if (ctx_compute_schwarz(c)) return CINTB200_ENODEV;
+    if (q) memcpy(q, c->schwarz.data(), sizeof(double) * c->schwarz.size());
+    return (int)c->schwarz.size();
+}
+
 // ------------------------------------------------------------------ libcint drop-in calls
 // Contexts for calls that pass opt == NULL (or an opt built from different arrays) are cached by
 // content hash so that loops such as testsuite/test_cint.py:235-256 do not rebuild tables per call.

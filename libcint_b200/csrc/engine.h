@@ -27,6 +27,8 @@ struct CINTOpt {
     std::vector<PairHdr> pairs;
     std::vector<PrimPair> prims;
     std::vector<double> pcoef;
+    std::vector<double> schwarz;        // sqrt(max|(ij|ij)|) per pair id, filled on demand (device evaluation)
+    double schwarz_thr = 1e-15;         // whole-job driver: skip work items whose quartets are all bounded below this (0 = off)
     // device tables
     PairHdr *d_pairs = nullptr;
     PrimPair *d_prims = nullptr;
@@ -48,6 +50,7 @@ struct CINTOpt {
 
 struct JobPlan;
 void jobplan_free(JobPlan *p);
+int ctx_compute_schwarz(CINTOpt *c);
 int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);
 int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_host);

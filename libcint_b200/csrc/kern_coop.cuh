@@ -20,7 +20,10 @@
 // per-(root,axis) G block padded to an odd number of doubles so the 3N lanes that write them hit distinct banks
 // resident blocks per SM the compiler must allow, by accumulator count per lane (measured per class on C60:
 // small-accumulator classes gain 20-25% from 3-4 blocks, the (dd|x) classes with 62 accumulators lose from spills)
-__host__ __device__ constexpr int coop_min_blocks(int nacc) { return nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2; }
+#ifndef COOP_THREADS
+#define COOP_THREADS 128
+#endif
+__host__ __device__ constexpr int coop_min_blocks(int nacc) { return (nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2) * 128 / COOP_THREADS > 0 ? (nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2) * 128 / COOP_THREADS : 1; }
 
 __host__ __device__ constexpr int coop_g_task(int nmax, int mmax) { return ((nmax + 1) * (mmax + 1)) | 1; }
 __host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * coop_g_task(nmax, mmax); }
@@ -31,7 +34,7 @@ __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, in
 }
 
 template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T>
-__global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
+__global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     constexpr int NFA = cx_ncart(LA), NFB = cx_ncart(LB), NFC = cx_ncart(LC), NFD = cx_ncart(LD);
     constexpr int DA = SphDim<LA>::value, DB = SphDim<LB>::value, DC = SphDim<LC>::value, DD = SphDim<LD>::value;
     constexpr int NAB = DA * DB;
-    constexpr int QPB = REG_THREADS / FS;                       // quartets per block
+    constexpr int QPB = COOP_THREADS / FS;                       // quartets per block
     constexpr int NCT = REG_IS_T ? NCR : NCL, NCU = REG_IS_T ? NCL : NCR;
     constexpr int USTR = 9 + NCU;
     constexpr int GSZ = coop_g_size(N, NMAX, MMAX);
@@ -60,12 +63,12 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     const int nint = c_rys_meta.nint[N];
     {
         constexpr int ROW = (RYS_DEG + 1) * 2 * N;
-        for (int i = tid; i < nint * ROW; i += REG_THREADS) {
+        for (int i = tid; i < nint * ROW; i += COOP_THREADS) {
             int r = i / ROW, c = i - r * ROW;
             s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
         }
     }
-    constexpr int NWARP = REG_THREADS / 32, QPW = 32 / FS;     // quartets per warp
+    constexpr int NWARP = COOP_THREADS / 32, QPW = 32 / FS;     // quartets per warp
     const int warp = tid >> 5, wl = tid & 31;
     double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;        // this WARP's ket primitives [nppu <= umax]
     double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + (size_t)q * XSZ;      // this quartet's area
@@ -109,7 +112,10 @@ __global__ void __launch_bounds__(REG_THREADS, coop_min_blocks(NCR * NCL * cx_nr
     const int t = t0 + (q - warp * QPW);
     const bool active = t < P.t_end;
     const int tt = active ? t : P.t_end - 1;
-    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
+    // Schwarz: if every quartet of this warp is bounded below the threshold, skip the primitive loops -- the
+    // accumulators stay zero and the epilogue zero-fills the blocks (what the reference does for empty blocks)
+    const bool negligible = P.schwarz_thr > 0 && P.tq[tt] * P.uq[u] < P.schwarz_thr;
+    const int Qb = __all_sync(0xffffffffu, negligible) ? 0 : __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     const size_t NT = P.NT;
     double raT[3], abT[3];

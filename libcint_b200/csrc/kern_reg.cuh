@@ -307,7 +307,10 @@ eri_reg_kernel(const TileParams P)
     const int tt = active ? t : P.t_end - 1;
     // warp-uniform primitive loop bound: the largest count among the warp's T pairs (shorter pairs are padded with
     // zero-weight primitives; neighbouring list entries have similar counts by construction)
-    const int Qb = __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
+    // Schwarz: if every quartet of this warp is bounded below the threshold, skip the primitive loops -- the
+    // accumulators stay zero and the epilogue zero-fills the blocks (what the reference does for empty blocks)
+    const bool negligible = P.schwarz_thr > 0 && P.tq[tt] * P.uq[u] < P.schwarz_thr;
+    const int Qb = __all_sync(0xffffffffu, negligible) ? 0 : __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     // --- per-thread (T pair) constants ---
     const size_t NT = P.NT;

@@ -69,6 +69,9 @@ struct TileParams {
     const int *tstride;        // [2][NT] sa, sb (elements)
     const int *tI;             // [NT] larger shell index of the pair
     const int *tpair;          // [NT] pair ids (for the generic kernel's tile mode)
+    const double *tq;          // [NT] Schwarz bound sqrt(max|(ab|ab)|) of every T pair (NULL: screening off)
+    const double *uq;          // [NU_all] same for the kets
+    double schwarz_thr;        // skip a work item when bound(T) * bound(U) < thr for all of its quartets
     const int *tnpp;           // [NT] primitive pairs per T pair (>= 1); lists are sorted by descending count inside a chunk
     int NT, Q;                 // pairs in class, primitives per pair (padded)
     int t_begin, t_end;        // range of this chunk inside the class list

@@ -103,3 +103,59 @@ def test_c60_job_statistics_and_sample():
         nb, nk = dims[i] * dims[j], dims[k] * dims[l]
         got = tile[r - g["row0"]:r - g["row0"] + nb, c:c + nk]
         assert np.abs(got - want.reshape((nb, nk), order="F")).max() <= 1e-12 * max(1.0, np.abs(want).max()), (i, j, k, l)
+
+
+def _dimer(name, shift):
+    """Two copies of a fixture molecule, the second shifted by `shift` Bohr along x (far apart -> most inter-molecular
+    quartets are negligible)."""
+    atm, bas, env = cb.load_fixture(name)
+    natm, nbas = len(atm), len(bas)
+    env2 = list(env)
+    atm2 = np.vstack([atm, atm]).astype(np.int32)
+    for i in range(natm):
+        atm2[natm + i, 1] = len(env2)
+        x, y, z = env[atm[i, 1]:atm[i, 1] + 3]
+        env2 += [x + shift, y, z]
+    bas2 = np.vstack([bas, bas]).astype(np.int32)
+    bas2[nbas:, 0] += natm
+    return atm2, bas2, np.array(env2)
+
+
+def test_schwarz_bounds_and_screened_job():
+    which, _ = ou.best()
+    atm, bas, env = _dimer("c2h6_631g", 40.0)
+    nbas = len(bas)
+    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    ctx = cb.Context(atm, bas, env)
+    q = ctx.schwarz_bounds()
+    assert len(q) == nbas * (nbas + 1) // 2
+    rng = np.random.default_rng(2)
+    # the bound holds: max|(ij|kl)| <= q_ij q_kl
+    quart = rng.integers(0, nbas, (300, 4)).astype(np.int32)
+    v, o, s, _ = ctx.int2e_batch(quart)
+    for n, (i, j, k, l) in enumerate(quart):
+        pij = max(i, j) * (max(i, j) + 1) // 2 + min(i, j)
+        pkl = max(k, l) * (max(k, l) + 1) // 2 + min(k, l)
+        assert np.abs(v[o[n]:o[n] + s[n]]).max() <= q[pij] * q[pkl] * (1 + 1e-10) + 1e-300
+    # whole job with screening (default 1e-15): identical to the oracle within the parity tolerance, and genuinely
+    # negligible blocks come out as exact zeros
+    ctx.all_unique(chunk_bytes=1 << 30)
+    tile, g = ctx.chunk(0)
+    zeros = 0
+    for _ in range(1500):
+        i = int(rng.integers(0, nbas)); j = int(rng.integers(0, i + 1))
+        k = int(rng.integers(0, i + 1)); l = int(rng.integers(0, k + 1))
+        r, _ = ctx.pair_offsets(i, j)
+        _, c = ctx.pair_offsets(k, l)
+        want, _ = ou.eval_tuple(which, "int2e_sph", (i, j, k, l), atm, bas, env)
+        nb, nk = dims[i] * dims[j], dims[k] * dims[l]
+        got = tile[r:r + nb, c:c + nk]
+        assert np.abs(got - want.reshape((nb, nk), order="F")).max() <= 1e-12 * max(1.0, np.abs(want).max()), (i, j, k, l)
+        zeros += int(np.all(got == 0))
+    assert zeros > 50                      # inter-molecular charge clouds do not overlap at 40 Bohr
+    # switching the screening off changes nothing beyond 1e-15
+    ctx2 = cb.Context(atm, bas, env)
+    ctx2.set_schwarz_threshold(0.0)
+    ctx2.all_unique(chunk_bytes=1 << 30)
+    tile2, _ = ctx2.chunk(0)
+    assert np.abs(tile - tile2).max() < 1e-14

@@ -201,6 +201,16 @@ class Context:
         f(self.handle, _p(q))
         return q
 
+    def block(self, row, col, nrow, ncol):
+        """nrow x ncol rectangle (global row offset, this rank's column offset) of the LAST chunk's tile."""
+        f = self.lib.cintb200_debug_block
+        f.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        out = np.zeros((nrow, ncol), order="F")
+        if f(self.handle, row, col, nrow, ncol, _p(out)) != 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        return out
+
     def launch_rows(self):
         """Launch list of the cached whole-job plan in execution order (see driver.cu)."""
         f = self.lib.cintb200_debug_launch_rows

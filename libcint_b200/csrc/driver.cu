@@ -648,3 +648,20 @@ extern "C" int cintb200_debug_launch_rows(cintb200_ctx *c, double *rows, int max
     }
     return n;
 }
+
+// Fetch an nrow x ncol rectangle (column-major, leading dimension nrow) of the LAST chunk's tile, still resident in
+// device buffer 0 after a run without host sink: verification of full-size jobs without copying whole tiles.
+extern "C" int cintb200_debug_block(cintb200_ctx *c, long long row, long long col, int nrow, int ncol, double *host_out)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan) return b200_fail(CINTB200_EINVAL, "run cintb200_int2e_sph_all_unique first");
+    JobPlan *plan = c->plan;
+    const int ch = (int)plan->chunks.size() - 1;
+    const long long row0 = plan->rows_before[plan->chunks[ch].first];
+    const long long ld = plan->rows_before[plan->chunks[ch].second] - row0;
+    if (row < row0 || row + nrow > row0 + ld || col < 0 || col + ncol > plan->chunk_cols[ch])
+        return b200_fail(CINTB200_EINVAL, "rectangle outside the last chunk");
+    CU_OK(cudaSetDevice(c->device));
+    CU_OK(cudaMemcpy2D(host_out, sizeof(double) * nrow, plan->d_out[0] + (row - row0) + col * ld, sizeof(double) * ld,
+                       sizeof(double) * nrow, ncol, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -159,3 +159,34 @@ def test_schwarz_bounds_and_screened_job():
     ctx2.all_unique(chunk_bytes=1 << 30)
     tile2, _ = ctx2.chunk(0)
     assert np.abs(tile - tile2).max() < 1e-14
+
+
+def test_c60_full_size_bench_configuration():
+    # BASELINE.json configs[1] exactly as bench.py runs it (80 GB tile buffer, 7 chunks): sampled blocks of the last
+    # chunk against the oracle, plus the size-independent property (ij|kl) == (kl|ij)^T between different blocks
+    which, _ = ou.best()
+    atm, bas, env = cb.load_fixture("c60_ccpvdz")
+    ctx = cb.Context(atm, bas, env)
+    st = ctx.all_unique(chunk_bytes=80 << 30)
+    assert st[0] == 1023783775
+    geom = np.zeros(8, dtype=np.int64)
+    ctx.lib.cintb200_debug_chunk(ctx.handle, int(st[9]) - 1, None, 0, geom.ctypes.data_as(__import__("ctypes").c_void_p))
+    i0, i1 = int(geom[0]), int(geom[1])
+    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    rng = np.random.default_rng(80)
+    for n in range(400):
+        i = int(rng.integers(i0, i1)); j = int(rng.integers(0, i + 1))
+        k = int(rng.integers(0, i + 1)); l = int(rng.integers(0, k + 1))
+        if n % 4 == 0:                       # force diagonal kets (k inside the chunk's own shell range)
+            k = int(rng.integers(i0, i + 1)); l = int(rng.integers(0, k + 1))
+        r, _ = ctx.pair_offsets(i, j)
+        _, c = ctx.pair_offsets(k, l)
+        nb, nk = dims[i] * dims[j], dims[k] * dims[l]
+        got = ctx.block(r, c, nb, nk)
+        want, _ = ou.eval_tuple(which, "int2e_sph", (i, j, k, l), atm, bas, env)
+        assert np.abs(got - want.reshape((nb, nk), order="F")).max() <= 1e-12 * max(1.0, np.abs(want).max()), (i, j, k, l)
+        if k >= i0 and i <= k:               # i == k: the transposed block (kl|ij) with i <= k is also part of the job
+            r2, _ = ctx.pair_offsets(k, l)
+            _, c2 = ctx.pair_offsets(i, j)
+            tr = ctx.block(r2, c2, nk, nb)
+            assert np.abs(tr - got.T).max() < 1e-13

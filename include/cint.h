@@ -76,6 +76,11 @@ CINTIntegralFunction  int3c2e_sph;          /* src/cint3c2e.c:693 */
 CINTIntegralFunction  int3c2e_cart;         /* src/cint3c2e.c:710 */
 CINTOptimizerFunction int3c2e_optimizer;    /* src/cint3c2e.c:702 */
 
+/* ---- 2-centre ERIs (density-fitting metric): src/cint2c2e.c:351-375 ---- */
+CINTIntegralFunction  int2c2e_sph;          /* src/cint2c2e.c:351 */
+CINTIntegralFunction  int2c2e_cart;         /* src/cint2c2e.c:368 */
+CINTOptimizerFunction int2c2e_optimizer;    /* src/cint2c2e.c:360 */
+
 /* ---- v2-style wrappers (src/misc.h:35-61 ALL_CINT, include/cint.h.in:264-278) ---- */
 FINT cint2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 FINT cint2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
@@ -85,6 +90,10 @@ FINT cint3c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT
 FINT cint3c2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 void cint3c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 void cint3c2e_cart_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
+FINT cint2c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+FINT cint2c2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+void cint2c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
+void cint2c2e_cart_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 
 /* ---- optimizer life cycle: src/optimizer.c:22-72 ---- */
 void CINTinit_2e_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);

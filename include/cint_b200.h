@@ -57,6 +57,11 @@ long cintb200_int2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n
 long cintb200_int3c2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
                             const size_t *out_off, double *out, int on_device, int *nonzero);
 
+/* Same for shell pairs (i|k), shls[2*t .. 2*t+1]; block (di,dk): the density-fitting metric.  int2c2e_sph/_cart,
+ * src/cint2c2e.c:351,368 (same Rys engine with aj = al = 0, src/g2c2e.c:15-100). */
+long cintb200_int2c2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                            const size_t *out_off, double *out, int on_device, int *nonzero);
+
 /* Size in doubles of one block / of a packed batch (host-side helper). */
 size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, int ncenter);
 

@@ -37,7 +37,7 @@ def load_library():
     lib.cintb200_create.restype = ci
     lib.cintb200_destroy.argtypes = [vp]
     lib.cintb200_destroy.restype = None
-    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch"):
+    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch"):
         f = getattr(lib, name)
         f.argtypes = [vp, ci, vp, sz, vp, vp, ci, vp]
         f.restype = ctypes.c_long
@@ -60,11 +60,11 @@ def load_library():
         lib.cintb200_debug_profile.restype = None
         lib.cintb200_debug_profile_rows.argtypes = [vp, vp, ci]
         lib.cintb200_debug_profile_rows.restype = ci
-    for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart"):
+    for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart", "int2c2e_sph", "int2c2e_cart"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
         f.restype = ci
-    for name in ("cint2e_sph", "cint2e_cart", "cint3c2e_sph", "cint3c2e_cart"):
+    for name in ("cint2e_sph", "cint2e_cart", "cint3c2e_sph", "cint3c2e_cart", "cint2c2e_sph", "cint2c2e_cart"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, ci, vp, ci, vp, vp]
         f.restype = ci
@@ -144,6 +144,10 @@ class Context:
 
     def int3c2e_batch(self, shls, kind=SPH, **kw):
         return self._batch(self.lib.cintb200_int3c2e_batch, 3, shls, kind, **kw)
+
+    def int2c2e_batch(self, shls, kind=SPH, **kw):
+        """Shell pairs (i|k): the 2-centre Coulomb metric of density fitting (src/cint2c2e.c:351)."""
+        return self._batch(self.lib.cintb200_int2c2e_batch, 2, shls, kind, **kw)
 
     def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
         """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array."""
@@ -259,6 +263,14 @@ def int3c2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
 
 def int3c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int3c2e_cart", 3, shls, atm, bas, env, opt, dims, out, cart=True)
+
+
+def int2c2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int2c2e_sph", 2, shls, atm, bas, env, opt, dims, out)
+
+
+def int2c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
+    return _call_single("int2c2e_cart", 2, shls, atm, bas, env, opt, dims, out, cart=True)
 
 
 def plan_summary(atm, bas, env, rank=0, nranks=1, chunk_bytes=0):

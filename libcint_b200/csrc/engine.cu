@@ -388,10 +388,23 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         const int *s = shls + t * ncenter;
         for (int m = 0; m < ncenter; m++)
             if (s[m] < 0 || s[m] >= c->nbas) return b200_fail(CINTB200_EINVAL, "tuple %zu: shell id %d out of range", t, s[m]);
+        Task &T = tasks[t];
+        if (ncenter == 2) {
+            // (i|k): both sides are single-shell pseudo pairs (aj = al = 0, src/g2c2e.c:15-100); block (di,dk)
+            const int i = s[0], k = s[1];
+            const long long di = shell_dim(c->shells[i], cart), dk = shell_dim(c->shells[k], cart);
+            T.bra = (int)(npair2 + i); T.ket = (int)(npair2 + k);
+            T.sa = 1; T.sb = 0; T.sc = di; T.sd = 0;
+            offs[t] = out_off ? out_off[t] : total;
+            T.off = (long long)offs[t];
+            total = std::max(total, offs[t] + (size_t)(di * dk));
+            const PairHdr &hb = c->pairs[T.bra], &hk = c->pairs[T.ket];
+            keys[t] = ClassKey{hb.la, hb.lb, hk.la, hk.lb, hb.nca * hb.ncb, hk.nca * hk.ncb};
+            continue;
+        }
         const int i = s[0], j = s[1], k = s[2], l = (ncenter == 4) ? s[3] : -1;
         const long long di = shell_dim(c->shells[i], cart), dj = shell_dim(c->shells[j], cart);
         const long long dk = shell_dim(c->shells[k], cart), dl = (l >= 0) ? shell_dim(c->shells[l], cart) : 1;
-        Task &T = tasks[t];
         T.bra = (int)((i >= j) ? (size_t)i * (i + 1) / 2 + j : (size_t)j * (j + 1) / 2 + i);
         const PairHdr &hb = c->pairs[T.bra];
         const long long si = 1, sj = di, sk = di * dj, sl = di * dj * dk;
@@ -486,6 +499,10 @@ extern "C" long cintb200_int2e_batch(cintb200_ctx *c, int kind, const int *shls,
 extern "C" long cintb200_int3c2e_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
                                        double *out, int on_device, int *nonzero)
 { return run_batch(c, 3, kind, shls, n, out_off, out, on_device, nonzero); }
+
+extern "C" long cintb200_int2c2e_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                       double *out, int on_device, int *nonzero)
+{ return run_batch(c, 2, kind, shls, n, out_off, out, on_device, nonzero); }
 
 // ------------------------------------------------------------------ Schwarz bounds (device)
 // q[p] = sqrt(max |(ij|ij)|) over the block of shell pair p: |(ij|kl)| <= q[ij] q[kl].  The reference has no
@@ -611,7 +628,7 @@ static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT
     long rc = run_batch(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz);
     if (rc < 0) return 0;
     // embed into the caller's larger tensor: leading dimensions dims[] (src/cint2e.c:853-856)
-    const size_t ni = dims[0], nj = dims[1], nk = dims[2];
+    const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1;
     for (size_t l = 0; l < d[3]; l++)
         for (size_t k = 0; k < d[2]; k++)
             for (size_t j = 0; j < d[1]; j++)
@@ -628,6 +645,19 @@ CACHE_SIZE_T int3c2e_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT na
 { (void)cache; return drop_in(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
 CACHE_SIZE_T int3c2e_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
 { (void)cache; return drop_in(3, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+
+CACHE_SIZE_T int2c2e_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in(2, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+CACHE_SIZE_T int2c2e_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in(2, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+void int2c2e_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+FINT cint2c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int2c2e_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+FINT cint2c2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int2c2e_cart(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+void cint2c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env) { int2c2e_optimizer(opt, atm, natm, bas, nbas, env); }
+void cint2c2e_cart_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env) { int2c2e_optimizer(opt, atm, natm, bas, nbas, env); }
 
 void int2e_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
 { *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }

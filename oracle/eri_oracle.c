@@ -165,8 +165,16 @@ static int eri_tuple(double *out, const int *dims, const int *shls, int ncenter,
         static const double zero_exp[1] = {0.0}, one_coef[1] = {1.0};
         int n, ic;
         (void)natm; (void)nbas;
-        for (n = 0; n < ncenter; n++) load_shell(&sh[n], shls[n], atm, bas, env);
-        if (ncenter == 3) {
+        if (ncenter == 2) {
+                /* (i|k): aj = al = 0, rij = ri, rkl = rk (src/g2c2e.c:15-100); no primitive screening (src/cint2c2e.c:113-150) */
+                load_shell(&sh[0], shls[0], atm, bas, env);
+                load_shell(&sh[2], shls[1], atm, bas, env);
+                sh[1].l = 0; sh[1].nprim = 1; sh[1].nctr = 1;
+                sh[1].r = sh[0].r; sh[1].a = zero_exp; sh[1].c = one_coef; sh[1].logmaxc[0] = 0;
+        } else {
+                for (n = 0; n < ncenter; n++) load_shell(&sh[n], shls[n], atm, bas, env);
+        }
+        if (ncenter <= 3) {
                 sh[3].l = 0; sh[3].nprim = 1; sh[3].nctr = 1;
                 sh[3].r = sh[2].r; sh[3].a = zero_exp; sh[3].c = one_coef; sh[3].logmaxc[0] = 0;
         }
@@ -178,9 +186,11 @@ static int eri_tuple(double *out, const int *dims, const int *shls, int ncenter,
         const double omega = env[PTR_RANGE_OMEGA];
 
         double common = (M_PI * M_PI * M_PI) * 2 / 1.7724538509055160272981674833411451
-                * fac_sp(li) * fac_sp(lj) * fac_sp(lk);
+                * fac_sp(li) * (ncenter == 2 ? 1.0 : fac_sp(lj)) * fac_sp(lk);
         double expcutoff;
-        if (ncenter == 4) {
+        if (ncenter == 2) {
+                expcutoff = 1e300;
+        } else if (ncenter == 4) {
                 common *= fac_sp(ll);
                 expcutoff = (env[PTR_EXPCUTOFF] == 0) ? 60 : fmax(40, env[PTR_EXPCUTOFF]) + 1;
         } else {
@@ -193,8 +203,8 @@ static int eri_tuple(double *out, const int *dims, const int *shls, int ncenter,
         const int di = (sph ? 2 * li + 1 : nfi), dj = (sph ? 2 * lj + 1 : nfj);
         const int dk = (sph ? 2 * lk + 1 : nfk), dl = (ncenter == 4) ? (sph ? 2 * ll + 1 : nfl) : 1;
         const size_t ni = dims ? dims[0] : (size_t)di * nci;
-        const size_t nj = dims ? dims[1] : (size_t)dj * ncj;
-        const size_t nk = dims ? dims[2] : (size_t)dk * nck;
+        const size_t nj = (ncenter == 2) ? 1 : dims ? dims[1] : (size_t)dj * ncj;
+        const size_t nk = (ncenter == 2) ? 1 : dims ? dims[2] : (size_t)dk * nck;
 
         double *gctr = calloc((size_t)nc * nf, sizeof(double));
         int nonempty = 0;
@@ -520,3 +530,9 @@ int oracle_int3c2e_sph(double *out, const int *dims, const int *shls, const int 
 int oracle_int3c2e_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                         const int *bas, int nbas, const double *env)
 { return eri_tuple(out, dims, shls, 3, 0, atm, natm, bas, nbas, env); }
+int oracle_int2c2e_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                       const int *bas, int nbas, const double *env)
+{ return eri_tuple(out, dims, shls, 2, 1, atm, natm, bas, nbas, env); }
+int oracle_int2c2e_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                        const int *bas, int nbas, const double *env)
+{ return eri_tuple(out, dims, shls, 2, 0, atm, natm, bas, nbas, env); }

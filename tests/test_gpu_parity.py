@@ -69,6 +69,37 @@ def test_known_answer_int3c2e_sph():
     assert round(abs(tot - 1586.350797347553) / cnt ** .5, 10) == 0
 
 
+def test_known_answer_int2c2e_sph():
+    # testsuite/test_3c2e.py:266-294,318 through our cint2c2e_sph / batch entry points
+    which, _ = ou.best()
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    ctx = cb.Context(atm, bas, env)
+    t = np.array([(i, k) for k in range(8) for i in range(8)], np.int32)
+    v, o, s, nz = ctx.int2c2e_batch(t)
+    want = ou.eval_many(which, "int2c2e_sph", t, atm, bas, env)
+    assert_blocks_close(split(v, o, s), want, t, what="int2c2e_sph")
+    tot = sum(np.abs(b).sum() for b, sh in zip(split(v, o, s), t) if sh[0] < 4 and sh[1] < 4)
+    assert abs(tot - 782.3104849606677) < 1e-9
+    assert nz.all()
+    v, o, s, nz = ctx.int2c2e_batch(t, kind=cb.CART)
+    want = ou.eval_many(which, "int2c2e_cart", t, atm, bas, env)
+    assert_blocks_close(split(v, o, s), want, t, what="int2c2e_cart")
+    # drop-in symbol with dims embedding (out is a window of a larger matrix)
+    big = np.full((40, 30), 7.0, order="F")
+    d = cb.shell_dims(bas, (1, 3))
+    sub, rc = cb.int2c2e_sph((1, 3), atm, bas, env, dims=(40, 30), out=big)
+    ref_blk, _ = ou.eval_tuple(which, "int2c2e_sph", (1, 3), atm, bas, env)
+    assert np.abs(big[:d[0], :d[1]] - ref_blk.reshape(d, order="F")).max() < 1e-12 and rc == 1
+    assert (big[d[0]:, :] == 7.0).all() and (big[:, d[1]:] == 7.0).all()
+    # range-separated metric: long-range + short-range == full
+    for om in (0.3, -0.3):
+        e2 = env.copy()
+        e2[8] = om
+        v2, o2, s2, _ = cb.Context(atm, bas, e2).int2c2e_batch(t)
+        w2 = ou.eval_many(which, "int2c2e_sph", t, atm, bas, e2)
+        assert_blocks_close(split(v2, o2, s2), w2, t, tol=1e-10 if om < 0 else TOL, what="int2c2e omega %g" % om)
+
+
 def test_golden_testbasis_all_quartets():
     g = np.load(os.path.join(GOLD, "testbasis.npz"))
     atm, bas, env = reference_test_basis(with_fit_shells=True)

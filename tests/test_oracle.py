@@ -47,6 +47,22 @@ def test_known_answer_int3c2e_sph():
     assert round(abs(tot - 1586.350797347553) / cnt ** .5, 10) == 0
 
 
+def test_known_answer_int2c2e_sph():
+    # testsuite/test_3c2e.py:266-294,318: sum over i,k < 4 == 782.3104849606677 (10 places) and element-wise equality
+    # with int3c2e_sph whose second shell is the zero-exponent s shell placed on atom(i)
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    tot, cnt = 0.0, 0
+    for k in range(4):
+        for i in range(4):
+            bas[9, 0] = bas[i, 0]
+            v2, _ = ou.eval_tuple("port", "int2c2e_sph", (i, k), atm, bas, env)
+            v3, _ = ou.eval_tuple("port", "int3c2e_sph", (i, 9, k), atm, bas, env)
+            assert np.abs(v2 - v3).max() <= 1e-12 * max(1.0, np.abs(v3).max())
+            tot += np.abs(v2).sum()
+            cnt += v2.size
+    assert round(abs(tot - 782.3104849606677) / cnt ** .5, 10) == 0
+
+
 def test_port_vs_golden_testbasis():
     g = np.load(os.path.join(GOLD, "testbasis.npz"))
     atm, bas, env = reference_test_basis(with_fit_shells=True)

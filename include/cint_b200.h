@@ -80,6 +80,17 @@ size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, i
 int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
                                   double *host_sink, double *stats);
 
+/*
+ * Whole-job driver for density fitting: every shell triple (ij|k) of int3c2e_sph (src/cint3c2e.c:693) with orbital
+ * shells i >= j in [0, aux_shell0) and auxiliary shells k in [aux_shell0, nbas) -- orbital and auxiliary basis share one
+ * bas array, as in the reference's callers.  Output tiles are column-major out[row(ij) + ld * col(k)]: a row block is
+ * the (di, dj) block of the shell pair laid out like the reference's buf (i fastest), a column block the dk functions
+ * of shell k.  Rows are streamed through the device buffer chunk by chunk (ranges of i); the auxiliary shells are dealt
+ * round-robin to the ranks inside every (l, nctr) class (static sharding, no communication).  host_sink / stats as above.
+ */
+int cintb200_int3c2e_sph_all(cintb200_ctx *ctx, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
+                             double *host_sink, double *stats);
+
 /* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
  * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity
  * tolerance by construction); 0 switches it off.  The bounds are evaluated on the device on first use.
@@ -93,6 +104,10 @@ int cintb200_schwarz_bounds(cintb200_ctx *ctx, double *q);
  * out[7] kernel launches, out[8] bytes of one tile buffer. */
 int cintb200_plan_summary(const int *atm, int natm, const int *bas, int nbas, const double *env,
                           int rank, int nranks, size_t chunk_bytes, double *out);
+
+/* Same for the density-fitting job cintb200_int3c2e_sph_all (out[0] counts shell triples, out[4] this rank's auxiliary columns). */
+int cintb200_plan_summary_3c(const int *atm, int natm, const int *bas, int nbas, const double *env, int aux_shell0,
+                             int rank, int nranks, size_t chunk_bytes, double *out);
 
 /* Measured FP64 FMA peak of the device in TFLOP/s (DFMA-chain microbenchmark run for about `seconds`);
  * the roofline denominator of bench.py, since MEASURED_PEAKS.json has no FP64 entry. */

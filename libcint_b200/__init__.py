@@ -159,6 +159,27 @@ class Context:
         return stats
 
 
+    def int3c2e_all(self, aux_shell0, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
+        """Whole density-fitting job: every (ij|k), orbital shells i >= j < aux_shell0 <= k (cintb200_int3c2e_sph_all)."""
+        f = self.lib.cintb200_int3c2e_sph_all
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        stats = np.zeros(16)
+        rc = f(self.handle, aux_shell0, rank, nranks, chunk_bytes, ctypes.c_void_p(host_sink) if host_sink else None, _p(stats))
+        if rc < 0:
+            raise B200Error("int3c2e_all failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return stats
+
+    def aux_offset(self, k):
+        """This rank's column offset of auxiliary shell k in the tiles of int3c2e_all (-1: owned by another rank)."""
+        f = self.lib.cintb200_debug_aux_offset
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        col = ctypes.c_longlong()
+        if f(self.handle, k, ctypes.byref(col)) != 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        return col.value
+
     # ---- verification helpers (tests only) ----
     def force_generic(self, on=True):
         self.lib.cintb200_debug_force_generic(self.handle, int(on))
@@ -273,14 +294,20 @@ def int2c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int2c2e_cart", 2, shls, atm, bas, env, opt, dims, out, cart=True)
 
 
-def plan_summary(atm, bas, env, rank=0, nranks=1, chunk_bytes=0):
-    """Static sharding of the whole job (host only, no GPU): dict of counts for `rank` of `nranks`."""
+def plan_summary(atm, bas, env, rank=0, nranks=1, chunk_bytes=0, aux_shell0=None):
+    """Static sharding of the whole job (host only, no GPU): dict of counts for `rank` of `nranks`.
+    aux_shell0 given -> the density-fitting job (ij|k) with auxiliary shells [aux_shell0, nbas)."""
     lib = load_library()
     atm, bas, env = _as_basis(atm, bas, env)
     out = np.zeros(16)
     lib.cintb200_plan_summary.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
-    rc = lib.cintb200_plan_summary(_p(atm), len(atm), _p(bas), len(bas), _p(env), rank, nranks, chunk_bytes, _p(out))
+    lib.cintb200_plan_summary_3c.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p]
+    if aux_shell0 is not None:
+        rc = lib.cintb200_plan_summary_3c(_p(atm), len(atm), _p(bas), len(bas), _p(env), aux_shell0, rank, nranks, chunk_bytes, _p(out))
+    else:
+        rc = lib.cintb200_plan_summary(_p(atm), len(atm), _p(bas), len(bas), _p(env), rank, nranks, chunk_bytes, _p(out))
     if rc != 0:
         raise B200Error(lib.cintb200_last_error().decode())
     keys = ("quartets", "integrals", "prim_quartets", "model_flops", "columns", "rows", "chunks", "launches", "tile_bytes")

@@ -50,7 +50,10 @@ struct LaunchRec;
 struct JobPlan {
     int rank = 0, nranks = 1;
     size_t chunk_bytes = 0;
+    int ncenter = 4, aux0 = 0;              // 3: rows = orbital pairs of shells [0, aux0), columns = auxiliary shells [aux0, nbas)
     std::vector<PairClass> classes;
+    std::vector<PairClass> uclasses;        // 3-centre jobs: classes of the single-shell pseudo pairs (kets); 4-centre: unused
+    std::vector<long long> colof_aux;       // 3-centre jobs: this rank's column offset of auxiliary shell aux0 + n, or -1
     std::vector<long long> rowoff;          // per pair id
     std::vector<long long> rows_before;     // [nbas+1] rows of pairs with I < i
     std::vector<long long> cols_before;     // [nbas+1] this rank's columns of kets with K < i
@@ -80,6 +83,7 @@ struct JobPlan {
 void jobplan_free(JobPlan *p)
 {
     if (!p) return;
+    for (PairClass &c : p->uclasses) { cudaFree(c.d_tpair); cudaFree(c.d_tI); cudaFree(c.d_ucol); cudaFree(c.d_ustride); }
     for (PairClass &c : p->classes) {
         cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
@@ -128,8 +132,12 @@ static void model_flops(int li, int lj, int lk, int ll, int nc, double *per_prim
 
 static int build_plan(CINTOpt *c, JobPlan *plan)
 {
-    const int nbas = c->nbas, nranks = plan->nranks, rank = plan->rank;
+    const int nranks = plan->nranks, rank = plan->rank;
+    const bool three = plan->ncenter == 3;
+    const int nbas = three ? plan->aux0 : c->nbas;          // shells that form the bra pairs (rows)
     const size_t npair = (size_t)nbas * (nbas + 1) / 2;
+    long long aux_cols = 0;                                 // 3-centre: spherical AOs of all auxiliary shells
+    if (three) for (int k = plan->aux0; k < c->nbas; k++) aux_cols += (2 * c->shells[k].l + 1) * c->shells[k].nctr;
     auto pair_dim = [&](int i, int j) {
         const ShellInfo &si = c->shells[i], &sj = c->shells[j];
         return (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
@@ -171,7 +179,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     //    per-chunk reordering, the buffer is then sized from the exact maximum)
     const size_t cap = plan->chunk_bytes / sizeof(double);
     const long long slack = maxdim * (long long)plan->classes.size() * 2;
-    auto est_cols = [&](int i1) { return (size_t)(tcols_before[i1] / nranks + slack); };
+    auto est_cols = [&](int i1) { return (size_t)((three ? aux_cols : tcols_before[i1]) / nranks + slack); };
     int i0 = 0;
     while (i0 < nbas) {
         int i1 = i0 + 1;
@@ -214,7 +222,55 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     plan->cols_before.assign(nbas + 1, 0);
     long long cols = 0;
     size_t need = 1;
-    for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
+    if (three) {
+        // kets = single-shell pseudo pairs of the auxiliary shells (pair ids npair_all + k, engine.cu:build_pairs), grouped
+        // by (l, nctr); dealt round-robin to the ranks inside every class; every chunk (range of bra shells) needs all of them
+        const size_t npair_all = (size_t)c->nbas * (c->nbas + 1) / 2;
+        std::map<std::vector<int>, int> ukey;
+        for (int k = plan->aux0; k < c->nbas; k++) {
+            const ShellInfo &sk = c->shells[k];
+            std::vector<int> key = {sk.l, sk.nctr};
+            auto it = ukey.find(key);
+            int ci;
+            if (it == ukey.end()) {
+                ci = (int)plan->uclasses.size();
+                ukey[key] = ci;
+                PairClass pc;
+                pc.la = sk.l; pc.lb = 0; pc.nca = sk.nctr; pc.ncb = 1; pc.Q = 1;
+                plan->uclasses.push_back(pc);
+            } else ci = it->second;
+            PairClass &pc = plan->uclasses[ci];
+            pc.ids.push_back((int)(npair_all + k));
+            pc.I.push_back(k);
+            pc.npp.push_back(sk.nprim);
+            pc.Q = std::max(pc.Q, sk.nprim);
+        }
+        plan->colof_aux.assign(c->nbas - plan->aux0, -1);
+        for (PairClass &pc : plan->uclasses) {
+            const size_t NU = pc.ids.size();
+            std::vector<long long> ucol(NU, -1);
+            std::vector<int> ustride(2 * NU, 0);
+            for (size_t n = 0; n < NU; n++) {
+                ustride[n] = 1;                                 // stride of the auxiliary index in columns; no second ket index
+                if ((int)(n % nranks) != rank) continue;
+                ucol[n] = cols;
+                plan->colof_aux[pc.I[n] - plan->aux0] = cols;
+                cols += (2 * pc.la + 1) * pc.nca;
+            }
+            pc.npp_prefix.assign(NU + 1, 0);
+            for (size_t n = 0; n < NU; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
+            pc.chunk_lo.assign(plan->chunks.size() + 1, (int)NU);
+            if (plan->host_only) continue;
+            if (upload(&pc.d_tpair, pc.ids) || upload(&pc.d_tI, pc.I) || upload(&pc.d_ucol, ucol) || upload(&pc.d_ustride, ustride))
+                return CINTB200_ENOMEM;
+        }
+        for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
+            plan->chunk_cols.push_back(cols);
+            const size_t r = (size_t)(plan->rows_before[plan->chunks[ch].second] - plan->rows_before[plan->chunks[ch].first]);
+            need = std::max(need, r * (size_t)std::max<long long>(cols, 1));
+        }
+    }
+    for (size_t ch = 0; ch < plan->chunks.size() && !three; ch++) {
         for (int i = plan->chunks[ch].first; i < plan->chunks[ch].second; i++) plan->cols_before[i] = cols;   // lower bound only
         for (PairClass &pc : plan->classes)
             for (int k = pc.chunk_lo[ch]; k < pc.chunk_lo[ch + 1]; k++) {
@@ -341,11 +397,13 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
             std::vector<double> cnt_ge(i1 - i0 + 1, 0.0), npp_ge(i1 - i0 + 1, 0.0);
             for (int t = t_begin; t < t_end; t++) { cnt_ge[T.I[t] - i0] += 1; npp_ge[T.I[t] - i0] += T.npp[t]; }
             for (int k = i1 - i0 - 1; k >= 0; k--) { cnt_ge[k] += cnt_ge[k + 1]; npp_ge[k] += npp_ge[k + 1]; }
-            for (size_t cu = 0; cu < plan->classes.size(); cu++) {
-              PairClass &U = plan->classes[cu];
+            std::vector<PairClass> &UC = (plan->ncenter == 3) ? plan->uclasses : plan->classes;
+            for (size_t cu = 0; cu < UC.size(); cu++) {
+              PairClass &U = UC[cu];
               // part 0: kets below the chunk's shell range (every bra of the chunk is valid; bras sorted by primitive count)
               // part 1: kets inside it (valid bras = those with I >= K: a suffix of the shell-sorted ordering B)
-              for (int part = 0; part < 2; part++) {
+              // 3-centre jobs: every auxiliary ket meets every bra pair of the chunk -> part 0 only, all kets
+              for (int part = 0; part < (plan->ncenter == 3 ? 1 : 2); part++) {
                 const int u_lo = part == 0 ? 0 : U.chunk_lo[ch], u_hi = part == 0 ? U.chunk_lo[ch] : U.chunk_lo[ch + 1];
                 // this rank's kets in [u_lo, u_hi): indices congruent to rank modulo nranks
                 int u_first = u_lo + ((rank - u_lo) % nranks + nranks) % nranks;
@@ -375,7 +433,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 double q_here = 0, prim_here = 0;
                 for (int j = 0; j < nu_mine; j++) {
                     const int u = u_first + nranks * j;
-                    const int kk = std::max(U.I[u], i0) - i0;          // K < i0: every T pair of the chunk is valid
+                    const int kk = (plan->ncenter == 3) ? 0 : std::max(U.I[u], i0) - i0;   // K < i0: every T pair of the chunk is valid
                     q_here += cnt_ge[kk];
                     prim_here += (double)U.npp[u] * npp_ge[kk];
                 }
@@ -428,19 +486,24 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
     return 0;
 }
 
-extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes,
-                                             double *host_sink, double *stats)
+// ncenter = 4: every unique quartet of int2e_sph; ncenter = 3: every triple (ij|k), i >= j < aux0 <= k, of int3c2e_sph
+static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks, size_t chunk_bytes,
+                   double *host_sink, double *stats)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (nranks < 1 || rank < 0 || rank >= nranks) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
-    if (c->schwarz_thr > 0 && c->omega == 0 && !c->force_generic && ctx_compute_schwarz(c)) return CINTB200_ENODEV;
+    if (ncenter == 3 && (aux0 < 1 || aux0 >= c->nbas))
+        return b200_fail(CINTB200_EINVAL, "first auxiliary shell %d outside 1..%d", aux0, c->nbas - 1);
+    if (ncenter == 4 && c->schwarz_thr > 0 && c->omega == 0 && !c->force_generic && ctx_compute_schwarz(c)) return CINTB200_ENODEV;
     std::lock_guard<std::mutex> lock(c->mtx);
     CU_OK(cudaSetDevice(c->device));
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
     JobPlan *plan = c->plan;
-    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic || plan->schwarz_thr != c->schwarz_thr) {
+    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic
+        || plan->schwarz_thr != c->schwarz_thr || plan->ncenter != ncenter || plan->aux0 != (ncenter == 3 ? aux0 : 0)) {
         if (plan) { cudaDeviceSynchronize(); jobplan_free(plan); c->plan = nullptr; }
         plan = new JobPlan();
+        plan->ncenter = ncenter; plan->aux0 = (ncenter == 3) ? aux0 : 0;
         plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic; plan->schwarz_thr = c->schwarz_thr;
         int rc = build_plan(c, plan);
         if (!rc) rc = build_launches(c, plan);
@@ -454,7 +517,7 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
                          "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
     EngineParams EP;
     EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
-    EP.expcutoff = c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
+    EP.expcutoff = (ncenter == 3) ? c->expcutoff3 : c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
 
     double d2h = 0;
     long long nlaunch = 0, reg_launches = 0;
@@ -559,6 +622,14 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
     return 0;
 }
 
+extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes,
+                                             double *host_sink, double *stats)
+{ return run_job(c, 4, 0, rank, nranks, chunk_bytes, host_sink, stats); }
+
+extern "C" int cintb200_int3c2e_sph_all(cintb200_ctx *c, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
+                                        double *host_sink, double *stats)
+{ return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, host_sink, stats); }
+
 // Copy a rectangle of the most recent tile of chunk `chunk` ... (verification helper for tests):
 // evaluates ONE chunk and returns it on the host together with its geometry.
 extern "C" int cintb200_debug_chunk(cintb200_ctx *c, int chunk, double *host_out, size_t host_cap, long long *geom)
@@ -590,8 +661,19 @@ extern "C" int cintb200_debug_pair_offsets(cintb200_ctx *c, int i, int j, long l
     JobPlan *plan = c->plan;
     if (i < j) std::swap(i, j);
     const int p = i * (i + 1) / 2 + j;
+    if ((size_t)p >= plan->rowoff.size()) return b200_fail(CINTB200_EINVAL, "pair (%d,%d) is not a bra pair of the cached job", i, j);
     *row = plan->rowoff[p];
     *col_owner_rank = plan->colof[p];       // -1: another rank owns this ket
+    return 0;
+}
+
+// 3-centre jobs: this rank's column offset of auxiliary shell k (-1: another rank owns it)
+extern "C" int cintb200_debug_aux_offset(cintb200_ctx *c, int k, long long *col)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan || c->plan->ncenter != 3) return b200_fail(CINTB200_EINVAL, "no 3-centre plan");
+    JobPlan *plan = c->plan;
+    if (k < plan->aux0 || k >= c->nbas) return b200_fail(CINTB200_EINVAL, "shell %d is not an auxiliary shell", k);
+    *col = plan->colof_aux[k - plan->aux0];
     return 0;
 }
 
@@ -610,14 +692,16 @@ extern "C" int cintb200_debug_profile_rows(cintb200_ctx *c, double *rows, int ma
 //   out[0] shell quartets   out[1] integrals   out[2] primitive quartets   out[3] model flops
 //   out[4] columns owned    out[5] total rows  out[6] chunks               out[7] kernel launches
 //   out[8] tile buffer bytes
-extern "C" int cintb200_plan_summary(const int *atm, int natm, const int *bas, int nbas, const double *env,
-                                     int rank, int nranks, size_t chunk_bytes, double *out)
+static int plan_summary(int ncenter, int aux0, const int *atm, int natm, const int *bas, int nbas, const double *env,
+                        int rank, int nranks, size_t chunk_bytes, double *out)
 {
     if (nranks < 1 || rank < 0 || rank >= nranks || !out) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (ncenter == 3 && (aux0 < 1 || aux0 >= nbas)) return b200_fail(CINTB200_EINVAL, "first auxiliary shell %d outside 1..%d", aux0, nbas - 1);
     CINTOpt *c = nullptr;
     int rc = ctx_new_host(&c, atm, natm, bas, nbas, env);
     if (rc) return rc;
     JobPlan *plan = new JobPlan();
+    plan->ncenter = ncenter; plan->aux0 = (ncenter == 3) ? aux0 : 0; nbas = (ncenter == 3) ? aux0 : nbas;
     plan->rank = rank; plan->nranks = nranks; plan->host_only = 1;
     plan->chunk_bytes = chunk_bytes ? chunk_bytes : (size_t)16 << 30;
     rc = build_plan(c, plan);
@@ -632,6 +716,14 @@ extern "C" int cintb200_plan_summary(const int *atm, int natm, const int *bas, i
     cintb200_destroy(c);
     return rc;
 }
+
+extern "C" int cintb200_plan_summary(const int *atm, int natm, const int *bas, int nbas, const double *env,
+                                     int rank, int nranks, size_t chunk_bytes, double *out)
+{ return plan_summary(4, 0, atm, natm, bas, nbas, env, rank, nranks, chunk_bytes, out); }
+
+extern "C" int cintb200_plan_summary_3c(const int *atm, int natm, const int *bas, int nbas, const double *env, int aux_shell0,
+                                        int rank, int nranks, size_t chunk_bytes, double *out)
+{ return plan_summary(3, aux_shell0, atm, natm, bas, nbas, env, rank, nranks, chunk_bytes, out); }
 
 // Launch list of the cached plan in execution order: rows of 12 doubles
 // {chunk, la, lb, lc, ld, nct, ncu, kind (0 generic, 1 register, 2 cooperative), part, quartets, integrals, model flops}.

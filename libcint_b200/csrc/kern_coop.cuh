@@ -234,9 +234,14 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             }
             __syncwarp();
             // --- quadrature sum for my f ---
-            double val[NE];
+            // one contraction combination: the coefficient is folded into the z column and the products are added
+            // straight into the accumulators (no per-primitive val[] block: NE registers and NE FMAs less)
+            double val[NCOMB == 1 ? 1 : NE];
+            if constexpr (NCOMB > 1) {
 #pragma unroll
-            for (int e = 0; e < NE; e++) val[e] = 0.0;
+                for (int e = 0; e < NE; e++) val[e] = 0.0;
+            }
+            const double cc1 = (NCOMB == 1) ? ccT[0] * su[9] : 1.0;
             static_for<N>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
                 const double *gx = s_q + (size_t)(3 * r) * GT + fx;
@@ -245,17 +250,19 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
                 double cx[NMAX + 1], cy[NMAX + 1], cz[NMAX + 1];
 #pragma unroll
                 for (int n = 0; n <= NMAX; n++) { cx[n] = gx[n * MS]; cy[n] = gy[n * MS]; cz[n] = gz[n * MS]; }
+                if constexpr (NCOMB == 1) {
+#pragma unroll
+                    for (int n = 0; n <= NMAX; n++) cz[n] *= cc1;
+                }
                 static_for<NE>([&](auto EE) {
                     constexpr int e = decltype(EE)::value;
                     constexpr int le = cx_range_l(LA, e), ie = cx_range_i(LA, e);
                     constexpr int ex = cx_lx(le, ie), ey = cx_ly(le, ie), ez = cx_lz(le, ie);
-                    val[e] = fma(cx[ex] * cy[ey], cz[ez], val[e]);
+                    if constexpr (NCOMB == 1) acc[e] = fma(cx[ex] * cy[ey], cz[ez], acc[e]);
+                    else val[e] = fma(cx[ex] * cy[ey], cz[ez], val[e]);
                 });
             });
             if constexpr (NCOMB == 1) {
-                const double cc = ccT[0] * su[9];
-#pragma unroll
-                for (int e = 0; e < NE; e++) acc[e] = fma(cc, val[e], acc[e]);
             } else {
                 static_for<NCL>([&](auto CL) {
                     static_for<NCR>([&](auto CR) {

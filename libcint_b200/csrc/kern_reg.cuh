@@ -175,19 +175,27 @@ __device__ __forceinline__ void hrr_step_reg(const double *in, double *out, cons
     });
 }
 
+// levels J..LB of the HRR, one temporary per intermediate level (any LB)
+template <int L0, int LB, int J, int PRE, int POST>
+__device__ __forceinline__ void hrr_chain_reg(const double *in, double *out, const double (&ab)[3])
+{
+    if constexpr (J == LB) {
+        hrr_step_reg<L0, LB, J, PRE, POST>(in, out, ab);
+    } else {
+        double tmp[PRE * cx_hrr_size(L0, LB, J) * POST];
+        hrr_step_reg<L0, LB, J, PRE, POST>(in, tmp, ab);
+        hrr_chain_reg<L0, LB, J + 1, PRE, POST>(tmp, out, ab);
+    }
+}
+
 // full HRR of one pair: in [PRE][range L0..L0+LB][POST] -> out [PRE][ncart(L0)][ncart(LB)][POST]
 template <int L0, int LB, int PRE, int POST>
 __device__ __forceinline__ void hrr_pair_reg(const double *in, double *out, const double (&ab)[3])
 {
     if constexpr (LB == 0) {
         static_for<PRE * cx_ncart(L0) * POST>([&](auto I) { out[decltype(I)::value] = in[decltype(I)::value]; });
-    } else if constexpr (LB == 1) {
-        hrr_step_reg<L0, LB, 1, PRE, POST>(in, out, ab);
     } else {
-        static_assert(LB == 2, "register HRR implemented up to LB = 2");
-        double tmp[PRE * cx_hrr_size(L0, LB, 1) * POST];
-        hrr_step_reg<L0, LB, 1, PRE, POST>(in, tmp, ab);
-        hrr_step_reg<L0, LB, 2, PRE, POST>(tmp, out, ab);
+        hrr_chain_reg<L0, LB, 1, PRE, POST>(in, out, ab);
     }
 }
 

@@ -190,3 +190,59 @@ def test_c60_full_size_bench_configuration():
             _, c2 = ctx.pair_offsets(i, j)
             tr = ctx.block(r2, c2, nk, nb)
             assert np.abs(tr - got.T).max() < 1e-13
+
+
+def check_df_job(max_atoms, nranks=1, force_generic=False, chunk_bytes=1 << 30, max_triples=None, aux_lmax=4):
+    """int3c2e whole-job driver (cintb200_int3c2e_sph_all) on the first atoms of the config-3 stand-in: every block of
+    the last tile against the oracle, triple and integral counts over all chunks and ranks."""
+    from libcint_b200.basis import c60_df_basis
+    which, _ = ou.best()
+    atm, bas, env, norb = c60_df_basis(max_atoms=max_atoms, aux_lmax=aux_lmax)
+    nbas = len(bas)
+    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    rng = np.random.default_rng(5)
+    tot_triples, tot_ints, worst, kinds = 0, 0, 0.0, set()
+    for rank in range(nranks):
+        ctx = cb.Context(atm, bas, env)
+        if force_generic:
+            ctx.force_generic(True)
+        st = ctx.int3c2e_all(norb, rank=rank, nranks=nranks, chunk_bytes=chunk_bytes)
+        tot_triples += st[0]
+        tot_ints += st[1]
+        kinds |= set(int(r[7]) for r in ctx.launch_rows())
+        nch = int(st[9])
+        tile, g = ctx.chunk(nch - 1)
+        todo = [(i, j, k) for i in range(g["i0"], g["i1"]) for j in range(i + 1) for k in range(norb, nbas)]
+        if max_triples and len(todo) > max_triples:
+            todo = [todo[s] for s in rng.choice(len(todo), max_triples, replace=False)]
+        for (i, j, k) in todo:
+            c = ctx.aux_offset(k)
+            if c < 0:
+                continue
+            r, _ = ctx.pair_offsets(i, j)
+            r -= g["row0"]
+            want, _ = ou.eval_tuple(which, "int3c2e_sph", (i, j, k), atm, bas, env)
+            nb = dims[i] * dims[j]
+            got = tile[r:r + nb, c:c + dims[k]]
+            err = np.abs(got - want.reshape((nb, dims[k]), order="F")).max()
+            scale = max(1.0, np.abs(want).max())
+            assert err <= 1e-12 * scale, (rank, (i, j, k), err, scale)
+            worst = max(worst, err / scale)
+        ctx.close()
+    assert tot_triples == norb * (norb + 1) // 2 * (nbas - norb)
+    nao, naux = sum(dims[:norb]), sum(dims[norb:])
+    npairs_ao = sum(dims[i] * dims[j] for i in range(norb) for j in range(i + 1))
+    assert tot_ints == npairs_ao * naux, (tot_ints, nao, naux)
+    return worst, kinds
+
+
+def test_df_tiles_specialised_kernels():
+    # s..f orbital shells x s..g auxiliary shells: register and cooperative kernels only (no generic launch)
+    worst, kinds = check_df_job(2)
+    assert kinds <= {1, 2}, kinds
+
+
+def test_df_tiles_generic_and_sharded():
+    check_df_job(2, force_generic=True, max_triples=1500)
+    check_df_job(2, nranks=2, max_triples=3000)
+    check_df_job(3, nranks=3, chunk_bytes=300_000, max_triples=2000)

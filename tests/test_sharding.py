@@ -83,3 +83,26 @@ def test_chunking_respects_budget():
     # a chunk never holds less than one bra shell x all kets, so a tiny budget is exceeded -- but the buffer
     # shrinks to that minimum
     assert small["tile_bytes"] < big["tile_bytes"] / 5
+
+
+def test_density_fitting_job_sharding():
+    # config 3 stand-in (C60, carbon cc-pVTZ + s..g auxiliary shells): the int3c2e whole job shards over the auxiliary
+    # columns; counts partition exactly, model FLOPs stay within 2% of the mean at 8 ranks, chunks stream the rows
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis()
+    one = cb.plan_summary(atm, bas, env, chunk_bytes=80 << 30, aux_shell0=norb)
+    nao, naux = 1800, 4800
+    assert one["quartets"] == norb * (norb + 1) // 2 * (len(bas) - norb)
+    assert one["columns"] == naux and one["chunks"] == 1
+    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas[:norb]]
+    rows = sum(dims[i] * dims[j] for i in range(norb) for j in range(i + 1))
+    assert one["rows"] == rows and one["integrals"] == rows * naux
+    assert rows >= nao * (nao + 1) // 2
+    for n in (2, 8):
+        parts = [cb.plan_summary(atm, bas, env, rank=r, nranks=n, chunk_bytes=80 << 30, aux_shell0=norb) for r in range(n)]
+        assert sum(p["quartets"] for p in parts) == one["quartets"]
+        assert sum(p["integrals"] for p in parts) == one["integrals"]
+        assert sum(p["columns"] for p in parts) == naux
+        assert max(p["model_flops"] for p in parts) * n / one["model_flops"] < 1.02
+    small = cb.plan_summary(atm, bas, env, chunk_bytes=8 << 30, aux_shell0=norb)
+    assert small["chunks"] >= 8 and small["integrals"] == one["integrals"] and small["tile_bytes"] <= (8 << 30) * 1.05

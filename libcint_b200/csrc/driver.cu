@@ -215,6 +215,19 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
         for (size_t k = 0; k < order.size(); k++) { ids[k] = pc.ids[order[k]]; I[k] = pc.I[order[k]]; npp[k] = pc.npp[order[k]]; }
         pc.ids.swap(ids); pc.I.swap(I); pc.npp.swap(npp);
     }
+    // 3b. row numbering: inside every chunk the row blocks follow the class lists (class by class, in list order), so the
+    //     quartets of one warp -- consecutive list entries -- own ADJACENT row blocks and the kernels' stores coalesce
+    //     (a chunk still holds exactly the pairs of its bra-shell range, so rows_before[] is unchanged)
+    for (size_t ch = 0; ch < plan->chunks.size(); ch++) {
+        long long r = plan->rows_before[plan->chunks[ch].first];
+        for (PairClass &pc : plan->classes)
+            for (int k = pc.chunk_lo[ch]; k < pc.chunk_lo[ch + 1]; k++) {
+                const int p = pc.ids[k], i = pc.I[k], j = p - i * (i + 1) / 2;
+                plan->rowoff[p] = r;
+                r += pair_dim(i, j);
+            }
+        if (r != plan->rows_before[plan->chunks[ch].second]) return b200_fail(CINTB200_EINVAL, "internal: row numbering of chunk %zu is inconsistent", ch);
+    }
     // 4. this rank's kets: index in the final class order modulo nranks; columns numbered chunk by chunk so that
     //    the kets with K < i1 always occupy the first cols_before[i1] columns
     std::vector<long long> &colof = plan->colof;

@@ -105,6 +105,9 @@ __host__ __device__ constexpr int cx_hrr_off(int l0, int le, int j)   // offset 
 #endif
 #define REG_MAXU 64            // most primitive pairs of a U pair (8 x 8)
 
+// doubles of shared memory per warp for the epilogue's output staging: [32][RB] values + [32][RB] int2 table + [32] int2
+__host__ __device__ constexpr int reg_stage_doubles(int rb) { return 32 * rb * 2 + 32; }
+
 // row stride (doubles) of the smem copy of the Rys table: odd, so rows fall on distinct 8-byte bank pairs
 __host__ __device__ constexpr int rys_smem_stride(int n) { return (RYS_DEG + 1) * 2 * n + 1; }
 
@@ -259,6 +262,12 @@ eri_reg_kernel(const TileParams P)
     constexpr int NWARP = REG_THREADS / 32;
     const int warp = tid >> 5, lane = tid & 31;
     double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;     // this WARP's ket primitives [nppu <= umax][USTR]
+    // per-warp output staging (epilogue): one column of the 32 quartets' blocks [32][RB] + gather table + per-thread row info
+    constexpr int RB = DA * DB;
+    double *s_st = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR
+                   + (reg_acc_in_smem(NCT, NCT * NCU * NEF) ? (size_t)NCT * NCU * NEF * REG_THREADS : 0) + (size_t)warp * reg_stage_doubles(RB);
+    int2 *s_tab = (int2 *)(s_st + 32 * RB);                     // [32*RB] {row offset in the tile or -1, index into s_st}
+    int2 *s_meta = s_tab + 32 * RB;                             // [32] {row base or -1, +di if a is the first index else -di}
     const long long total = (long long)P.gx * P.NU;
     int cur_by = -1;
     PairHdr hu;
@@ -453,16 +462,37 @@ eri_reg_kernel(const TileParams P)
                 }
         }
     }
-    if (!active) continue;
-
     // --- epilogue: HRR, c2s, store ---
+    // Stores go through a per-warp shared-memory transpose: a thread owns a whole (ab|cd) block, whose rows are
+    // contiguous in the tile only inside one column, so direct stores would touch 32 different sectors per instruction
+    // (measured: every single-primitive class saturated at ~900 GB/s of 8-byte sector writes).  Per column the 32 threads
+    // stage their RB row values, then the warp writes the 32*RB values in tile order (runs of >= DA or DB doubles,
+    // the whole RB when the pair is uncontracted; neighbouring quartets own neighbouring row blocks by construction).
     const int sa = P.tstride[tt], sb = P.tstride[NT + tt];
     const long long sc = (long long)P.ustride[u] * P.ld, sd = (long long)P.ustride[P.NU_all + u] * P.ld;
-    double *obase = P.out + (P.trow[tt] - P.row0) + P.ucol[u] * P.ld;
+    const int rowbase0 = (int)(P.trow[tt] - P.row0);
+    double *obase = P.out + P.ucol[u] * P.ld;
     const int nca_t = P.nca_t, nca_u = P.nca_u;
 #pragma unroll 1
     for (int comb = 0; comb < NCT * NCU; comb++) {
         const int ct = comb / NCU, cu = comb - ct * NCU;
+        if (cu == 0) {
+            // gather table of this T contraction block: element e = q * RB + r' of the warp's column slice, r' in tile order
+            const int ca = ct % nca_t, cb = ct / nca_t;
+            __syncwarp();
+            s_meta[lane] = make_int2(active ? rowbase0 + ca * DA * sa + cb * DB * sb : -1, sa == 1 ? sb : -sa);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < RB; k++) {
+                const int e = lane + 32 * k, q = e / RB, rp = e - q * RB;
+                const int2 m = s_meta[q];
+                int ma, mb, off;
+                if (m.y > 0) { mb = rp / DA; ma = rp - mb * DA; off = ma + mb * m.y; }      // a is the first (unit-stride) index
+                else { ma = rp / DB; mb = rp - ma * DB; off = mb - ma * m.y; }
+                s_tab[e] = make_int2(m.x < 0 ? -1 : m.x + off, q * RB + ma * DB + mb);
+            }
+            __syncwarp();
+        }
         // select the accumulator block of this combination (dynamic index -> predicated copies)
         double ef[NEF];
         if constexpr (ACC_SMEM) {
@@ -495,17 +525,25 @@ eri_reg_kernel(const TileParams P)
         if constexpr (LD >= 2) c2s_reg<LD, DA * DB * DC, 1>(p3, s4);
         double *p4 = (LD >= 2) ? s4 : p3;
 
-        const int ca = ct % nca_t, cb = ct / nca_t, cc = cu % nca_u, cd = cu / nca_u;
-        double *dst = obase + (long long)ca * DA * sa + (long long)cb * DB * sb + cc * DC * sc + cd * DD * sd;
+        const int cc = cu % nca_u, cd = cu / nca_u;
+        double *dst = obase + cc * DC * sc + cd * DD * sd;
         static_for<DD>([&](auto MD) {
             static_for<DC>([&](auto MC) {
-                static_for<DB>([&](auto MB) {
-                    static_for<DA>([&](auto MA) {
+                constexpr int mc = decltype(MC)::value, md = decltype(MD)::value;
+                static_for<DA>([&](auto MA) {
+                    static_for<DB>([&](auto MB) {
                         constexpr int ma = decltype(MA)::value, mb = decltype(MB)::value;
-                        constexpr int mc = decltype(MC)::value, md = decltype(MD)::value;
-                        dst[ma * sa + mb * sb + mc * sc + md * sd] = p4[((ma * DB + mb) * DC + mc) * DD + md];
+                        s_st[lane * RB + ma * DB + mb] = p4[((ma * DB + mb) * DC + mc) * DD + md];
                     });
                 });
+                __syncwarp();
+                double *cp = dst + mc * sc + md * sd;
+#pragma unroll
+                for (int k = 0; k < RB; k++) {
+                    const int2 t = s_tab[lane + 32 * k];
+                    if (t.x >= 0) cp[t.x] = s_st[t.y];
+                }
+                __syncwarp();
             });
         });
     }

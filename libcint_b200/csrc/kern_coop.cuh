@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
     double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
     const long long total = (long long)P.gx * P.NU;
-    int cur_by = -1;
+    int cur_by = -1, t_lo = P.t_begin;
     PairHdr hu;
     __syncthreads();                    // table staged; warps are independent from here on (see kern_reg.cuh)
     for (;;) {
@@ -99,13 +99,13 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
         }
         __syncwarp();
         cur_by = by;
-    }
-    int t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings
-    if (P.tri) {
-        const int K = P.uK[u];
-        int lo = P.t_begin, hi = P.t_end;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
-        t_lo = lo;
+        t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings; once per ket, not per work item
+        if (P.tri) {
+            const int K = P.uK[u];
+            int lo = P.t_begin, hi = P.t_end;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
+            t_lo = lo;
+        }
     }
     const int t0 = t_lo + bx * QPW;
     if (t0 >= P.t_end) continue;         // warp-uniform

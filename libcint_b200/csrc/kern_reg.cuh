@@ -269,7 +269,7 @@ eri_reg_kernel(const TileParams P)
     int2 *s_tab = (int2 *)(s_st + 32 * RB);                     // [32*RB] {row offset in the tile or -1, index into s_st}
     int2 *s_meta = s_tab + 32 * RB;                             // [32] {row base or -1, +di if a is the first index else -di}
     const long long total = (long long)P.gx * P.NU;
-    int cur_by = -1;
+    int cur_by = -1, t_lo = P.t_begin;
     PairHdr hu;
     __syncthreads();                    // table staged; from here on the warps run independently (no block barriers)
     // dynamic scheduling per WARP: a warp grabs batches of P.batch consecutive work items (item = one ket x 32 bras)
@@ -301,21 +301,20 @@ eri_reg_kernel(const TileParams P)
         }
         __syncwarp();
         cur_by = by;
-    }
-
-    // --- which T pairs does this item cover? ---
-    // reference loop bound k <= i (examples/time_c60.c:206).  tri = 0: this ket lies below the chunk's bra shells,
-    // every T pair is valid (list sorted by primitive count).  tri = 1: the list is sorted by the bra's larger
-    // shell index and the valid T pairs are the suffix starting at the first pair with I >= K.
-    int t_lo = P.t_begin;
-    if (P.tri) {
-        const int K = P.uK[u];
-        int lo = P.t_begin, hi = P.t_end;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+        // --- which T pairs do this ket's items cover? (once per ket) ---
+        // reference loop bound k <= i (examples/time_c60.c:206).  tri = 0: this ket lies below the chunk's bra shells,
+        // every T pair is valid (list sorted by primitive count).  tri = 1: the list is sorted by the bra's larger
+        // shell index and the valid T pairs are the suffix starting at the first pair with I >= K.
+        t_lo = P.t_begin;
+        if (P.tri) {
+            const int K = P.uK[u];
+            int lo = P.t_begin, hi = P.t_end;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+            }
+            t_lo = lo;
         }
-        t_lo = lo;
     }
     const int t0 = t_lo + bx * 32;
     if (t0 >= P.t_end) continue;        // warp-uniform
@@ -326,11 +325,11 @@ eri_reg_kernel(const TileParams P)
     // zero-weight primitives; neighbouring list entries have similar counts by construction)
     // Schwarz: if every quartet of this warp is bounded below the threshold, skip the primitive loops -- the
     // accumulators stay zero and the epilogue zero-fills the blocks (what the reference does for empty blocks)
+    const size_t NT = P.NT;
     const bool negligible = P.schwarz_thr > 0 && P.tq[tt] * P.uq[u] < P.schwarz_thr;
     const int Qb = __all_sync(0xffffffffu, negligible) ? 0 : __reduce_max_sync(0xffffffffu, P.tnpp[tt]);
 
     // --- per-thread (T pair) constants ---
-    const size_t NT = P.NT;
     double ra[3], abT[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) { ra[d] = P.tgeom[d * NT + tt]; abT[d] = P.tgeom[(3 + d) * NT + tt]; }

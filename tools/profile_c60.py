@@ -5,9 +5,10 @@ import numpy as np
 import libcint_b200 as cb
 name = sys.argv[1] if len(sys.argv) > 1 else "c60_ccpvdz"
 atm, bas, env = cb.load_fixture(name)
+CH = int(os.environ.get("CHUNK_GB", "16")) << 30
 ctx = cb.Context(atm, bas, env)
-ctx.all_unique(chunk_bytes=16 << 30)
-st, rows = ctx.profile(chunk_bytes=16 << 30)
+ctx.all_unique(chunk_bytes=CH)
+st, rows = ctx.profile(chunk_bytes=CH)
 tot = rows[:, 7].sum()
 print("total %.1f ms (events sum %.1f) model %.3e flop" % (st[7], tot, st[6]))
 print("class nct ncu kind      ms    %%   quartets   primq   GFLOP/s(model)  ns/primq  launches")

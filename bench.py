@@ -83,8 +83,9 @@ def dump_basis_bin(path, atm, bas, env):
         env.astype(np.float64).tofile(f)
 
 
-def run_reference_sample(atm, bas, env, stride, phase, threads=None):
-    """Time oracle/_ref (the unmodified reference) on a 1/stride sample of the benchmark loop."""
+def run_reference_sample(atm, bas, env, stride, phase, threads=None, aux0=None):
+    """Time oracle/_ref (the unmodified reference) on a 1/stride sample of the benchmark loop
+    (aux0 given: the density-fitting loop int3c2e_sph over orbital pairs x all auxiliary shells)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "time_ref")
     lib = os.path.join(ROOT, "oracle", "_ref", "libcint_ref.so")
     if not (os.path.exists(exe) and os.path.exists(lib)):
@@ -95,10 +96,22 @@ def run_reference_sample(atm, bas, env, stride, phase, threads=None):
         e = dict(os.environ)
         if threads:
             e["OMP_NUM_THREADS"] = str(threads)
-        out = subprocess.run([exe, lib, bb, str(stride), str(phase)], capture_output=True, text=True, env=e, timeout=1800)
+        cmd = [exe, lib, bb, str(stride), str(phase)] + ([str(aux0)] if aux0 else [])
+        out = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=1800)
         if out.returncode != 0:
             return None
         return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+DF_WORKLOAD = ("C60 int3c2e_sph, carbon cc-pVTZ orbital shells (1800 AOs) x even-tempered s..g auxiliary shells (4800 AOs; stand-in for "
+               "def2-universal-JKFIT, whose exponents are not available offline): all 175 284 000 shell triples i>=j, k per step")
+
+
+def df_count(bas, norb):
+    """Integrals of the density-fitting job counted like the reference drivers count: nao^2 naux / 2."""
+    nao = sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas[:norb])
+    naux = sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas[norb:])
+    return float(nao) ** 2 * naux / 2
 
 
 def host_cores():
@@ -131,6 +144,14 @@ def reference_arm(args):
     secs = sum(r["seconds"] for r in res)
     ints = sum(r["integrals"] for r in res) * (tot / produced)       # count like the reference driver does
     value = ints / secs
+    # secondary workload (BASELINE.json configs[2]): the density-fitting loop, 1/12 of the orbital pairs
+    from libcint_b200.basis import c60_df_basis
+    a3, b3, e3, norb = c60_df_basis()
+    r3 = run_reference_sample(np.asarray(a3), b3, e3, 12, 5, cores, aux0=norb)
+    extra = None
+    if r3 is not None:
+        extra = {"int3c2e_df": {"value": r3["integrals"] / r3["seconds"], "unit": "integrals/s", "workload": DF_WORKLOAD,
+                                "sample": "every 12-th orbital shell pair x all auxiliary shells, %.1f s, %d threads" % (r3["seconds"], r3["threads"])}}
     line = {
         "metric": METRIC, "value": value, "unit": "integrals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(res)), "higher_is_better": True, "scaling": "strong",
@@ -140,7 +161,7 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "integrals/s", "cores": cores, "kind": "reference",
                          "sample": "1/%d of the ij pairs per step, %d steps, OpenMP schedule(dynamic,2)" % (stride, len(res))},
         "e2e": {"value": value, "unit": "integrals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "extra": extra,
     }
     print(json.dumps(line))
     return 0
@@ -155,6 +176,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each moves ~505/N GB to the host)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-df", action="store_true", help="skip the secondary density-fitting workload (int3c2e)")
     ap.add_argument("--chunk-gb", type=float, default=80.0, help="device-resident tile buffer (one buffer)")
     ap.add_argument("--e2e-chunk-gb", type=float, default=16.0, help="tile / pinned sink size of the end-to-end mode (two device buffers)")
     args = ap.parse_args()
@@ -293,6 +315,34 @@ def main():
         else:
             cpu = {"value": None, "unit": "integrals/s", "cores": cores, "kind": "reference", "sample": "oracle/_ref missing"}
 
+    # ---------------- secondary workload (BASELINE.json configs[2]): the whole density-fitting job ----------------
+    extra = None
+    if not args.no_df:
+        from libcint_b200.basis import c60_df_basis
+        ctx.close()
+        a3, b3, e3, norb = c60_df_basis()
+        c3 = cb.Context(a3, b3, e3, device=local)
+        for _ in range(3):
+            s3 = c3.int3c2e_all(norb, rank=rank, nranks=world, chunk_bytes=chunk)
+        barrier()
+        ms3 = 0.0
+        for _ in range(args.steps):
+            s3 = c3.int3c2e_all(norb, rank=rank, nranks=world, chunk_bytes=chunk)
+            ms3 += s3[7]
+        barrier()
+        ms3 = max_over_ranks(ms3 / args.steps)
+        fl3, wr3 = sum_over_ranks(s3[6]), sum_over_ranks(s3[1])
+        c3.close()
+        extra = {"int3c2e_df": {"value": df_count(b3, norb) / (ms3 * 1e-3), "unit": "integrals/s", "ms_per_step": ms3,
+                                "workload": DF_WORKLOAD, "integrals_written": wr3,
+                                "model_tflops": fl3 / (ms3 * 1e-3) / 1e12, "store_gbs_per_gpu": 8 * wr3 / (ms3 * 1e-3) / 1e9 / world,
+                                "parallelism": "auxiliary shells dealt round-robin per (l, nctr) class over %d GPU(s), no collective" % world}}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            r3 = run_reference_sample(np.asarray(a3), b3, e3, 12, 5, host_cores(), aux0=norb)
+            if r3 is not None:
+                extra["int3c2e_df"]["cpu_baseline"] = {"value": r3["integrals"] / r3["seconds"], "unit": "integrals/s", "cores": r3["threads"],
+                                                       "kind": "reference", "sample": "every 12-th orbital shell pair x all auxiliary shells, %.1f s" % r3["seconds"]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "integrals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -303,7 +353,7 @@ def main():
                        "l2": "each step streams %.0f GB of output through L2 (>> 126 MB); pair tables (~20 MB) stay L2-resident by design" % (8 * produced / 1e9),
                        "chunk_gb": args.chunk_gb, "wall_ms_per_step": wall_ms},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": sampler.summary(),
+            "clocks": sampler.summary(), "extra": extra,
         }
         print(json.dumps(line))
     if dist is not None:

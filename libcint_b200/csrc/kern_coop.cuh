@@ -23,7 +23,13 @@
 #ifndef COOP_THREADS
 #define COOP_THREADS 128
 #endif
-__host__ __device__ constexpr int coop_min_blocks(int nacc) { return (nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2) * 128 / COOP_THREADS > 0 ? (nacc <= 16 ? 4 : nacc <= 32 ? 3 : 2) * 128 / COOP_THREADS : 1; }
+#ifndef COOP_MB16
+#define COOP_MB16 4
+#endif
+#ifndef COOP_MB32
+#define COOP_MB32 3
+#endif
+__host__ __device__ constexpr int coop_min_blocks(int nacc) { return (nacc <= 16 ? COOP_MB16 : nacc <= 32 ? COOP_MB32 : 2) * 128 / COOP_THREADS > 0 ? (nacc <= 16 ? COOP_MB16 : nacc <= 32 ? COOP_MB32 : 2) * 128 / COOP_THREADS : 1; }
 
 __host__ __device__ constexpr int coop_g_task(int nmax, int mmax) { return ((nmax + 1) * (mmax + 1)) | 1; }
 __host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * coop_g_task(nmax, mmax); }

@@ -6,7 +6,9 @@
  *   - the basis comes from a binary dump (natm, nbas, nenv, atm, bas, env) instead of inline C;
  *   - only every `stride`-th ij pair (offset `phase`) is evaluated so the run is a bounded sample;
  *   - one buffer per thread instead of malloc/free per quartet (the library call is what is timed).
- * usage: time_ref <lib.so> <basis.bin> <stride> <phase> [repeat]
+ * usage: time_ref <lib.so> <basis.bin> <stride> <phase> [aux_shell0]
+ * With aux_shell0 > 0 the density-fitting loop is timed instead: int3c2e_sph for every `stride`-th orbital shell pair
+ * i >= j < aux_shell0 and ALL auxiliary shells k >= aux_shell0 (the loop shape of cintb200_int3c2e_sph_all).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -37,6 +39,45 @@ int main(int argc, char **argv)
         if (fread(env, sizeof(double), nenv, f) != (size_t)nenv) return 1;
         fclose(f);
         long stride = atol(argv[3]), phase = atol(argv[4]);
+        int aux0 = (argc > 5) ? atoi(argv[5]) : 0;
+        if (aux0 > 0) {
+                intor_t intor3 = (intor_t)dlsym(h, "int3c2e_sph");
+                optim_t optim3 = (optim_t)dlsym(h, "int3c2e_optimizer");
+                if (!intor3 || !optim3 || aux0 >= nbas) { fprintf(stderr, "bad 3-centre input\n"); return 1; }
+                long np3 = (long)aux0 * (aux0 + 1) / 2;
+                int *is3 = malloc(sizeof(int) * np3), *js3 = malloc(sizeof(int) * np3);
+                long q = 0;
+                int md = 0;
+                for (int i = 0; i < nbas; i++) { int d = (2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3]; if (d > md) md = d; }
+                for (int i = 0; i < aux0; i++) for (int j = 0; j <= i; j++, q++) { is3[q] = i; js3[q] = j; }
+                void *opt3 = NULL;
+                optim3(&opt3, atm, natm, bas, nbas, env);
+                double nints3 = 0, chk3 = 0;
+                long ntrip = 0;
+                double t0 = omp_get_wtime();
+#pragma omp parallel reduction(+ : nints3, chk3, ntrip)
+                {
+                        double *buf = malloc(sizeof(double) * md * md * md);
+#pragma omp for schedule(dynamic, 2)
+                        for (long p = phase; p < np3; p += stride) {
+                                int i = is3[p], j = js3[p];
+                                long dij = (long)(2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3] * (2 * bas[j * 8 + 1] + 1) * bas[j * 8 + 3];
+                                for (int k = aux0; k < nbas; k++) {
+                                        int shls[3] = {i, j, k};
+                                        intor3(buf, NULL, shls, atm, natm, bas, nbas, env, opt3, NULL);
+                                        long n = dij * (2 * bas[k * 8 + 1] + 1) * bas[k * 8 + 3];
+                                        nints3 += n;
+                                        chk3 += buf[0] + buf[n - 1];
+                                }
+                                ntrip += nbas - aux0;
+                        }
+                        free(buf);
+                }
+                double t1 = omp_get_wtime();
+                printf("{\"seconds\": %.6f, \"integrals\": %.0f, \"quartets\": %ld, \"threads\": %d, \"stride\": %ld, \"phase\": %ld, \"checksum\": %.15e}\n",
+                       t1 - t0, nints3, ntrip, omp_get_max_threads(), stride, phase, chk3);
+                return 0;
+        }
         long npair = (long)nbas * (nbas + 1) / 2;
         int *ish = malloc(sizeof(int) * npair), *jsh = malloc(sizeof(int) * npair);
         int *dim = malloc(sizeof(int) * nbas);

@@ -260,8 +260,17 @@ def main():
         except Exception:
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
+        traffic, traffic_note = None, None
+        try:        # DRAM bytes of one captured launch of the dominant kernel (tools/ncu_summarize.py -> profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tj["kernel"].replace(" ", "") == "eri_reg_kernel<%d,%d,%d,%d,%d,%d>" % tuple(int(v) for v in top[:6]) and int(top[6]) == 1:
+                traffic = tj["traffic_bytes"]
+                traffic_note = {k: tj.get(k) for k in ("capture", "dram_read_bytes", "dram_write_bytes", "algorithmic_store_bytes", "duration_us")}
+        except Exception:
+            pass
         roofline = {
-            "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+            "traffic_note": traffic_note,
             "peak_source": "in-bench DFMA-chain microbenchmark on this GPU (MEASURED_PEAKS.json has no FP64 entry; B200 datasheet ~37-40)",
             "kernel": "eri %s kernel, class (%d%d|%d%d) nct=%d ncu=%d" % (kinds[int(top[6])], top[0], top[1], top[2], top[3], top[4], top[5]),
             "kernel_share_of_step": top[7] / tot_ms,

@@ -22,6 +22,7 @@
 #include "types.h"
 #include "kernels.h"
 #include "engine.h"
+#include "rys.cuh"
 
 int rys_tab_off(int nroots);
 extern const int *engine_c2s_off();
@@ -466,6 +467,8 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci);
                     L.coop = L.fn != nullptr;
                 }
+                if (L.fn && !L.coop && REG_FAST_RYS && L.nroots <= RYS_FNMAX)
+                    P.rys = c->d_rys_fast + rys_fast_off(L.nroots);   // register kernels of low order read the degree-6 tables
                 if (L.fn) {
                     const int qpb = L.coop ? 32 / L.ci.fs : 32;       // bras per work item (one warp)
                     L.gx = (t_end - t_begin + qpb - 1) / qpb;

@@ -21,11 +21,13 @@
 #include "kernels.h"
 #include "rys.cuh"
 #include "rys_tables.inc"
+#include "rys_tables_fast.inc"
 #include "c2s_tables.inc"
 #include "engine.h"
 
 static_assert(RYS_TAB_DEG == RYS_DEG && RYS_TAB_M == RYS_M && RYS_TAB_NMAX == RYS_NMAX, "rys.cuh out of sync with rys_tables.inc");
 static_assert(C2S_LMAX >= B200_LMAX, "c2s table too small");
+static_assert(RYS_FAST_DEG == RYS_FDEG && RYS_FAST_M == RYS_FM && RYS_FAST_NMAX == RYS_FNMAX && RYS_FAST_C0 == 8, "rys.cuh out of sync with rys_tables_fast.inc");
 
 __constant__ RysMeta c_rys_meta;
 __constant__ double c_rys_lx_r[RYS_NMAX * (RYS_NMAX + 1) / 2];
@@ -131,6 +133,7 @@ static int setup_device_constants(int dev)
     RysMeta meta;
     memset(&meta, 0, sizeof meta);
     for (int n = 1; n <= RYS_NMAX; n++) { meta.off[n] = RYS_TAB_OFF[n]; meta.nint[n] = RYS_TAB_NINT[n]; }
+    for (int n = 1; n <= RYS_FNMAX; n++) meta.fast_nint[n] = RYS_FAST_NINT[n];
     CUDA_OK(cudaMemcpyToSymbol(c_rys_meta, &meta, sizeof meta));
     CUDA_OK(cudaMemcpyToSymbol(c_rys_lx_r, RYS_LX_R, sizeof(double) * RYS_NMAX * (RYS_NMAX + 1) / 2));
     CUDA_OK(cudaMemcpyToSymbol(c_rys_lx_v, RYS_LX_V, sizeof(double) * RYS_NMAX * (RYS_NMAX + 1) / 2));
@@ -251,6 +254,8 @@ static int ctx_upload(CINTOpt *c)
     CUDA_OK(cudaMalloc(&c->d_prims, sizeof(PrimPair) * std::max<size_t>(1, c->prims.size())));
     CUDA_OK(cudaMalloc(&c->d_pcoef, sizeof(double) * std::max<size_t>(1, c->pcoef.size())));
     CUDA_OK(cudaMalloc(&c->d_rys, sizeof(RYS_TAB_COEF)));
+    CUDA_OK(cudaMalloc(&c->d_rys_fast, sizeof(RYS_FAST_COEF)));
+    CUDA_OK(cudaMemcpy(c->d_rys_fast, RYS_FAST_COEF, sizeof(RYS_FAST_COEF), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&c->d_c2s, sizeof(C2S_COEF)));
     CUDA_OK(cudaMemcpy(c->d_pairs, c->pairs.data(), sizeof(PairHdr) * c->pairs.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->d_prims, c->prims.data(), sizeof(PrimPair) * c->prims.size(), cudaMemcpyHostToDevice));
@@ -325,7 +330,7 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
     }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_c2s);
+    cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_rys_fast); cudaFree(c->d_c2s);
     cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_nonzero); cudaFree(c->d_scratch); cudaFree(c->d_counters);
     if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -693,6 +698,8 @@ extern "C" void cintb200_debug_force_generic(cintb200_ctx *c, int on) { if (c &&
 
 int rys_tab_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_NINT[nroots] : 0; }
 int rys_tab_off(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_OFF[nroots] : 0; }
+int rys_fast_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_NINT[nroots] : 0; }
+int rys_fast_off(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_OFF[nroots] : 0; }
 
 // ------------------------------------------------------------------ FP64 roofline denominator
 // MEASURED_PEAKS.json carries no FP64 entry, so the bench measures the DFMA peak itself: 8 independent

@@ -32,7 +32,7 @@ struct CINTOpt {
     // device tables
     PairHdr *d_pairs = nullptr;
     PrimPair *d_prims = nullptr;
-    double *d_pcoef = nullptr, *d_rys = nullptr, *d_c2s = nullptr;
+    double *d_pcoef = nullptr, *d_rys = nullptr, *d_rys_fast = nullptr, *d_c2s = nullptr;
     // reusable work buffers
     Task *d_tasks = nullptr;        size_t cap_tasks = 0;
     double *d_out = nullptr;        size_t cap_out = 0;

@@ -110,6 +110,35 @@ __host__ __device__ constexpr int reg_stage_doubles(int rb) { return 32 * rb * 2
 
 // row stride (doubles) of the smem copy of the Rys table: odd, so rows fall on distinct 8-byte bank pairs
 __host__ __device__ constexpr int rys_smem_stride(int n) { return (RYS_DEG + 1) * 2 * n + 1; }
+// the register kernels of order <= RYS_FNMAX use the degree-6 table set (rys.cuh)
+__host__ __device__ constexpr bool reg_fast_rys(int n) { return REG_FAST_RYS && n <= RYS_FNMAX; }
+__host__ __device__ constexpr int reg_rys_stride(int n) { return reg_fast_rys(n) ? (RYS_FDEG + 1) * 2 * n + 1 : rys_smem_stride(n); }
+__host__ __device__ constexpr int reg_rys_row(int n) { return (reg_fast_rys(n) ? RYS_FDEG + 1 : RYS_DEG + 1) * 2 * n; }
+
+template <int N>
+__device__ __forceinline__ void rys_roots_smem_fast(const double *tab, double x, double (&t2)[N], double (&w)[N])
+{
+    // same branch-free structure as rys_roots_smem below, degree 6 on the 64-intervals-per-octave grid
+    const bool large = x >= 35.0 + 5.0 * N;
+    const double isx = fast_rsqrt(large ? x : 1.0);
+    const double ix = isx * isx;
+    int idx;
+    double y;
+    rys_locate_m<RYS_FM>(large ? 0.0 : x, idx, y);
+    const double *c = tab + idx * reg_rys_stride(N);
+    static_assert(RYS_FDEG == 6, "Estrin scheme below is written for degree 6");
+    const double y2 = y * y, y4 = y2 * y2;
+#pragma unroll
+    for (int p = 0; p < 2 * N; p++) {
+        const double p01 = fma(c[1 * 2 * N + p], y, c[0 * 2 * N + p]);
+        const double p23 = fma(c[3 * 2 * N + p], y, c[2 * 2 * N + p]);
+        const double p45 = fma(c[5 * 2 * N + p], y, c[4 * 2 * N + p]);
+        const double q0 = fma(p23, y2, p01), q1 = fma(c[6 * 2 * N + p], y2, p45);
+        const double v = fma(q1, y4, q0);
+        if (p & 1) w[p >> 1] = large ? c_rys_lx_v[N * (N - 1) / 2 + (p >> 1)] * isx : v;
+        else t2[p >> 1] = large ? c_rys_lx_r[N * (N - 1) / 2 + (p >> 1)] * ix : v;
+    }
+}
 
 template <int N>
 __device__ __forceinline__ void rys_roots_smem(const double *tab, int nint, double x, double (&t2)[N], double (&w)[N])
@@ -251,20 +280,22 @@ eri_reg_kernel(const TileParams P)
 
     // --- stage the Rys table of N roots ONCE per block; the block then walks a contiguous range of work items
     //     (item = one ket x 32 bras, one WARP each), so the table and the ket's primitives are reused ---
-    const int nint = c_rys_meta.nint[N];
+    constexpr bool FASTRYS = reg_fast_rys(N);
+    constexpr int RSTR = reg_rys_stride(N);
+    const int nint = FASTRYS ? c_rys_meta.fast_nint[N] : c_rys_meta.nint[N];
     {
-        constexpr int ROW = (RYS_DEG + 1) * 2 * N;
+        constexpr int ROW = reg_rys_row(N);
         for (int i = tid; i < nint * ROW; i += REG_THREADS) {
             int r = i / ROW, c = i - r * ROW;
-            s_rys[r * rys_smem_stride(N) + c] = __ldg(P.rys + i);
+            s_rys[r * RSTR + c] = __ldg(P.rys + i);
         }
     }
     constexpr int NWARP = REG_THREADS / 32;
     const int warp = tid >> 5, lane = tid & 31;
-    double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;     // this WARP's ket primitives [nppu <= umax][USTR]
+    double *s_u = s_rys + nint * RSTR + (size_t)warp * P.umax * USTR;     // this WARP's ket primitives [nppu <= umax][USTR]
     // per-warp output staging (epilogue): one column of the 32 quartets' blocks [32][RB] + gather table + per-thread row info
     constexpr int RB = DA * DB;
-    double *s_st = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR
+    double *s_st = s_rys + nint * RSTR + (size_t)NWARP * P.umax * USTR
                    + (reg_acc_in_smem(NCT, NCT * NCU * NEF) ? (size_t)NCT * NCU * NEF * REG_THREADS : 0) + (size_t)warp * reg_stage_doubles(RB);
     int2 *s_tab = (int2 *)(s_st + 32 * RB);                     // [32*RB] {row offset in the tile or -1, index into s_st}
     int2 *s_meta = s_tab + 32 * RB;                             // [32] {row base or -1, +di if a is the first index else -di}
@@ -342,7 +373,7 @@ eri_reg_kernel(const TileParams P)
     constexpr int NACC = NCT * NCU * NEF;
     constexpr bool ACC_SMEM = reg_acc_in_smem(NCT, NACC);
     double acc[ACC_SMEM ? 1 : NACC];
-    double *s_acc = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + tid;         // [NACC][REG_THREADS]
+    double *s_acc = s_rys + nint * RSTR + (size_t)NWARP * P.umax * USTR + tid;         // [NACC][REG_THREADS]
     if constexpr (ACC_SMEM) {
 #pragma unroll
         for (int i = 0; i < NACC; i++) s_acc[i * REG_THREADS] = 0.0;
@@ -385,7 +416,8 @@ eri_reg_kernel(const TileParams P)
             const double x = a0 * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
             const double fac = common * kT * su[8] * iaT * iaU * rs;
             double t2[N], w[N];
-            rys_roots_smem<N>(s_rys, nint, x, t2, w);
+            if constexpr (FASTRYS) rys_roots_smem_fast<N>(s_rys, x, t2, w);
+            else rys_roots_smem<N>(s_rys, nint, x, t2, w);
             const double rho_u = aU * inv, rho_t = aT * inv;
             double val[(NCU == 1) ? 1 : NEF];
             if constexpr (NCU > 1) {

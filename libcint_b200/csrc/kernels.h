@@ -32,6 +32,8 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
 typedef void (*RegKernelFn)(const TileParams);
 RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu);
 int rys_tab_nint(int nroots);
+int rys_fast_nint(int nroots);
+int rys_fast_off(int nroots);
 int reg_kernel_launch(RegKernelFn fn, int nroots, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);
 
 // cooperative kernels (kern_coop_inst*.cu): FS lanes per quartet

@@ -54,5 +54,30 @@ for f in sorted(os.listdir(G)):
             out.append("  %-82s %16s %s\n" % (k, d[k][0], d[k][1]))
     import shutil
     shutil.copy(os.path.join(G, "prof_%s_%s_details.txt" % (m.group(1), rnd)), os.path.join(P, "%s_ncu_%s_details.txt" % (rnd, m.group(1))))
+# DRAM traffic of the dominant kernel's captured launch (bench.py's roofline.traffic): ncu capture `reg_psps` = the
+# (skip+1)-th launch of eri_reg_kernel<1,0,1,0,2,2> in one pass; its algorithmic bytes come from the launch list
+try:
+    import json
+    import numpy as np
+    f = os.path.join(G, "prof_reg_psps_%s_raw.csv" % rnd)
+    rows = list(csv.reader(open(f, errors="ignore")))
+    d = dict(zip(rows[0], zip(rows[-1], rows[1])))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd = float(d["dram__bytes_read.sum"][0].replace(",", "")) * scale[d["dram__bytes_read.sum"][1]]
+    wr = float(d["dram__bytes_write.sum"][0].replace(",", "")) * scale[d["dram__bytes_write.sum"][1]]
+    tr = {"kernel": "eri_reg_kernel<1,0,1,0,2,2>", "capture": "ncu --set full --clock-control none, 9th launch of this kernel in one C60 pass (-s 8 -c 1)",
+          "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
+          "duration_us": float(d["gpu__time_duration.sum"][0].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(d["gpu__time_duration.sum"][1], 1.0)}
+    lr = os.path.join(G, "launch_rows.npy")
+    if os.path.exists(lr):
+        L = np.load(lr)
+        mine = [r for r in L if tuple(int(v) for v in r[1:7]) == (1, 0, 1, 0, 2, 2)]
+        if len(mine) > 8:
+            tr["algorithmic_store_bytes"] = float(mine[8][10]) * 8
+            tr["model_flops"] = float(mine[8][11])
+    json.dump(tr, open(os.path.join(P, "%s_traffic.json" % rnd), "w"), indent=1)
+    out.append("\n# roofline.traffic source: %s\n" % json.dumps(tr))
+except Exception as e:
+    out.append("\n# no traffic figure: %r\n" % (e,))
 open(os.path.join(P, "%s_ncu_summary.txt" % rnd), "w").write("".join(out))
 print("".join(out))

@@ -83,7 +83,7 @@ def dump_basis_bin(path, atm, bas, env):
         env.astype(np.float64).tofile(f)
 
 
-def run_reference_sample(atm, bas, env, stride, phase, threads=None, aux0=None):
+def run_reference_sample(atm, bas, env, stride, phase, threads=None, aux0=None, affinity=None):
     """Time oracle/_ref (the unmodified reference) on a 1/stride sample of the benchmark loop
     (aux0 given: the density-fitting loop int3c2e_sph over orbital pairs x all auxiliary shells)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "time_ref")
@@ -97,7 +97,8 @@ def run_reference_sample(atm, bas, env, stride, phase, threads=None, aux0=None):
         if threads:
             e["OMP_NUM_THREADS"] = str(threads)
         cmd = [exe, lib, bb, str(stride), str(phase)] + ([str(aux0)] if aux0 else [])
-        out = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=1800)
+        out = subprocess.run(cmd, capture_output=True, text=True, env=e, timeout=1800,
+                             preexec_fn=(lambda: os.sched_setaffinity(0, affinity)) if affinity else None)
         if out.returncode != 0:
             return None
         return json.loads(out.stdout.strip().splitlines()[-1])
@@ -112,6 +113,29 @@ def df_count(bas, norb):
     nao = sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas[:norb])
     naux = sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas[norb:])
     return float(nao) ** 2 * naux / 2
+
+
+def bind_to_gpu_numa(torch, local):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that the pinned host buffers of the end-to-end
+    mode are first-touched on the NUMA node behind the GPU's PCIe root (D2H at link speed instead of crossing sockets).
+    Returns (cpus bound to or None, the original affinity) -- CPU baselines run with the original affinity."""
+    orig = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        target = cpus & orig
+        if target and target != orig:
+            os.sched_setaffinity(0, target)
+            return sorted(target), orig
+    except Exception:
+        pass
+    return None, orig
 
 
 def host_cores():
@@ -147,11 +171,11 @@ def reference_arm(args):
     # secondary workload (BASELINE.json configs[2]): the density-fitting loop, 1/12 of the orbital pairs
     from libcint_b200.basis import c60_df_basis
     a3, b3, e3, norb = c60_df_basis()
-    r3 = run_reference_sample(np.asarray(a3), b3, e3, 12, 5, cores, aux0=norb)
+    r3 = run_reference_sample(np.asarray(a3), b3, e3, 2, 1, cores, aux0=norb)
     extra = None
     if r3 is not None:
         extra = {"int3c2e_df": {"value": r3["integrals"] / r3["seconds"], "unit": "integrals/s", "workload": DF_WORKLOAD,
-                                "sample": "every 12-th orbital shell pair x all auxiliary shells, %.1f s, %d threads" % (r3["seconds"], r3["threads"])}}
+                                "sample": "every 2nd orbital shell pair x all auxiliary shells, %.1f s, %d threads" % (r3["seconds"], r3["threads"])}}
     line = {
         "metric": METRIC, "value": value, "unit": "integrals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(res)), "higher_is_better": True, "scaling": "strong",
@@ -191,6 +215,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcint_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa_cpus, orig_affinity = bind_to_gpu_numa(torch, local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -307,16 +332,18 @@ def main():
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
         d2h_tot = sum_over_ranks(d2h / args.e2e_steps)
         e2e = {"value": tot / e2e_s, "unit": "integrals/s", "h2d_bytes_per_step": int(h2d * world),
-               "d2h_bytes_per_step": int(d2h_tot), "s_per_step": e2e_s,
+               "d2h_bytes_per_step": int(d2h_tot), "s_per_step": e2e_s, "d2h_gbs_per_gpu": d2h_tot / world / e2e_s / 1e9,
+               "host_numa_cpus": ("%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus)) if numa_cpus else "unchanged",
+
                "includes": "context build from host atm/bas/env + pair tables upload, all kernels, D2H of every tile into pinned host memory"}
         del sink
 
     # ---------------- CPU baseline: the compiled reference on this box's cores (rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = host_cores()
+        cores = len(orig_affinity)
         stride = max(8, int(round(600.0 * 8 / cores / 15.0)))
-        r = run_reference_sample(atm, bas, env, stride, 1, cores)
+        r = run_reference_sample(atm, bas, env, stride, 1, cores, affinity=orig_affinity)
         if r is not None:
             cpu = {"value": r["integrals"] * (tot / 6.3086e10) / r["seconds"], "unit": "integrals/s", "cores": cores,
                    "kind": "reference", "sample": "every %d-th ij shell pair (all kl), %.1f s, OpenMP schedule(dynamic,2), optimizer on"
@@ -347,10 +374,10 @@ def main():
                                 "model_tflops": fl3 / (ms3 * 1e-3) / 1e12, "store_gbs_per_gpu": 8 * wr3 / (ms3 * 1e-3) / 1e9 / world,
                                 "parallelism": "auxiliary shells dealt round-robin per (l, nctr) class over %d GPU(s), no collective" % world}}
         if rank == 0 and world == 1 and not args.no_cpu:
-            r3 = run_reference_sample(np.asarray(a3), b3, e3, 12, 5, host_cores(), aux0=norb)
+            r3 = run_reference_sample(np.asarray(a3), b3, e3, 2, 1, len(orig_affinity), aux0=norb, affinity=orig_affinity)
             if r3 is not None:
                 extra["int3c2e_df"]["cpu_baseline"] = {"value": r3["integrals"] / r3["seconds"], "unit": "integrals/s", "cores": r3["threads"],
-                                                       "kind": "reference", "sample": "every 12-th orbital shell pair x all auxiliary shells, %.1f s" % r3["seconds"]}
+                                                       "kind": "reference", "sample": "every 2nd orbital shell pair x all auxiliary shells, %.1f s" % r3["seconds"]}
 
     if rank == 0:
         line = {

@@ -193,9 +193,13 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
                     double y;
                     rys_locate(x, idx, y);
                     const double *cf = s_rys + idx * rys_smem_stride(N) + p;
-                    v = cf[RYS_DEG * 2 * N];
-#pragma unroll
-                    for (int j = RYS_DEG - 1; j >= 0; j--) v = fma(v, y, cf[j * 2 * N]);
+                    // Estrin (depth 4) instead of Horner (depth 9): this phase is a dependent chain on a few busy lanes
+                    static_assert(RYS_DEG == 9, "Estrin scheme written for degree 9");
+                    const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
+                    const double p01 = fma(cf[1 * 2 * N], y, cf[0]), p23 = fma(cf[3 * 2 * N], y, cf[2 * 2 * N]);
+                    const double p45 = fma(cf[5 * 2 * N], y, cf[4 * 2 * N]), p67 = fma(cf[7 * 2 * N], y, cf[6 * 2 * N]);
+                    const double p89 = fma(cf[9 * 2 * N], y, cf[8 * 2 * N]);
+                    v = fma(p89, y8, fma(fma(p67, y2, p45), y4, fma(p23, y2, p01)));
                 }
                 s_rw[p] = v;
             }

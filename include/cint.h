@@ -81,6 +81,14 @@ CINTIntegralFunction  int2c2e_sph;          /* src/cint2c2e.c:351 */
 CINTIntegralFunction  int2c2e_cart;         /* src/cint2c2e.c:368 */
 CINTOptimizerFunction int2c2e_optimizer;    /* src/cint2c2e.c:360 */
 
+/* ---- first derivatives ( nabla i j | k l ), 3 components, out[comp][l][k][j][i] ---- */
+CINTIntegralFunction  int2e_ip1_sph;        /* src/autocode/grad2.c:51 */
+CINTIntegralFunction  int2e_ip1_cart;       /* src/autocode/grad2.c:42 */
+CINTOptimizerFunction int2e_ip1_optimizer;  /* src/autocode/grad2.c:35 */
+CINTIntegralFunction  int3c2e_ip1_sph;      /* src/autocode/int3c2e.c (int3c2e_ip1_sph) */
+CINTIntegralFunction  int3c2e_ip1_cart;
+CINTOptimizerFunction int3c2e_ip1_optimizer;
+
 /* ---- v2-style wrappers (src/misc.h:35-61 ALL_CINT, include/cint.h.in:264-278) ---- */
 FINT cint2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 FINT cint2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
@@ -90,6 +98,10 @@ FINT cint3c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT
 FINT cint3c2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 void cint3c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 void cint3c2e_cart_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
+FINT cint2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+FINT cint3c2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+void cint2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
+void cint3c2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 FINT cint2c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 FINT cint2c2e_cart(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 void cint2c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);

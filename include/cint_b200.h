@@ -62,6 +62,15 @@ long cintb200_int3c2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t
 long cintb200_int2c2e_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
                             const size_t *out_off, double *out, int on_device, int *nonzero);
 
+/* First derivatives ( nabla i j | k l ) and ( nabla i j | k ): int2e_ip1_sph/_cart (src/autocode/grad2.c:19-68) and
+ * int3c2e_ip1_sph/_cart.  Every block holds 3 components, out[comp][l][k][j][i] -- 3x the size of the plain block, the
+ * reference's layout for dims == NULL.  Evaluated as a combination of the blocks of a raised and a lowered shell i
+ * (the shell-level form of CINTnabla1i_2e, src/g2e.c:4550) through the generic kernel + one assembly kernel. */
+long cintb200_int2e_ip1_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                              const size_t *out_off, double *out, int on_device, int *nonzero);
+long cintb200_int3c2e_ip1_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                                const size_t *out_off, double *out, int on_device, int *nonzero);
+
 /* Size in doubles of one block / of a packed batch (host-side helper). */
 size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, int ncenter);
 

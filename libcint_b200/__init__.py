@@ -37,7 +37,8 @@ def load_library():
     lib.cintb200_create.restype = ci
     lib.cintb200_destroy.argtypes = [vp]
     lib.cintb200_destroy.restype = None
-    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch"):
+    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch", "cintb200_int2e_ip1_batch",
+                 "cintb200_int3c2e_ip1_batch"):
         f = getattr(lib, name)
         f.argtypes = [vp, ci, vp, sz, vp, vp, ci, vp]
         f.restype = ctypes.c_long
@@ -60,7 +61,8 @@ def load_library():
         lib.cintb200_debug_profile.restype = None
         lib.cintb200_debug_profile_rows.argtypes = [vp, vp, ci]
         lib.cintb200_debug_profile_rows.restype = ci
-    for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart", "int2c2e_sph", "int2c2e_cart"):
+    for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart", "int2c2e_sph", "int2c2e_cart",
+                 "int2e_ip1_sph", "int2e_ip1_cart", "int3c2e_ip1_sph", "int3c2e_ip1_cart"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
         f.restype = ci
@@ -114,11 +116,11 @@ class Context:
 
     __del__ = close
 
-    def _batch(self, fn, ncenter, shls, kind, out=None, out_off=None, device_ptr=None):
+    def _batch(self, fn, ncenter, shls, kind, out=None, out_off=None, device_ptr=None, ncomp=1):
         shls = np.ascontiguousarray(shls, dtype=np.int32).reshape(-1, ncenter)
         n = len(shls)
         cart = kind == CART
-        sizes = np.array([int(np.prod(shell_dims(self.bas, s, cart))) for s in shls], dtype=np.uint64)
+        sizes = np.array([ncomp * int(np.prod(shell_dims(self.bas, s, cart))) for s in shls], dtype=np.uint64)
         if out_off is None:
             offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
             total = int(sizes.sum())
@@ -148,6 +150,13 @@ class Context:
     def int2c2e_batch(self, shls, kind=SPH, **kw):
         """Shell pairs (i|k): the 2-centre Coulomb metric of density fitting (src/cint2c2e.c:351)."""
         return self._batch(self.lib.cintb200_int2c2e_batch, 2, shls, kind, **kw)
+
+    def int2e_ip1_batch(self, shls, kind=SPH, **kw):
+        """( nabla i j | k l ): 3 components per quartet, block layout [comp][l][k][j][i] (src/autocode/grad2.c:19-68)."""
+        return self._batch(self.lib.cintb200_int2e_ip1_batch, 4, shls, kind, ncomp=3, **kw)
+
+    def int3c2e_ip1_batch(self, shls, kind=SPH, **kw):
+        return self._batch(self.lib.cintb200_int3c2e_ip1_batch, 3, shls, kind, ncomp=3, **kw)
 
     def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
         """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array."""

@@ -333,6 +333,7 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
     cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_rys_fast); cudaFree(c->d_c2s);
     cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_nonzero); cudaFree(c->d_scratch); cudaFree(c->d_counters);
     if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
+    if (c->deriv) { cintb200_destroy(c->deriv); c->deriv = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->magic = 0;
@@ -362,6 +363,8 @@ struct ClassKey {
 };
 
 static inline int shell_dim(const ShellInfo &s, int cart) { return (cart ? B200_NCART(s.l) : 2 * s.l + 1) * s.nctr; }
+static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
+                      double *out, int on_device, int *nonzero, int first_cart = 0);
 
 extern "C" size_t cintb200_block_size(const cintb200_ctx *c, int kind, const int *shls, int ncenter)
 {
@@ -374,8 +377,10 @@ extern "C" size_t cintb200_block_size(const cintb200_ctx *c, int kind, const int
     return n;
 }
 
+// first_cart = 1: the FIRST shell of every tuple keeps Cartesian components while the others are transformed to the
+// requested kind (used by the first-derivative assembly, which differentiates in the Cartesian basis)
 static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
-                      double *out, int on_device, int *nonzero)
+                      double *out, int on_device, int *nonzero, int first_cart)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (n == 0) return 0;
@@ -408,13 +413,14 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
             continue;
         }
         const int i = s[0], j = s[1], k = s[2], l = (ncenter == 4) ? s[3] : -1;
-        const long long di = shell_dim(c->shells[i], cart), dj = shell_dim(c->shells[j], cart);
+        const long long di = shell_dim(c->shells[i], cart || first_cart), dj = shell_dim(c->shells[j], cart);
         const long long dk = shell_dim(c->shells[k], cart), dl = (l >= 0) ? shell_dim(c->shells[l], cart) : 1;
         T.bra = (int)((i >= j) ? (size_t)i * (i + 1) / 2 + j : (size_t)j * (j + 1) / 2 + i);
         const PairHdr &hb = c->pairs[T.bra];
         const long long si = 1, sj = di, sk = di * dj, sl = di * dj * dk;
         if (hb.sh_a == i && (i != j || true)) { T.sa = (int)si; T.sb = (int)sj; }
         if (hb.sh_a != i) { T.sa = (int)sj; T.sb = (int)si; }
+        if (first_cart) T.flags = (hb.sh_a == i) ? 1 : 2;
         if (l >= 0) {
             T.ket = (int)((k >= l) ? (size_t)k * (k + 1) / 2 + l : (size_t)l * (l + 1) / 2 + k);
             const PairHdr &hk = c->pairs[T.ket];
@@ -486,7 +492,8 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
     if (!on_device) {
         if (out_off) {
             for (size_t t = 0; t < n; t++) {
-                const size_t len = cintb200_block_size(c, kind, shls + t * ncenter, ncenter);
+                size_t len = cintb200_block_size(c, kind, shls + t * ncenter, ncenter);
+                if (first_cart) len = len / shell_dim(c->shells[shls[t * ncenter]], cart) * shell_dim(c->shells[shls[t * ncenter]], 1);
                 memcpy(out + offs[t], (double *)c->h_stage + offs[t], sizeof(double) * len);
             }
         } else {
@@ -509,6 +516,185 @@ extern "C" long cintb200_int2c2e_batch(cintb200_ctx *c, int kind, const int *shl
                                        double *out, int on_device, int *nonzero)
 { return run_batch(c, 2, kind, shls, n, out_off, out, on_device, nonzero); }
 
+// ------------------------------------------------------------------ first derivatives
+// int2e_ip1 / int3c2e_ip1: ( nabla i j | k l ), src/autocode/grad2.c:19-68 and src/autocode/int3c2e.c (ng = {1,0,0,0,1,1,1,3}:
+// one extra unit of angular momentum on i, 3 tensor components).  The reference differentiates on the g array,
+//     d/dx [ (x-X)^n e^{-a (x-X)^2} ] = n (x-X)^{n-1} e^{..} - 2 a (x-X)^{n+1} e^{..}          (CINTnabla1i_2e, src/g2e.c:4550)
+// Here the same identity is applied one level up, on whole SHELLS: a helper context holds for every shell i a raised shell
+// i+ (l+1, contraction coefficients -2 a_p c_kp) and a lowered shell i- (l-1, same coefficients).  The Cartesian blocks
+// (i+ j|kl) and (i- j|kl) come from the ordinary engine (first index left in Cartesians), and one small kernel combines
+// them component by component, applies cart->sph on i and writes the three blocks out[comp][l][k][j][i].
+struct IpTask {
+    size_t off_p, off_m, off_o, comp_stride;   // element offsets of the raised / lowered / output blocks, stride between components
+    int li, nctr, rest, has_m;                 // rest = product of the other dimensions (contraction included)
+};
+
+__device__ __forceinline__ void ip_cart_xyz(int l, int idx, int &lx, int &ly, int &lz)
+{
+    int n = 0;
+    for (lx = l; lx >= 0; lx--) {
+        const int cnt = l - lx + 1;
+        if (idx < n + cnt) { lz = idx - n; ly = l - lx - lz; return; }
+        n += cnt;
+    }
+    lx = ly = lz = 0;
+}
+__device__ __forceinline__ int ip_cart_index(int lx, int lz, int l) { const int r = l - lx; return r * (r + 1) / 2 + lz; }
+
+__global__ void ip1_assemble_kernel(const IpTask *__restrict__ tasks, size_t ntasks, const double *__restrict__ bp,
+                                    const double *__restrict__ bm, double *__restrict__ out, const double *__restrict__ c2s,
+                                    const int *__restrict__ c2s_off, int cart)
+{
+    const double fsp[2] = {0.282094791773878143, 0.488602511902919921};
+    for (size_t t = blockIdx.x; t < ntasks; t += gridDim.x) {
+        const IpTask T = tasks[t];
+        const int li = T.li, nfi = B200_NCART(li), nfp = B200_NCART(li + 1), nfm = li > 0 ? B200_NCART(li - 1) : 0;
+        const bool sph = !cart && li >= 2;
+        const int di = sph ? 2 * li + 1 : nfi;
+        // the engine scales s and p functions by fac_sp(l) (src/g1e.c:565-572) instead of transforming them: undo it for
+        // the raised / lowered shell and apply the factor of the target shell
+        const double fi = li < 2 ? fsp[li] : 1.0;
+        const double sp = fi / (li + 1 < 2 ? fsp[li + 1] : 1.0);
+        const double sm = li > 0 ? fi / (li - 1 < 2 ? fsp[li - 1] : 1.0) : 0.0;
+        const double *cm = c2s + c2s_off[li];
+        const size_t per = (size_t)di * T.nctr * T.rest;
+        for (size_t idx = threadIdx.x; idx < 3 * per; idx += blockDim.x) {
+            const int comp = (int)(idx / per);
+            size_t w = idx - (size_t)comp * per;
+            const int m = (int)(w % di);
+            w /= di;
+            const int ic = (int)(w % T.nctr);
+            const size_t r = w / T.nctr;
+            const double *pp = bp + T.off_p + (size_t)ic * nfp + (size_t)T.nctr * nfp * r;
+            const double *pm = bm + T.off_m + (size_t)ic * nfm + (size_t)T.nctr * nfm * r;
+            double v = 0;
+            const int a0 = sph ? 0 : m, a1 = sph ? nfi : m + 1;
+            for (int a = a0; a < a1; a++) {
+                const double coef = sph ? cm[m * nfi + a] : 1.0;
+                if (coef == 0.0) continue;
+                int ax, ay, az;
+                ip_cart_xyz(li, a, ax, ay, az);
+                const int n = comp == 0 ? ax : comp == 1 ? ay : az;
+                const int up = ip_cart_index(ax + (comp == 0), az + (comp == 2), li + 1);
+                double d = sp * pp[up];
+                if (n > 0 && T.has_m) d += n * sm * pm[ip_cart_index(ax - (comp == 0), az - (comp == 2), li - 1)];
+                v = fma(coef, d, v);
+            }
+            out[T.off_o + (size_t)comp * T.comp_stride + (size_t)ic * di + m + (size_t)T.nctr * di * r] = v;
+        }
+    }
+}
+
+static CINTOpt *ctx_deriv(CINTOpt *c)
+{
+    std::lock_guard<std::mutex> lock(c->mtx);
+    if (c->deriv) return c->deriv;
+    const int nb = c->nbas;
+    std::vector<int> xbas(c->bas);
+    xbas.resize((size_t)3 * nb * BAS_SLOTS);
+    std::vector<double> xenv(c->env);
+    for (int i = 0; i < nb; i++) {
+        const ShellInfo &s = c->shells[i];
+        int *up = xbas.data() + (size_t)(nb + i) * BAS_SLOTS, *dn = xbas.data() + (size_t)(2 * nb + i) * BAS_SLOTS;
+        memcpy(up, c->bas.data() + (size_t)i * BAS_SLOTS, sizeof(int) * BAS_SLOTS);
+        memcpy(dn, c->bas.data() + (size_t)i * BAS_SLOTS, sizeof(int) * BAS_SLOTS);
+        up[ANG_OF] = std::min(s.l + 1, B200_LMAX);          // l = LMAX: placeholder, rejected when it is differentiated
+        dn[ANG_OF] = std::max(s.l - 1, 0);                  // l = 0: placeholder, never used
+        up[PTR_COEFF] = (int)xenv.size();
+        for (int k = 0; k < s.nctr; k++)
+            for (int p = 0; p < s.nprim; p++) xenv.push_back(-2.0 * s.exps[p] * s.coef[k * s.nprim + p]);
+    }
+    CINTOpt *d = NULL;
+    if (cintb200_create(&d, c->atm.data(), c->natm, xbas.data(), 3 * nb, xenv.data(), c->device)) return NULL;
+    c->deriv = d;
+    return d;
+}
+
+static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
+                          double *out, int on_device, int *nonzero)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    if (n == 0) return 0;
+    if (!shls || !out) return b200_fail(CINTB200_EINVAL, "NULL shls/out");
+    const int cart = (kind == CINTB200_CART), nb = c->nbas;
+    for (size_t t = 0; t < n; t++)
+        for (int m = 0; m < ncenter; m++) {
+            const int sh = shls[t * ncenter + m];
+            if (sh < 0 || sh >= nb) return b200_fail(CINTB200_EINVAL, "tuple %zu: shell id %d out of range", t, sh);
+            if (m == 0 && c->shells[sh].l + 1 > B200_LMAX)
+                return b200_fail(CINTB200_ENOSUP, "derivative of a shell with l = %d needs l + 1 > %d", c->shells[sh].l, B200_LMAX);
+        }
+    CINTOpt *d = ctx_deriv(c);
+    if (!d) return CINTB200_ENODEV;
+    std::vector<int> shp(n * ncenter), shm;
+    std::vector<size_t> offp(n), offm;
+    std::vector<IpTask> it(n);
+    std::vector<size_t> mslot(n, (size_t)-1);
+    size_t totp = 0, totm = 0, toto = 0;
+    for (size_t t = 0; t < n; t++) {
+        const int *s = shls + t * ncenter;
+        const ShellInfo &si = c->shells[s[0]];
+        size_t rest = 1;
+        for (int m = 1; m < ncenter; m++) rest *= shell_dim(c->shells[s[m]], cart);
+        const size_t di = (size_t)(cart ? B200_NCART(si.l) : 2 * si.l + 1) * si.nctr;
+        IpTask &T = it[t];
+        T.li = si.l; T.nctr = si.nctr; T.rest = (int)rest; T.has_m = si.l > 0;
+        T.comp_stride = di * rest;
+        T.off_o = out_off ? out_off[t] : toto;
+        toto = std::max(toto, T.off_o + 3 * T.comp_stride);
+        for (int m = 0; m < ncenter; m++) shp[t * ncenter + m] = s[m];
+        shp[t * ncenter] = nb + s[0];
+        offp[t] = T.off_p = totp;
+        totp += (size_t)B200_NCART(si.l + 1) * si.nctr * rest;
+        T.off_m = 0;
+        if (si.l > 0) {
+            mslot[t] = offm.size();
+            for (int m = 0; m < ncenter; m++) shm.push_back(m == 0 ? 2 * nb + s[0] : s[m]);
+            offm.push_back(totm);
+            T.off_m = totm;
+            totm += (size_t)B200_NCART(si.l - 1) * si.nctr * rest;
+        }
+    }
+    CUDA_OK(cudaSetDevice(c->device));
+    double *d_p = nullptr, *d_m = nullptr, *d_o = nullptr;
+    IpTask *d_it = nullptr;
+    int *d_c2soff = nullptr;
+    auto cleanup = [&]() { cudaFree(d_p); cudaFree(d_m); cudaFree(d_it); cudaFree(d_c2soff); if (!on_device) cudaFree(d_o); };
+    if (cudaMalloc(&d_p, sizeof(double) * std::max<size_t>(1, totp)) != cudaSuccess || cudaMalloc(&d_m, sizeof(double) * std::max<size_t>(1, totm)) != cudaSuccess ||
+        cudaMalloc(&d_it, sizeof(IpTask) * n) != cudaSuccess || cudaMalloc(&d_c2soff, sizeof(C2S_OFF)) != cudaSuccess) {
+        cleanup();
+        return b200_fail(CINTB200_ENOMEM, "derivative scratch allocation failed");
+    }
+    d_o = out;
+    if (!on_device && cudaMalloc(&d_o, sizeof(double) * toto) != cudaSuccess) { d_o = nullptr; cleanup(); return b200_fail(CINTB200_ENOMEM, "derivative output allocation failed"); }
+    std::vector<int> nzp(n, 0), nzm(offm.size(), 0);
+    long rc = run_batch(d, ncenter, kind, shp.data(), n, offp.data(), d_p, 1, nzp.data(), 1);
+    if (rc >= 0 && !offm.empty()) rc = run_batch(d, ncenter, kind, shm.data(), offm.size(), offm.data(), d_m, 1, nzm.data(), 1);
+    if (rc < 0) { cleanup(); return rc; }
+    {
+        std::lock_guard<std::mutex> lock(c->mtx);
+        cudaMemcpyAsync(d_it, it.data(), sizeof(IpTask) * n, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_c2soff, C2S_OFF, sizeof(C2S_OFF), cudaMemcpyHostToDevice, c->stream);
+        const unsigned grid = (unsigned)std::min<size_t>(n, 148 * 16);
+        ip1_assemble_kernel<<<grid, 128, 0, c->stream>>>(d_it, n, d_p, d_m, d_o, c->d_c2s, d_c2soff, cart);
+        c->launches++;
+        if (!on_device) cudaMemcpyAsync(out, d_o, sizeof(double) * toto, cudaMemcpyDeviceToHost, c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cleanup(); return b200_fail(CINTB200_ENODEV, "derivative assembly failed: %s", cudaGetErrorString(e)); }
+    }
+    if (nonzero) for (size_t t = 0; t < n; t++) nonzero[t] = nzp[t] | (mslot[t] != (size_t)-1 ? nzm[mslot[t]] : 0);
+    cleanup();
+    return (long)n;
+}
+
+extern "C" long cintb200_int2e_ip1_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                         double *out, int on_device, int *nonzero)
+{ return run_batch_ip1(c, 4, kind, shls, n, out_off, out, on_device, nonzero); }
+
+extern "C" long cintb200_int3c2e_ip1_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                           double *out, int on_device, int *nonzero)
+{ return run_batch_ip1(c, 3, kind, shls, n, out_off, out, on_device, nonzero); }
+
 // ------------------------------------------------------------------ Schwarz bounds (device)
 // q[p] = sqrt(max |(ij|ij)|) over the block of shell pair p: |(ij|kl)| <= q[ij] q[kl].  The reference has no
 // shell-quartet screening (its callers do it); the whole-job driver uses these bounds to skip work items
@@ -529,9 +715,6 @@ __global__ void block_maxabs_kernel(const double *__restrict__ v, const size_t *
         q[p] = sqrt(m);
     }
 }
-
-static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
-                      double *out, int on_device, int *nonzero);
 
 int ctx_compute_schwarz(CINTOpt *c)
 {
@@ -641,7 +824,62 @@ static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT
     return nz;
 }
 
+// ( nabla i j | k l ): three blocks, out[comp][l][k][j][i]; with dims the stride between components is the product of dims
+static CACHE_SIZE_T drop_in_ip1(int ncenter, int kind, double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm,
+                                FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{
+    if (out == NULL) {
+        size_t n = 3;
+        for (int m = 0; m < ncenter; m++) n *= CINTcgto_cart(shls[m], bas);
+        return (CACHE_SIZE_T)n;
+    }
+    CINTOpt *c = context_for(opt, atm, natm, bas, nbas, env);
+    if (!c) return 0;
+    const int cart = (kind == CINTB200_CART);
+    size_t d[4] = {1, 1, 1, 1};
+    for (int m = 0; m < ncenter; m++) {
+        if (shls[m] < 0 || shls[m] >= nbas) { b200_fail(CINTB200_EINVAL, "shell id %d out of range", shls[m]); return 0; }
+        d[m] = shell_dim(c->shells[shls[m]], cart);
+    }
+    const size_t len = d[0] * d[1] * d[2] * d[3];
+    int nz = 0;
+    if (!dims) {
+        long rc = run_batch_ip1(c, ncenter, kind, shls, 1, NULL, out, 0, &nz);
+        return rc < 0 ? 0 : nz;
+    }
+    std::vector<double> tmp(3 * len);
+    long rc = run_batch_ip1(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz);
+    if (rc < 0) return 0;
+    const size_t ni = dims[0], nj = dims[1], nk = dims[2], nl = (ncenter > 3) ? dims[3] : 1;
+    for (size_t comp = 0; comp < 3; comp++)
+        for (size_t l = 0; l < d[3]; l++)
+            for (size_t k = 0; k < d[2]; k++)
+                for (size_t j = 0; j < d[1]; j++)
+                    memcpy(out + comp * ni * nj * nk * nl + ni * (j + nj * (k + nk * l)),
+                           tmp.data() + comp * len + d[0] * (j + d[1] * (k + d[2] * l)), sizeof(double) * d[0]);
+    return nz;
+}
+
 extern "C" {
+CACHE_SIZE_T int2e_ip1_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(4, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+CACHE_SIZE_T int2e_ip1_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(4, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+CACHE_SIZE_T int3c2e_ip1_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+CACHE_SIZE_T int3c2e_ip1_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(3, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+void int2e_ip1_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+void int3c2e_ip1_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+FINT cint2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int2e_ip1_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+FINT cint3c2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int3c2e_ip1_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+void cint2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env) { int2e_ip1_optimizer(opt, atm, natm, bas, nbas, env); }
+void cint3c2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env) { int3c2e_ip1_optimizer(opt, atm, natm, bas, nbas, env); }
+
 CACHE_SIZE_T int2e_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
 { (void)cache; return drop_in(4, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
 CACHE_SIZE_T int2e_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)

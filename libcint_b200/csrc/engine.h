@@ -42,6 +42,8 @@ struct CINTOpt {
     unsigned long long *d_counters = nullptr;
     long long launches = 0;
     struct JobPlan *plan = nullptr;     // cached whole-job plan (driver.cu)
+    CINTOpt *deriv = nullptr;           // first-derivative helper context: shells [nbas, 2 nbas) = l+1 with coefficients -2 a c,
+                                        // [2 nbas, 3 nbas) = l-1 (engine.cu:ctx_deriv), built on first use
     int profile = 0;                    // record per-launch events in the whole-job driver
     std::vector<double> profile_rows;
     int force_generic = 0;              // tests: route every class through the generic kernel

@@ -96,6 +96,7 @@ __device__ __forceinline__ Task tile_task(const TileParams &T, long long w)
     k.sc = (long long)T.ustride[u] * T.ld;
     k.sd = (long long)T.ustride[T.NU_all + u] * T.ld;
     k.off = (T.trow[t] - T.row0) + T.ucol[u] * T.ld;
+    k.flags = 0; k.pad = 0;
     return k;
 }
 
@@ -237,8 +238,9 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
 
         // ---- epilogue per contraction combination: HRR (bra, ket), c2s, strided store ----
         const int nfa = B200_NCART(la), nfb = B200_NCART(lb), nfc = B200_NCART(lc), nfd = B200_NCART(ld);
-        const int da = P.cart ? nfa : 2 * la + 1, db = P.cart ? nfb : 2 * lb + 1;
-        const int dc = P.cart ? nfc : 2 * lc + 1, dd = P.cart ? nfd : 2 * ld + 1;
+        const int cm = P.cart ? 15 : (task.flags & 15);          // indices that stay Cartesian (block-uniform)
+        const int da = (cm & 1) ? nfa : 2 * la + 1, db = (cm & 2) ? nfb : 2 * lb + 1;
+        const int dc = (cm & 4) ? nfc : 2 * lc + 1, dd = (cm & 8) ? nfd : 2 * ld + 1;
         for (int comb = 0; comb < ncomb; comb++) {
             const int cab = comb % C.ncab, ccd = comb / C.ncab;
             const int ca = cab % hb.nca, cb = cab / hb.nca;
@@ -257,11 +259,11 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
                 cur = nxt;
                 nxt = (nxt == w0) ? w1 : w0;
             }
-            if (!P.cart) {
-                if (la > 1) { c2s_index(cur, nxt, 1, nfb * nfc * nfd, la, P.c2s + C.c2s_off[0]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
-                if (lb > 1) { c2s_index(cur, nxt, da, nfc * nfd, lb, P.c2s + C.c2s_off[1]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
-                if (lc > 1) { c2s_index(cur, nxt, da * db, nfd, lc, P.c2s + C.c2s_off[2]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
-                if (ld > 1) { c2s_index(cur, nxt, da * db * dc, 1, ld, P.c2s + C.c2s_off[3]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+            if (cm != 15) {
+                if (la > 1 && !(cm & 1)) { c2s_index(cur, nxt, 1, nfb * nfc * nfd, la, P.c2s + C.c2s_off[0]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (lb > 1 && !(cm & 2)) { c2s_index(cur, nxt, da, nfc * nfd, lb, P.c2s + C.c2s_off[1]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (lc > 1 && !(cm & 4)) { c2s_index(cur, nxt, da * db, nfd, lc, P.c2s + C.c2s_off[2]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
+                if (ld > 1 && !(cm & 8)) { c2s_index(cur, nxt, da * db * dc, 1, ld, P.c2s + C.c2s_off[3]); __syncthreads(); cur = nxt; nxt = (nxt == w0) ? w1 : w0; }
             }
             // store: thread index runs over the index with the smallest stride first
             const int n_out = da * db * dc * dd;

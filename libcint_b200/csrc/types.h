@@ -47,6 +47,8 @@ struct Task {
     int sa;
     long long sc, sd;          // strides of c, d
     long long off;             // block offset in `out`
+    int flags;                 // bits 0..3: canonical index a/b/c/d stays Cartesian although the call is spherical
+    int pad;                   //            (first-derivative assembly needs the differentiated index in Cartesians)
 };
 
 struct EngineParams {          // passed by value to kernels

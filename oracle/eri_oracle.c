@@ -536,3 +536,128 @@ int oracle_int2c2e_sph(double *out, const int *dims, const int *shls, const int 
 int oracle_int2c2e_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                         const int *bas, int nbas, const double *env)
 { return eri_tuple(out, dims, shls, 2, 0, atm, natm, bas, nbas, env); }
+
+/* ---------------------------------------------------------------------------------------------
+ * First derivative ( nabla i j | k l ) -- int2e_ip1 / int3c2e_ip1 (src/autocode/grad2.c:19-68,
+ * src/autocode/int3c2e.c; ng = {1,0,0,0,1,1,1,3}).  The reference applies, on its g array,
+ *     f(i) = i g(i-1) - 2 a_i g(i+1)                         (CINTnabla1i_2e, src/g2e.c:4550)
+ * i.e. d/dx of the Cartesian Gaussian of centre i.  Restated one level up: the same identity holds for whole
+ * shells, so the derivative block is a combination of the Cartesian blocks of a raised shell (l+1, coefficients
+ * -2 a_p c_kp) and a lowered shell (l-1, coefficients c_kp), evaluated by eri_tuple above; s and p functions carry
+ * fac_sp(l) instead of a transformation (src/g1e.c:565-572), which is undone / re-applied for the changed l.
+ * Output: out[comp][l][k][j][i], comp = x, y, z (the reference's tensor-component-major layout).
+ */
+static int cidx(int lx, int lz, int l) { int r = l - lx; return r * (r + 1) / 2 + lz; }
+
+static void c2s_pass(const double *in, double *out, size_t pre, int nin, int nout, size_t post, const double *cm)
+{
+        size_t p, q;
+        int m, c;
+        for (p = 0; p < pre; p++)
+        for (m = 0; m < nout; m++)
+        for (q = 0; q < post; q++) {
+                double s = 0;
+                for (c = 0; c < nin; c++) s += cm[m * nin + c] * in[(p * nin + c) * post + q];
+                out[(p * nout + m) * post + q] = s;
+        }
+}
+
+static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, int sph,
+                   const int *atm, int natm, const int *bas, int nbas, const double *env)
+{
+        const int ish = shls[0];
+        const int li = bas[ish * BAS_SLOTS + ANG_OF], npi = bas[ish * BAS_SLOTS + NPRIM_OF], nci = bas[ish * BAS_SLOTS + NCTR_OF];
+        /* private copy of the basis with the raised (index nbas) and lowered (nbas + 1) shell appended */
+        int *xb = malloc(sizeof(int) * (nbas + 2) * BAS_SLOTS);
+        memcpy(xb, bas, sizeof(int) * nbas * BAS_SLOTS);
+        memcpy(xb + nbas * BAS_SLOTS, bas + ish * BAS_SLOTS, sizeof(int) * BAS_SLOTS);
+        memcpy(xb + (nbas + 1) * BAS_SLOTS, bas + ish * BAS_SLOTS, sizeof(int) * BAS_SLOTS);
+        int nenv = 20 /* PTR_ENV_START */, n, m;
+        for (n = 0; n < natm; n++) if (atm[n * ATM_SLOTS + PTR_COORD] + 3 > nenv) nenv = atm[n * ATM_SLOTS + PTR_COORD] + 3;
+        for (n = 0; n < nbas; n++) {
+                int e1 = bas[n * BAS_SLOTS + PTR_EXP] + bas[n * BAS_SLOTS + NPRIM_OF];
+                int e2 = bas[n * BAS_SLOTS + PTR_COEFF] + bas[n * BAS_SLOTS + NPRIM_OF] * bas[n * BAS_SLOTS + NCTR_OF];
+                if (e1 > nenv) nenv = e1;
+                if (e2 > nenv) nenv = e2;
+        }
+        double *xe = malloc(sizeof(double) * (nenv + npi * nci));
+        memcpy(xe, env, sizeof(double) * nenv);
+        const double *ai = env + bas[ish * BAS_SLOTS + PTR_EXP], *ci = env + bas[ish * BAS_SLOTS + PTR_COEFF];
+        for (n = 0; n < nci; n++) for (m = 0; m < npi; m++) xe[nenv + n * npi + m] = -2 * ai[m] * ci[n * npi + m];
+        xb[nbas * BAS_SLOTS + ANG_OF] = li + 1;
+        xb[nbas * BAS_SLOTS + PTR_COEFF] = nenv;
+        xb[(nbas + 1) * BAS_SLOTS + ANG_OF] = li > 0 ? li - 1 : 0;
+
+        int dcart[4] = {1, 1, 1, 1}, nctr[4] = {1, 1, 1, 1}, ls[4] = {0, 0, 0, 0};
+        for (n = 0; n < ncenter; n++) {
+                ls[n] = bas[shls[n] * BAS_SLOTS + ANG_OF];
+                nctr[n] = bas[shls[n] * BAS_SLOTS + NCTR_OF];
+                dcart[n] = ncart(ls[n]) * nctr[n];
+        }
+        const int nfi = ncart(li), nfp = ncart(li + 1), nfm = li > 0 ? ncart(li - 1) : 0;
+        const size_t rest = (size_t)dcart[1] * dcart[2] * dcart[3];
+        double *bp = calloc((size_t)nfp * nci * rest, sizeof(double));
+        double *bm = calloc((size_t)(nfm > 0 ? nfm : 1) * nci * rest, sizeof(double));
+        int xs[4] = {nbas, shls[1], ncenter > 2 ? shls[2] : 0, ncenter > 3 ? shls[3] : 0};
+        int ret = eri_tuple(bp, NULL, xs, ncenter, 0, atm, natm, xb, nbas + 2, xe);
+        if (li > 0) {
+                xs[0] = nbas + 1;
+                int r2 = eri_tuple(bm, NULL, xs, ncenter, 0, atm, natm, xb, nbas + 2, xe);
+                if (r2 < 0) ret = r2; else if (ret >= 0) ret |= r2;
+        }
+        if (ret < 0) { free(xb); free(xe); free(bp); free(bm); return ret; }
+        const double fi = fac_sp(li), sp = fi / fac_sp(li + 1), sm = li > 0 ? fi / fac_sp(li - 1) : 0;
+        int cx[64], cy[64], cz[64];
+        cart_comp(li, cx, cy, cz);
+        /* Cartesian derivative blocks, then cart->sph index by index */
+        const size_t ncar = (size_t)nfi * nci * rest;
+        double *t1 = malloc(sizeof(double) * ncar * 2), *t2 = t1 + ncar;
+        double *cmat = malloc(sizeof(double) * 21 * 128);
+        int comp;
+        for (comp = 0; comp < 3; comp++) {
+                size_t r;
+                int ic, a;
+                for (r = 0; r < rest; r++) for (ic = 0; ic < nci; ic++) for (a = 0; a < nfi; a++) {
+                        int nn = comp == 0 ? cx[a] : comp == 1 ? cy[a] : cz[a];
+                        int up = cidx(cx[a] + (comp == 0), cz[a] + (comp == 2), li + 1);
+                        double v = sp * bp[(size_t)ic * nfp + up + (size_t)nci * nfp * r];
+                        if (nn > 0) v += nn * sm * bm[(size_t)ic * nfm + cidx(cx[a] - (comp == 0), cz[a] - (comp == 2), li - 1) + (size_t)nci * nfm * r];
+                        t1[(size_t)ic * nfi + a + (size_t)nci * nfi * r] = v;
+                }
+                int d[4];
+                for (n = 0; n < 4; n++) d[n] = dcart[n];
+                if (sph) {
+                        for (n = 0; n < ncenter; n++) {
+                                if (ls[n] < 2) continue;
+                                size_t post = 1, pre = nctr[n];
+                                for (m = 0; m < n; m++) post *= d[m];
+                                for (m = n + 1; m < 4; m++) pre *= d[m];
+                                oracle_c2s_matrix(ls[n], cmat);
+                                c2s_pass(t1, t2, pre, ncart(ls[n]), 2 * ls[n] + 1, post, cmat);
+                                d[n] = (2 * ls[n] + 1) * nctr[n];
+                                { double *tt = t1; t1 = t2; t2 = tt; }
+                        }
+                }
+                const size_t ni = dims ? (size_t)dims[0] : (size_t)d[0], nj = dims ? (size_t)dims[1] : (size_t)d[1];
+                const size_t nk = (dims && ncenter > 2) ? (size_t)dims[2] : (size_t)d[2], nl = (dims && ncenter > 3) ? (size_t)dims[3] : (size_t)d[3];
+                int i, j, k, l;
+                for (l = 0; l < d[3]; l++) for (k = 0; k < d[2]; k++) for (j = 0; j < d[1]; j++) for (i = 0; i < d[0]; i++)
+                        out[comp * ni * nj * nk * nl + i + ni * (j + nj * (k + nk * (size_t)l))] = t1[i + (size_t)d[0] * (j + (size_t)d[1] * (k + (size_t)d[2] * l))];
+        }
+        if (t1 > t2) t1 = t2;
+        free(t1); free(cmat); free(xb); free(xe); free(bp); free(bm);
+        return ret;
+}
+
+int oracle_int2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                         const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 4, 1, atm, natm, bas, nbas, env); }
+int oracle_int2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                          const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 4, 0, atm, natm, bas, nbas, env); }
+int oracle_int3c2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 3, 1, atm, natm, bas, nbas, env); }
+int oracle_int3c2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                            const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 3, 0, atm, natm, bas, nbas, env); }

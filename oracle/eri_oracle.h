@@ -30,6 +30,15 @@ int oracle_int2c2e_sph(double *out, const int *dims, const int *shls, const int 
                        const int *bas, int nbas, const double *env);
 int oracle_int2c2e_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                         const int *bas, int nbas, const double *env);
+/* first derivative ( nabla i j | k l ), out[comp][l][k][j][i]: src/autocode/grad2.c:19-68, src/autocode/int3c2e.c */
+int oracle_int2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                         const int *bas, int nbas, const double *env);
+int oracle_int2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                          const int *bas, int nbas, const double *env);
+int oracle_int3c2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env);
+int oracle_int3c2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                            const int *bas, int nbas, const double *env);
 /* real-spherical transformation matrix of one l: c2s[(2l+1)][(l+1)(l+2)/2], row-major */
 int oracle_c2s_matrix(int l, double *c2s);
 double oracle_gto_norm(int l, double a);

@@ -56,12 +56,13 @@ def dims_of(bas, shls, cart=False):
 
 
 def eval_tuple(which, name, shls, atm, bas, env, dims=None):
-    """name in {int2e_sph,int2e_cart,int3c2e_sph,int3c2e_cart}; returns (flat F-order values, ret)."""
+    """name in {int2e_sph,int2e_cart,int3c2e_sph,int3c2e_cart,int2c2e_*,int2e_ip1_*,int3c2e_ip1_*}; returns (flat F-order
+    values -- 3 component blocks back to back for the ip1 derivatives --, ret)."""
     atm = np.ascontiguousarray(atm, np.int32)
     bas = np.ascontiguousarray(bas, np.int32)
     env = np.ascontiguousarray(env, np.float64)
     d = dims_of(bas, shls, name.endswith("cart"))
-    n = int(np.prod(dims if dims is not None else d))
+    n = int(np.prod(dims if dims is not None else d)) * (3 if "_ip1_" in name else 1)
     buf = np.zeros(n)
     cs = (ctypes.c_int * len(shls))(*[int(s) for s in shls])
     cd = (ctypes.c_int * len(shls))(*[int(x) for x in dims]) if dims is not None else None

@@ -100,6 +100,57 @@ def test_known_answer_int2c2e_sph():
         assert_blocks_close(split(v2, o2, s2), w2, t, tol=1e-10 if om < 0 else TOL, what="int2c2e omega %g" % om)
 
 
+def test_ip1_first_derivatives():
+    # ( nabla i j | k l ) and ( nabla i j | k ): known answers of testsuite/test_cint.py:480 and testsuite/test_3c2e.py:304
+    # through our batch entry points, element-wise parity with the oracle, Cartesian variant, drop-in symbol with dims
+    which, _ = ou.best()
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    ctx = cb.Context(atm, bas, env)
+    q = np.array([(i, j, k, l) for l in range(8) for k in range(l + 1) for j in range(8) for i in range(j + 1)], np.int32)
+    v, o, s, nz = ctx.int2e_ip1_batch(q)
+    assert abs(np.abs(v).sum() - 115489.8647398112) < 1e-6
+    rng = np.random.default_rng(12)
+    sel = rng.choice(len(q), 250, replace=False)
+    want = ou.eval_many(which, "int2e_ip1_sph", q[sel], atm, bas, env)
+    got = split(v, o, s)
+    assert_blocks_close([got[n] for n in sel], want, q[sel], what="int2e_ip1_sph")
+    q2 = rng.integers(0, 8, (120, 4)).astype(np.int32)
+    v2, o2, s2, _ = ctx.int2e_ip1_batch(q2, kind=cb.CART)
+    assert_blocks_close(split(v2, o2, s2), ou.eval_many(which, "int2e_ip1_cart", q2, atm, bas, env), q2, what="int2e_ip1_cart")
+    t3 = np.array([(i, j, k) for k in range(4) for j in range(4) for i in range(4)], np.int32)
+    v3, o3, s3, _ = ctx.int3c2e_ip1_batch(t3)
+    assert abs(np.abs(v3).sum() - 2242.052249221302) < 1e-8
+    t3 = rng.integers(0, 8, (150, 3)).astype(np.int32)
+    v3, o3, s3, _ = ctx.int3c2e_ip1_batch(t3)
+    assert_blocks_close(split(v3, o3, s3), ou.eval_many(which, "int3c2e_ip1_sph", t3, atm, bas, env), t3, what="int3c2e_ip1_sph")
+    # drop-in symbol, embedded with dims: component stride = product of dims (src/cart2sph.c:5340-5352)
+    sh = (1, 2, 5, 3)
+    d = cb.shell_dims(bas, sh)
+    dims = (d[0] + 2, d[1] + 1, d[2], d[3] + 3)
+    big = np.full(dims + (3,), 5.0, order="F")
+    lib = cb.load_library()
+    import ctypes
+    cs, cd = (ctypes.c_int * 4)(*sh), (ctypes.c_int * 4)(*dims)
+    a32, b32, e64 = np.ascontiguousarray(atm, np.int32), np.ascontiguousarray(bas, np.int32), np.ascontiguousarray(env)
+    rc = lib.int2e_ip1_sph(big.ctypes.data_as(ctypes.c_void_p), cd, cs, a32.ctypes.data_as(ctypes.c_void_p), len(a32),
+                           b32.ctypes.data_as(ctypes.c_void_p), len(b32), e64.ctypes.data_as(ctypes.c_void_p), None, None)
+    ref_blk, _ = ou.eval_tuple(which, "int2e_ip1_sph", sh, atm, bas, env)
+    ref_blk = ref_blk.reshape(tuple(d) + (3,), order="F")
+    assert rc == 1 and np.abs(big[:d[0], :d[1], :d[2], :d[3], :] - ref_blk).max() < 1e-12 * max(1.0, np.abs(ref_blk).max())
+    assert (big[d[0]:] == 5.0).all() and (big[:, d[1]:] == 5.0).all() and (big[:, :, :, d[3]:] == 5.0).all()
+
+
+def test_ip1_on_c60_sample():
+    # gradient integrals on the benchmark molecule: contracted s shells, p/d shells, distant centres
+    which, _ = ou.best()
+    atm, bas, env = cb.load_fixture("c60_ccpvdz")
+    ctx = cb.Context(atm, bas, env)
+    rng = np.random.default_rng(99)
+    q = rng.integers(0, 300, (300, 4)).astype(np.int32)
+    v, o, s, _ = ctx.int2e_ip1_batch(q)
+    assert_blocks_close(split(v, o, s), ou.eval_many(which, "int2e_ip1_sph", q, atm, bas, env), q, what="c60 int2e_ip1_sph")
+
+
 def test_golden_testbasis_all_quartets():
     g = np.load(os.path.join(GOLD, "testbasis.npz"))
     atm, bas, env = reference_test_basis(with_fit_shells=True)

@@ -63,6 +63,41 @@ def test_known_answer_int2c2e_sph():
     assert round(abs(tot - 782.3104849606677) / cnt ** .5, 10) == 0
 
 
+def test_known_answer_ip1_derivatives():
+    # testsuite/test_cint.py:235-256,480: sum |cint2e_ip1_sph| over l, k<=l, j, i<=j of the 8 shells == 115489.8647398112
+    # (8 places after normalisation by sqrt(count)); testsuite/test_3c2e.py:304: cint3c2e_ip1_sph over i,j,k < 4 == 2242.052249221302
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    tot, cnt = 0.0, 0
+    for l in range(8):
+        for k in range(l + 1):
+            for j in range(8):
+                for i in range(j + 1):
+                    v, _ = ou.eval_tuple("port", "int2e_ip1_sph", (i, j, k, l), atm, bas, env)
+                    tot += np.abs(v).sum()
+                    cnt += v.size
+    assert round(abs(tot - 115489.8647398112) / cnt ** .5, 8) == 0
+    tot, cnt = 0.0, 0
+    for k in range(4):
+        for j in range(4):
+            for i in range(4):
+                v, _ = ou.eval_tuple("port", "int3c2e_ip1_sph", (i, j, k), atm, bas, env)
+                tot += np.abs(v).sum()
+                cnt += v.size
+    assert round(abs(tot - 2242.052249221302) / cnt ** .5, 10) == 0
+
+
+@pytest.mark.skipif(ou.ref() is None, reason="oracle/_ref not built")
+def test_port_ip1_vs_reference():
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    rng = np.random.default_rng(4)
+    for name, nc in (("int2e_ip1_sph", 4), ("int2e_ip1_cart", 4), ("int3c2e_ip1_sph", 3), ("int3c2e_ip1_cart", 3)):
+        for _ in range(60):
+            sh = tuple(int(x) for x in rng.integers(0, 8, nc))
+            a, ra = ou.eval_tuple("ref", name, sh, atm, bas, env)
+            b, rb = ou.eval_tuple("port", name, sh, atm, bas, env)
+            assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(a).max()), (name, sh)
+
+
 def test_port_vs_golden_testbasis():
     g = np.load(os.path.join(GOLD, "testbasis.npz"))
     atm, bas, env = reference_test_basis(with_fit_shells=True)

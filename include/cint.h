@@ -88,6 +88,13 @@ CINTOptimizerFunction int2e_ip1_optimizer;  /* src/autocode/grad2.c:35 */
 CINTIntegralFunction  int3c2e_ip1_sph;      /* src/autocode/int3c2e.c (int3c2e_ip1_sph) */
 CINTIntegralFunction  int3c2e_ip1_cart;
 CINTOptimizerFunction int3c2e_ip1_optimizer;
+CINTIntegralFunction  int3c2e_ip2_sph;      /* ( i j | nabla k ), src/autocode/int3c2e.c:161 */
+CINTIntegralFunction  int3c2e_ip2_cart;     /* src/autocode/int3c2e.c:153 */
+CINTOptimizerFunction int3c2e_ip2_optimizer;
+CINTIntegralFunction  int2c2e_ip1_sph;      /* ( nabla i | k ), src/autocode/int3c2e.c:376 */
+CINTOptimizerFunction int2c2e_ip1_optimizer;
+CINTIntegralFunction  int2c2e_ip2_sph;      /* ( i | nabla k ), src/autocode/int3c2e.c:454 */
+CINTOptimizerFunction int2c2e_ip2_optimizer;
 
 /* ---- v2-style wrappers (src/misc.h:35-61 ALL_CINT, include/cint.h.in:264-278) ---- */
 FINT cint2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
@@ -100,6 +107,9 @@ void cint3c2e_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT
 void cint3c2e_cart_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 FINT cint2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 FINT cint3c2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+FINT cint3c2e_ip2_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+FINT cint2c2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
+FINT cint2c2e_ip2_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);
 void cint2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 void cint3c2e_ip1_sph_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env);
 FINT cint2c2e_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt);

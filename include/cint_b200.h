@@ -70,6 +70,14 @@ long cintb200_int2e_ip1_batch(cintb200_ctx *ctx, int kind, const int *shls, size
                               const size_t *out_off, double *out, int on_device, int *nonzero);
 long cintb200_int3c2e_ip1_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
                                 const size_t *out_off, double *out, int on_device, int *nonzero);
+/* ( i j | nabla k ) -- the auxiliary-centre gradient of density fitting -- and the 2-centre ( nabla i | k ), ( i | nabla k ):
+ * int3c2e_ip2, int2c2e_ip1, int2c2e_ip2 (src/autocode/int3c2e.c:99-168, :330-383, :408-461); same layout, 3 components. */
+long cintb200_int3c2e_ip2_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                                const size_t *out_off, double *out, int on_device, int *nonzero);
+long cintb200_int2c2e_ip1_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                                const size_t *out_off, double *out, int on_device, int *nonzero);
+long cintb200_int2c2e_ip2_batch(cintb200_ctx *ctx, int kind, const int *shls, size_t n,
+                                const size_t *out_off, double *out, int on_device, int *nonzero);
 
 /* Size in doubles of one block / of a packed batch (host-side helper). */
 size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, int ncenter);

@@ -38,7 +38,7 @@ def load_library():
     lib.cintb200_destroy.argtypes = [vp]
     lib.cintb200_destroy.restype = None
     for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch", "cintb200_int2e_ip1_batch",
-                 "cintb200_int3c2e_ip1_batch"):
+                 "cintb200_int3c2e_ip1_batch", "cintb200_int3c2e_ip2_batch", "cintb200_int2c2e_ip1_batch", "cintb200_int2c2e_ip2_batch"):
         f = getattr(lib, name)
         f.argtypes = [vp, ci, vp, sz, vp, vp, ci, vp]
         f.restype = ctypes.c_long
@@ -62,7 +62,8 @@ def load_library():
         lib.cintb200_debug_profile_rows.argtypes = [vp, vp, ci]
         lib.cintb200_debug_profile_rows.restype = ci
     for name in ("int2e_sph", "int2e_cart", "int3c2e_sph", "int3c2e_cart", "int2c2e_sph", "int2c2e_cart",
-                 "int2e_ip1_sph", "int2e_ip1_cart", "int3c2e_ip1_sph", "int3c2e_ip1_cart"):
+                 "int2e_ip1_sph", "int2e_ip1_cart", "int3c2e_ip1_sph", "int3c2e_ip1_cart", "int3c2e_ip2_sph", "int3c2e_ip2_cart",
+                 "int2c2e_ip1_sph", "int2c2e_ip2_sph"):
         f = getattr(lib, name)
         f.argtypes = [vp, vp, vp, vp, ci, vp, ci, vp, vp, vp]
         f.restype = ci
@@ -157,6 +158,16 @@ class Context:
 
     def int3c2e_ip1_batch(self, shls, kind=SPH, **kw):
         return self._batch(self.lib.cintb200_int3c2e_ip1_batch, 3, shls, kind, ncomp=3, **kw)
+
+    def int3c2e_ip2_batch(self, shls, kind=SPH, **kw):
+        """( i j | nabla k ), src/autocode/int3c2e.c:161."""
+        return self._batch(self.lib.cintb200_int3c2e_ip2_batch, 3, shls, kind, ncomp=3, **kw)
+
+    def int2c2e_ip1_batch(self, shls, kind=SPH, **kw):
+        return self._batch(self.lib.cintb200_int2c2e_ip1_batch, 2, shls, kind, ncomp=3, **kw)
+
+    def int2c2e_ip2_batch(self, shls, kind=SPH, **kw):
+        return self._batch(self.lib.cintb200_int2c2e_ip2_batch, 2, shls, kind, ncomp=3, **kw)
 
     def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
         """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array."""

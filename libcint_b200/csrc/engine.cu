@@ -364,7 +364,7 @@ struct ClassKey {
 
 static inline int shell_dim(const ShellInfo &s, int cart) { return (cart ? B200_NCART(s.l) : 2 * s.l + 1) * s.nctr; }
 static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
-                      double *out, int on_device, int *nonzero, int first_cart = 0);
+                      double *out, int on_device, int *nonzero, int cart_pos = -1);
 
 extern "C" size_t cintb200_block_size(const cintb200_ctx *c, int kind, const int *shls, int ncenter)
 {
@@ -377,10 +377,10 @@ extern "C" size_t cintb200_block_size(const cintb200_ctx *c, int kind, const int
     return n;
 }
 
-// first_cart = 1: the FIRST shell of every tuple keeps Cartesian components while the others are transformed to the
-// requested kind (used by the first-derivative assembly, which differentiates in the Cartesian basis)
+// cart_pos >= 0: the shell at that position of every tuple keeps Cartesian components while the others are transformed
+// to the requested kind (used by the first-derivative assembly, which differentiates in the Cartesian basis)
 static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
-                      double *out, int on_device, int *nonzero, int first_cart)
+                      double *out, int on_device, int *nonzero, int cart_pos)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (n == 0) return 0;
@@ -402,9 +402,10 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         if (ncenter == 2) {
             // (i|k): both sides are single-shell pseudo pairs (aj = al = 0, src/g2c2e.c:15-100); block (di,dk)
             const int i = s[0], k = s[1];
-            const long long di = shell_dim(c->shells[i], cart), dk = shell_dim(c->shells[k], cart);
+            const long long di = shell_dim(c->shells[i], cart || cart_pos == 0), dk = shell_dim(c->shells[k], cart || cart_pos == 1);
             T.bra = (int)(npair2 + i); T.ket = (int)(npair2 + k);
             T.sa = 1; T.sb = 0; T.sc = di; T.sd = 0;
+            if (cart_pos >= 0) T.flags = cart_pos == 0 ? 1 : 4;
             offs[t] = out_off ? out_off[t] : total;
             T.off = (long long)offs[t];
             total = std::max(total, offs[t] + (size_t)(di * dk));
@@ -413,21 +414,25 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
             continue;
         }
         const int i = s[0], j = s[1], k = s[2], l = (ncenter == 4) ? s[3] : -1;
-        const long long di = shell_dim(c->shells[i], cart || first_cart), dj = shell_dim(c->shells[j], cart);
-        const long long dk = shell_dim(c->shells[k], cart), dl = (l >= 0) ? shell_dim(c->shells[l], cart) : 1;
+        const long long di = shell_dim(c->shells[i], cart || cart_pos == 0), dj = shell_dim(c->shells[j], cart || cart_pos == 1);
+        const long long dk = shell_dim(c->shells[k], cart || cart_pos == 2), dl = (l >= 0) ? shell_dim(c->shells[l], cart || cart_pos == 3) : 1;
         T.bra = (int)((i >= j) ? (size_t)i * (i + 1) / 2 + j : (size_t)j * (j + 1) / 2 + i);
         const PairHdr &hb = c->pairs[T.bra];
         const long long si = 1, sj = di, sk = di * dj, sl = di * dj * dk;
         if (hb.sh_a == i && (i != j || true)) { T.sa = (int)si; T.sb = (int)sj; }
         if (hb.sh_a != i) { T.sa = (int)sj; T.sb = (int)si; }
-        if (first_cart) T.flags = (hb.sh_a == i) ? 1 : 2;
+        if (cart_pos == 0) T.flags = (hb.sh_a == i) ? 1 : 2;
+        if (cart_pos == 1) T.flags = (hb.sh_a == j && hb.sh_a != i) ? 1 : 2;
         if (l >= 0) {
             T.ket = (int)((k >= l) ? (size_t)k * (k + 1) / 2 + l : (size_t)l * (l + 1) / 2 + k);
             const PairHdr &hk = c->pairs[T.ket];
             if (hk.sh_a == k) { T.sc = sk; T.sd = sl; } else { T.sc = sl; T.sd = sk; }
+            if (cart_pos == 2) T.flags = (hk.sh_a == k) ? 4 : 8;
+            if (cart_pos == 3) T.flags = (hk.sh_a == l && hk.sh_a != k) ? 4 : 8;
         } else {
             T.ket = (int)(npair2 + k);
             T.sc = sk; T.sd = 0;
+            if (cart_pos == 2) T.flags = 4;
         }
         const PairHdr &hk = c->pairs[T.ket];
         offs[t] = out_off ? out_off[t] : total;
@@ -493,7 +498,7 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         if (out_off) {
             for (size_t t = 0; t < n; t++) {
                 size_t len = cintb200_block_size(c, kind, shls + t * ncenter, ncenter);
-                if (first_cart) len = len / shell_dim(c->shells[shls[t * ncenter]], cart) * shell_dim(c->shells[shls[t * ncenter]], 1);
+                if (cart_pos >= 0) len = len / shell_dim(c->shells[shls[t * ncenter + cart_pos]], cart) * shell_dim(c->shells[shls[t * ncenter + cart_pos]], 1);
                 memcpy(out + offs[t], (double *)c->h_stage + offs[t], sizeof(double) * len);
             }
         } else {
@@ -526,7 +531,8 @@ extern "C" long cintb200_int2c2e_batch(cintb200_ctx *c, int kind, const int *shl
 // them component by component, applies cart->sph on i and writes the three blocks out[comp][l][k][j][i].
 struct IpTask {
     size_t off_p, off_m, off_o, comp_stride;   // element offsets of the raised / lowered / output blocks, stride between components
-    int li, nctr, rest, has_m;                 // rest = product of the other dimensions (contraction included)
+    int li, nctr, rest, has_m;                 // rest = product of the dimensions AFTER the differentiated index (contraction included)
+    int post, pad;                             // product of the dimensions BEFORE it (the faster-running indices)
 };
 
 __device__ __forceinline__ void ip_cart_xyz(int l, int idx, int &lx, int &ly, int &lz)
@@ -557,16 +563,19 @@ __global__ void ip1_assemble_kernel(const IpTask *__restrict__ tasks, size_t nta
         const double sp = fi / (li + 1 < 2 ? fsp[li + 1] : 1.0);
         const double sm = li > 0 ? fi / (li - 1 < 2 ? fsp[li - 1] : 1.0) : 0.0;
         const double *cm = c2s + c2s_off[li];
-        const size_t per = (size_t)di * T.nctr * T.rest;
+        const size_t post = (size_t)T.post;
+        const size_t per = post * di * T.nctr * T.rest;
         for (size_t idx = threadIdx.x; idx < 3 * per; idx += blockDim.x) {
             const int comp = (int)(idx / per);
             size_t w = idx - (size_t)comp * per;
+            const size_t q = w % post;
+            w /= post;
             const int m = (int)(w % di);
             w /= di;
             const int ic = (int)(w % T.nctr);
             const size_t r = w / T.nctr;
-            const double *pp = bp + T.off_p + (size_t)ic * nfp + (size_t)T.nctr * nfp * r;
-            const double *pm = bm + T.off_m + (size_t)ic * nfm + (size_t)T.nctr * nfm * r;
+            const double *pp = bp + T.off_p + q + post * ((size_t)ic * nfp + (size_t)T.nctr * nfp * r);
+            const double *pm = bm + T.off_m + q + post * ((size_t)ic * nfm + (size_t)T.nctr * nfm * r);
             double v = 0;
             const int a0 = sph ? 0 : m, a1 = sph ? nfi : m + 1;
             for (int a = a0; a < a1; a++) {
@@ -576,11 +585,11 @@ __global__ void ip1_assemble_kernel(const IpTask *__restrict__ tasks, size_t nta
                 ip_cart_xyz(li, a, ax, ay, az);
                 const int n = comp == 0 ? ax : comp == 1 ? ay : az;
                 const int up = ip_cart_index(ax + (comp == 0), az + (comp == 2), li + 1);
-                double d = sp * pp[up];
-                if (n > 0 && T.has_m) d += n * sm * pm[ip_cart_index(ax - (comp == 0), az - (comp == 2), li - 1)];
+                double d = sp * pp[post * up];
+                if (n > 0 && T.has_m) d += n * sm * pm[post * ip_cart_index(ax - (comp == 0), az - (comp == 2), li - 1)];
                 v = fma(coef, d, v);
             }
-            out[T.off_o + (size_t)comp * T.comp_stride + (size_t)ic * di + m + (size_t)T.nctr * di * r] = v;
+            out[T.off_o + (size_t)comp * T.comp_stride + q + post * ((size_t)ic * di + m + (size_t)T.nctr * di * r)] = v;
         }
     }
 }
@@ -610,8 +619,9 @@ static CINTOpt *ctx_deriv(CINTOpt *c)
     return d;
 }
 
-static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, size_t n, const size_t *out_off,
-                          double *out, int on_device, int *nonzero)
+// dpos: position of the differentiated shell inside the tuple (0 = i: the ip1 integrals; ncenter - 1 = k: int3c2e_ip2, int2c2e_ip2)
+static long run_batch_ip(CINTOpt *c, int ncenter, int dpos, int kind, const int *shls, size_t n, const size_t *out_off,
+                         double *out, int on_device, int *nonzero)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (n == 0) return 0;
@@ -621,7 +631,7 @@ static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, si
         for (int m = 0; m < ncenter; m++) {
             const int sh = shls[t * ncenter + m];
             if (sh < 0 || sh >= nb) return b200_fail(CINTB200_EINVAL, "tuple %zu: shell id %d out of range", t, sh);
-            if (m == 0 && c->shells[sh].l + 1 > B200_LMAX)
+            if (m == dpos && c->shells[sh].l + 1 > B200_LMAX)
                 return b200_fail(CINTB200_ENOSUP, "derivative of a shell with l = %d needs l + 1 > %d", c->shells[sh].l, B200_LMAX);
         }
     CINTOpt *d = ctx_deriv(c);
@@ -633,23 +643,25 @@ static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, si
     size_t totp = 0, totm = 0, toto = 0;
     for (size_t t = 0; t < n; t++) {
         const int *s = shls + t * ncenter;
-        const ShellInfo &si = c->shells[s[0]];
-        size_t rest = 1;
-        for (int m = 1; m < ncenter; m++) rest *= shell_dim(c->shells[s[m]], cart);
+        const ShellInfo &si = c->shells[s[dpos]];
+        size_t rest = 1, post = 1;
+        for (int m = 0; m < dpos; m++) post *= shell_dim(c->shells[s[m]], cart);
+        for (int m = dpos + 1; m < ncenter; m++) rest *= shell_dim(c->shells[s[m]], cart);
         const size_t di = (size_t)(cart ? B200_NCART(si.l) : 2 * si.l + 1) * si.nctr;
         IpTask &T = it[t];
-        T.li = si.l; T.nctr = si.nctr; T.rest = (int)rest; T.has_m = si.l > 0;
-        T.comp_stride = di * rest;
+        T.li = si.l; T.nctr = si.nctr; T.rest = (int)rest; T.has_m = si.l > 0; T.post = (int)post; T.pad = 0;
+        T.comp_stride = post * di * rest;
+        rest *= post;                                   // block sizes below: all other dimensions
         T.off_o = out_off ? out_off[t] : toto;
         toto = std::max(toto, T.off_o + 3 * T.comp_stride);
         for (int m = 0; m < ncenter; m++) shp[t * ncenter + m] = s[m];
-        shp[t * ncenter] = nb + s[0];
+        shp[t * ncenter + dpos] = nb + s[dpos];
         offp[t] = T.off_p = totp;
         totp += (size_t)B200_NCART(si.l + 1) * si.nctr * rest;
         T.off_m = 0;
         if (si.l > 0) {
             mslot[t] = offm.size();
-            for (int m = 0; m < ncenter; m++) shm.push_back(m == 0 ? 2 * nb + s[0] : s[m]);
+            for (int m = 0; m < ncenter; m++) shm.push_back(m == dpos ? 2 * nb + s[m] : s[m]);
             offm.push_back(totm);
             T.off_m = totm;
             totm += (size_t)B200_NCART(si.l - 1) * si.nctr * rest;
@@ -668,8 +680,8 @@ static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, si
     d_o = out;
     if (!on_device && cudaMalloc(&d_o, sizeof(double) * toto) != cudaSuccess) { d_o = nullptr; cleanup(); return b200_fail(CINTB200_ENOMEM, "derivative output allocation failed"); }
     std::vector<int> nzp(n, 0), nzm(offm.size(), 0);
-    long rc = run_batch(d, ncenter, kind, shp.data(), n, offp.data(), d_p, 1, nzp.data(), 1);
-    if (rc >= 0 && !offm.empty()) rc = run_batch(d, ncenter, kind, shm.data(), offm.size(), offm.data(), d_m, 1, nzm.data(), 1);
+    long rc = run_batch(d, ncenter, kind, shp.data(), n, offp.data(), d_p, 1, nzp.data(), dpos);
+    if (rc >= 0 && !offm.empty()) rc = run_batch(d, ncenter, kind, shm.data(), offm.size(), offm.data(), d_m, 1, nzm.data(), dpos);
     if (rc < 0) { cleanup(); return rc; }
     {
         std::lock_guard<std::mutex> lock(c->mtx);
@@ -689,11 +701,22 @@ static long run_batch_ip1(CINTOpt *c, int ncenter, int kind, const int *shls, si
 
 extern "C" long cintb200_int2e_ip1_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
                                          double *out, int on_device, int *nonzero)
-{ return run_batch_ip1(c, 4, kind, shls, n, out_off, out, on_device, nonzero); }
+{ return run_batch_ip(c, 4, 0, kind, shls, n, out_off, out, on_device, nonzero); }
 
 extern "C" long cintb200_int3c2e_ip1_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
                                            double *out, int on_device, int *nonzero)
-{ return run_batch_ip1(c, 3, kind, shls, n, out_off, out, on_device, nonzero); }
+{ return run_batch_ip(c, 3, 0, kind, shls, n, out_off, out, on_device, nonzero); }
+
+// ( i j | nabla k ), ( nabla i | k ), ( i | nabla k ): src/autocode/int3c2e.c:99-168, :330-383, :408-461
+extern "C" long cintb200_int3c2e_ip2_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                           double *out, int on_device, int *nonzero)
+{ return run_batch_ip(c, 3, 2, kind, shls, n, out_off, out, on_device, nonzero); }
+extern "C" long cintb200_int2c2e_ip1_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                           double *out, int on_device, int *nonzero)
+{ return run_batch_ip(c, 2, 0, kind, shls, n, out_off, out, on_device, nonzero); }
+extern "C" long cintb200_int2c2e_ip2_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,
+                                           double *out, int on_device, int *nonzero)
+{ return run_batch_ip(c, 2, 1, kind, shls, n, out_off, out, on_device, nonzero); }
 
 // ------------------------------------------------------------------ Schwarz bounds (device)
 // q[p] = sqrt(max |(ij|ij)|) over the block of shell pair p: |(ij|kl)| <= q[ij] q[kl].  The reference has no
@@ -826,7 +849,7 @@ static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT
 
 // ( nabla i j | k l ): three blocks, out[comp][l][k][j][i]; with dims the stride between components is the product of dims
 static CACHE_SIZE_T drop_in_ip1(int ncenter, int kind, double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm,
-                                FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+                                FINT *bas, FINT nbas, double *env, CINTOpt *opt, int dpos = 0)
 {
     if (out == NULL) {
         size_t n = 3;
@@ -844,13 +867,13 @@ static CACHE_SIZE_T drop_in_ip1(int ncenter, int kind, double *out, FINT *dims, 
     const size_t len = d[0] * d[1] * d[2] * d[3];
     int nz = 0;
     if (!dims) {
-        long rc = run_batch_ip1(c, ncenter, kind, shls, 1, NULL, out, 0, &nz);
+        long rc = run_batch_ip(c, ncenter, dpos, kind, shls, 1, NULL, out, 0, &nz);
         return rc < 0 ? 0 : nz;
     }
     std::vector<double> tmp(3 * len);
-    long rc = run_batch_ip1(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz);
+    long rc = run_batch_ip(c, ncenter, dpos, kind, shls, 1, NULL, tmp.data(), 0, &nz);
     if (rc < 0) return 0;
-    const size_t ni = dims[0], nj = dims[1], nk = dims[2], nl = (ncenter > 3) ? dims[3] : 1;
+    const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1, nl = (ncenter > 3) ? dims[3] : 1;
     for (size_t comp = 0; comp < 3; comp++)
         for (size_t l = 0; l < d[3]; l++)
             for (size_t k = 0; k < d[2]; k++)
@@ -869,6 +892,26 @@ CACHE_SIZE_T int3c2e_ip1_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FIN
 { (void)cache; return drop_in_ip1(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
 CACHE_SIZE_T int3c2e_ip1_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
 { (void)cache; return drop_in_ip1(3, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+CACHE_SIZE_T int3c2e_ip2_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt, 2); }
+CACHE_SIZE_T int3c2e_ip2_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(3, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt, 2); }
+CACHE_SIZE_T int2c2e_ip1_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(2, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt, 0); }
+CACHE_SIZE_T int2c2e_ip2_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in_ip1(2, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt, 1); }
+void int3c2e_ip2_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+void int2c2e_ip1_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+void int2c2e_ip2_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+{ *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
+FINT cint3c2e_ip2_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int3c2e_ip2_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+FINT cint2c2e_ip1_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int2c2e_ip1_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
+FINT cint2c2e_ip2_sph(double *out, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+{ return int2c2e_ip2_sph(out, NULL, shls, atm, natm, bas, nbas, env, opt, NULL); }
 void int2e_ip1_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
 { *opt = NULL; cintb200_create(opt, atm, natm, bas, nbas, env, -1); }
 void int3c2e_ip1_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)

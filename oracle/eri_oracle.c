@@ -562,10 +562,11 @@ static void c2s_pass(const double *in, double *out, size_t pre, int nin, int nou
         }
 }
 
+/* dpos: position of the differentiated shell in the tuple (0: ip1; last: int3c2e_ip2 / int2c2e_ip2, src/autocode/int3c2e.c:99,408) */
 static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, int sph,
-                   const int *atm, int natm, const int *bas, int nbas, const double *env)
+                   const int *atm, int natm, const int *bas, int nbas, const double *env, int dpos)
 {
-        const int ish = shls[0];
+        const int ish = shls[dpos];
         const int li = bas[ish * BAS_SLOTS + ANG_OF], npi = bas[ish * BAS_SLOTS + NPRIM_OF], nci = bas[ish * BAS_SLOTS + NCTR_OF];
         /* private copy of the basis with the raised (index nbas) and lowered (nbas + 1) shell appended */
         int *xb = malloc(sizeof(int) * (nbas + 2) * BAS_SLOTS);
@@ -595,13 +596,16 @@ static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, i
                 dcart[n] = ncart(ls[n]) * nctr[n];
         }
         const int nfi = ncart(li), nfp = ncart(li + 1), nfm = li > 0 ? ncart(li - 1) : 0;
-        const size_t rest = (size_t)dcart[1] * dcart[2] * dcart[3];
-        double *bp = calloc((size_t)nfp * nci * rest, sizeof(double));
-        double *bm = calloc((size_t)(nfm > 0 ? nfm : 1) * nci * rest, sizeof(double));
-        int xs[4] = {nbas, shls[1], ncenter > 2 ? shls[2] : 0, ncenter > 3 ? shls[3] : 0};
+        size_t post = 1, rest = 1;
+        for (n = 0; n < dpos; n++) post *= dcart[n];
+        for (n = dpos + 1; n < 4; n++) rest *= dcart[n];
+        double *bp = calloc((size_t)nfp * nci * rest * post, sizeof(double));
+        double *bm = calloc((size_t)(nfm > 0 ? nfm : 1) * nci * rest * post, sizeof(double));
+        int xs[4] = {shls[0], shls[1], ncenter > 2 ? shls[2] : 0, ncenter > 3 ? shls[3] : 0};
+        xs[dpos] = nbas;
         int ret = eri_tuple(bp, NULL, xs, ncenter, 0, atm, natm, xb, nbas + 2, xe);
         if (li > 0) {
-                xs[0] = nbas + 1;
+                xs[dpos] = nbas + 1;
                 int r2 = eri_tuple(bm, NULL, xs, ncenter, 0, atm, natm, xb, nbas + 2, xe);
                 if (r2 < 0) ret = r2; else if (ret >= 0) ret |= r2;
         }
@@ -610,19 +614,19 @@ static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, i
         int cx[64], cy[64], cz[64];
         cart_comp(li, cx, cy, cz);
         /* Cartesian derivative blocks, then cart->sph index by index */
-        const size_t ncar = (size_t)nfi * nci * rest;
+        const size_t ncar = (size_t)nfi * nci * rest * post;
         double *t1 = malloc(sizeof(double) * ncar * 2), *t2 = t1 + ncar;
         double *cmat = malloc(sizeof(double) * 21 * 128);
         int comp;
         for (comp = 0; comp < 3; comp++) {
-                size_t r;
+                size_t r, q;
                 int ic, a;
-                for (r = 0; r < rest; r++) for (ic = 0; ic < nci; ic++) for (a = 0; a < nfi; a++) {
+                for (r = 0; r < rest; r++) for (ic = 0; ic < nci; ic++) for (a = 0; a < nfi; a++) for (q = 0; q < post; q++) {
                         int nn = comp == 0 ? cx[a] : comp == 1 ? cy[a] : cz[a];
                         int up = cidx(cx[a] + (comp == 0), cz[a] + (comp == 2), li + 1);
-                        double v = sp * bp[(size_t)ic * nfp + up + (size_t)nci * nfp * r];
-                        if (nn > 0) v += nn * sm * bm[(size_t)ic * nfm + cidx(cx[a] - (comp == 0), cz[a] - (comp == 2), li - 1) + (size_t)nci * nfm * r];
-                        t1[(size_t)ic * nfi + a + (size_t)nci * nfi * r] = v;
+                        double v = sp * bp[q + post * ((size_t)ic * nfp + up + (size_t)nci * nfp * r)];
+                        if (nn > 0) v += nn * sm * bm[q + post * ((size_t)ic * nfm + cidx(cx[a] - (comp == 0), cz[a] - (comp == 2), li - 1) + (size_t)nci * nfm * r)];
+                        t1[q + post * ((size_t)ic * nfi + a + (size_t)nci * nfi * r)] = v;
                 }
                 int d[4];
                 for (n = 0; n < 4; n++) d[n] = dcart[n];
@@ -640,6 +644,7 @@ static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, i
                 }
                 const size_t ni = dims ? (size_t)dims[0] : (size_t)d[0], nj = dims ? (size_t)dims[1] : (size_t)d[1];
                 const size_t nk = (dims && ncenter > 2) ? (size_t)dims[2] : (size_t)d[2], nl = (dims && ncenter > 3) ? (size_t)dims[3] : (size_t)d[3];
+                /* 2-centre tuples are (i|k): the second shell sits at position 1 of d[] */
                 int i, j, k, l;
                 for (l = 0; l < d[3]; l++) for (k = 0; k < d[2]; k++) for (j = 0; j < d[1]; j++) for (i = 0; i < d[0]; i++)
                         out[comp * ni * nj * nk * nl + i + ni * (j + nj * (k + nk * (size_t)l))] = t1[i + (size_t)d[0] * (j + (size_t)d[1] * (k + (size_t)d[2] * l))];
@@ -651,13 +656,22 @@ static int eri_ip1(double *out, const int *dims, const int *shls, int ncenter, i
 
 int oracle_int2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
                          const int *bas, int nbas, const double *env)
-{ return eri_ip1(out, dims, shls, 4, 1, atm, natm, bas, nbas, env); }
+{ return eri_ip1(out, dims, shls, 4, 1, atm, natm, bas, nbas, env, 0); }
 int oracle_int2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                           const int *bas, int nbas, const double *env)
-{ return eri_ip1(out, dims, shls, 4, 0, atm, natm, bas, nbas, env); }
+{ return eri_ip1(out, dims, shls, 4, 0, atm, natm, bas, nbas, env, 0); }
 int oracle_int3c2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
                            const int *bas, int nbas, const double *env)
-{ return eri_ip1(out, dims, shls, 3, 1, atm, natm, bas, nbas, env); }
+{ return eri_ip1(out, dims, shls, 3, 1, atm, natm, bas, nbas, env, 0); }
 int oracle_int3c2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                             const int *bas, int nbas, const double *env)
-{ return eri_ip1(out, dims, shls, 3, 0, atm, natm, bas, nbas, env); }
+{ return eri_ip1(out, dims, shls, 3, 0, atm, natm, bas, nbas, env, 0); }
+int oracle_int3c2e_ip2_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 3, 1, atm, natm, bas, nbas, env, 2); }
+int oracle_int2c2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 2, 1, atm, natm, bas, nbas, env, 0); }
+int oracle_int2c2e_ip2_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env)
+{ return eri_ip1(out, dims, shls, 2, 1, atm, natm, bas, nbas, env, 1); }

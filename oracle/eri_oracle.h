@@ -39,6 +39,13 @@ int oracle_int3c2e_ip1_sph(double *out, const int *dims, const int *shls, const 
                            const int *bas, int nbas, const double *env);
 int oracle_int3c2e_ip1_cart(double *out, const int *dims, const int *shls, const int *atm, int natm,
                             const int *bas, int nbas, const double *env);
+/* ( i j | nabla k ), ( nabla i | k ), ( i | nabla k ): src/autocode/int3c2e.c:99-168, :330-383, :408-461 */
+int oracle_int3c2e_ip2_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env);
+int oracle_int2c2e_ip1_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env);
+int oracle_int2c2e_ip2_sph(double *out, const int *dims, const int *shls, const int *atm, int natm,
+                           const int *bas, int nbas, const double *env);
 /* real-spherical transformation matrix of one l: c2s[(2l+1)][(l+1)(l+2)/2], row-major */
 int oracle_c2s_matrix(int l, double *c2s);
 double oracle_gto_norm(int l, double a);

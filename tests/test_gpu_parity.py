@@ -140,6 +140,33 @@ def test_ip1_first_derivatives():
     assert (big[d[0]:] == 5.0).all() and (big[:, d[1]:] == 5.0).all() and (big[:, :, :, d[3]:] == 5.0).all()
 
 
+def test_df_gradient_integrals():
+    # ( i j | nabla k ), ( nabla i | k ), ( i | nabla k ): testsuite/test_3c2e.py:305,319,320 + element-wise parity; the
+    # density-fitting stand-in (f orbital shells, g auxiliary shells) through int3c2e_ip1 / int3c2e_ip2
+    import itertools
+    which, _ = ou.best()
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    ctx = cb.Context(atm, bas, env)
+    for fn, name, nc, ref in ((ctx.int3c2e_ip2_batch, "int3c2e_ip2_sph", 3, 1970.982483824248),
+                              (ctx.int2c2e_ip1_batch, "int2c2e_ip1_sph", 2, 394.6515972715189),
+                              (ctx.int2c2e_ip2_batch, "int2c2e_ip2_sph", 2, 394.6515972715189)):
+        t = np.array(list(itertools.product(range(8), repeat=nc)), np.int32)
+        v, o, s, _ = fn(t)
+        blocks = split(v, o, s)
+        tot = sum(np.abs(b).sum() for b, sh in zip(blocks, t) if (sh < 4).all())
+        assert abs(tot - ref) < 1e-8, (name, tot)
+        sel = np.random.default_rng(3).choice(len(t), min(len(t), 150), replace=False)
+        assert_blocks_close([blocks[n] for n in sel], ou.eval_many(which, name, t[sel], atm, bas, env), t[sel], what=name)
+    atm, bas, env, norb = c60_df_basis(max_atoms=6)
+    naux = len(bas) - norb
+    rng = np.random.default_rng(34)
+    t = np.stack([rng.integers(0, norb, 200), rng.integers(0, norb, 200), norb + rng.integers(0, naux, 200)], 1).astype(np.int32)
+    ctx = cb.Context(atm, bas, env)
+    for fn, name in ((ctx.int3c2e_ip1_batch, "int3c2e_ip1_sph"), (ctx.int3c2e_ip2_batch, "int3c2e_ip2_sph")):
+        v, o, s, _ = fn(t)
+        assert_blocks_close(split(v, o, s), ou.eval_many(which, name, t, atm, bas, env), t, tol=1e-11 if which == "ref" else TOL, what="df " + name)
+
+
 def test_ip1_on_c60_sample():
     # gradient integrals on the benchmark molecule: contracted s shells, p/d shells, distant centres
     which, _ = ou.best()

@@ -86,11 +86,26 @@ def test_known_answer_ip1_derivatives():
     assert round(abs(tot - 2242.052249221302) / cnt ** .5, 10) == 0
 
 
+def test_known_answer_df_gradient_integrals():
+    # testsuite/test_3c2e.py:305,319,320: cint3c2e_ip2_sph 1970.982483824248, cint2c2e_ip1_sph = cint2c2e_ip2_sph 394.6515972715189
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    for name, nc, ref in (("int3c2e_ip2_sph", 3, 1970.982483824248), ("int2c2e_ip1_sph", 2, 394.6515972715189),
+                          ("int2c2e_ip2_sph", 2, 394.6515972715189)):
+        tot, cnt = 0.0, 0
+        import itertools
+        for sh in itertools.product(range(4), repeat=nc):
+            v, _ = ou.eval_tuple("port", name, sh, atm, bas, env)
+            tot += np.abs(v).sum()
+            cnt += v.size
+        assert round(abs(tot - ref) / cnt ** .5, 10) == 0, name
+
+
 @pytest.mark.skipif(ou.ref() is None, reason="oracle/_ref not built")
 def test_port_ip1_vs_reference():
     atm, bas, env = reference_test_basis(with_fit_shells=True)
     rng = np.random.default_rng(4)
-    for name, nc in (("int2e_ip1_sph", 4), ("int2e_ip1_cart", 4), ("int3c2e_ip1_sph", 3), ("int3c2e_ip1_cart", 3)):
+    for name, nc in (("int2e_ip1_sph", 4), ("int2e_ip1_cart", 4), ("int3c2e_ip1_sph", 3), ("int3c2e_ip1_cart", 3),
+                     ("int3c2e_ip2_sph", 3), ("int2c2e_ip1_sph", 2), ("int2c2e_ip2_sph", 2)):
         for _ in range(60):
             sh = tuple(int(x) for x in rng.integers(0, 8, nc))
             a, ra = ou.eval_tuple("ref", name, sh, atm, bas, env)

@@ -467,7 +467,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci);
                     L.coop = L.fn != nullptr;
                 }
-                if (L.fn && !L.coop && REG_FAST_RYS && L.nroots <= RYS_FNMAX)
+                if (L.fn && !L.coop && REG_FAST_RYS && L.nroots <= RYS_FNMAX && L.nroots <= REG_FAST_NMAX)
                     P.rys = c->d_rys_fast + rys_fast_off(L.nroots);   // register kernels of low order read the degree-6 tables
                 if (L.fn) {
                     const int qpb = L.coop ? 32 / L.ci.fs : 32;       // bras per work item (one warp)

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
                     int idx;
                     double y;
                     rys_locate(x, idx, y);
+                    asm("" : "+r"(idx));        // opaque index: no 24-bit overflow of the folded grid offset in the LDS immediates
                     const double *cf = s_rys + idx * rys_smem_stride(N) + p;
                     // Estrin (depth 4) instead of Horner (depth 9): this phase is a dependent chain on a few busy lanes
                     static_assert(RYS_DEG == 9, "Estrin scheme written for degree 9");

@@ -111,7 +111,7 @@ __host__ __device__ constexpr int reg_stage_doubles(int rb) { return 32 * rb * 2
 // row stride (doubles) of the smem copy of the Rys table: odd, so rows fall on distinct 8-byte bank pairs
 __host__ __device__ constexpr int rys_smem_stride(int n) { return (RYS_DEG + 1) * 2 * n + 1; }
 // the register kernels of order <= RYS_FNMAX use the degree-6 table set (rys.cuh)
-__host__ __device__ constexpr bool reg_fast_rys(int n) { return REG_FAST_RYS && n <= RYS_FNMAX; }
+__host__ __device__ constexpr bool reg_fast_rys(int n) { return REG_FAST_RYS && n <= REG_FAST_NMAX && n <= RYS_FNMAX; }
 __host__ __device__ constexpr int reg_rys_stride(int n) { return reg_fast_rys(n) ? (RYS_FDEG + 1) * 2 * n + 1 : rys_smem_stride(n); }
 __host__ __device__ constexpr int reg_rys_row(int n) { return (reg_fast_rys(n) ? RYS_FDEG + 1 : RYS_DEG + 1) * 2 * n; }
 
@@ -125,6 +125,9 @@ __device__ __forceinline__ void rys_roots_smem_fast(const double *tab, double x,
     int idx;
     double y;
     rys_locate_m<RYS_FM>(large ? 0.0 : x, idx, y);
+    // keep the interval index opaque: otherwise the grid's exponent offset (bits(8.0) >> 46, times the row stride) is folded
+    // into the LDS immediates, overflows their 24 bits and is re-materialised with one integer add PER coefficient load
+    asm("" : "+r"(idx));
     const double *c = tab + idx * reg_rys_stride(N);
     static_assert(RYS_FDEG == 6, "Estrin scheme below is written for degree 6");
     const double y2 = y * y, y4 = y2 * y2;
@@ -154,6 +157,7 @@ __device__ __forceinline__ void rys_roots_smem(const double *tab, int nint, doub
     double y;
     rys_locate(large ? 0.0 : x, idx, y);
     (void)nint;
+    asm("" : "+r"(idx));            // see rys_roots_smem_fast: keeps the LDS immediates small (matters from nroots = 4 on)
     const double *c = tab + idx * rys_smem_stride(N);
     static_assert(RYS_DEG == 9, "Estrin scheme below is written for degree 9");
     // Estrin evaluation: depth 4 instead of Horner's 9 dependent FMAs
@@ -504,10 +508,21 @@ eri_reg_kernel(const TileParams P)
     const int rowbase0 = (int)(P.trow[tt] - P.row0);
     double *obase = P.out + P.ucol[u] * P.ld;
     const int nca_t = P.nca_t, nca_u = P.nca_u;
+    // Fast flush (uncontracted T pairs whose 32 row blocks are adjacent -- the normal case thanks to the class-contiguous
+    // row numbering): one column of the warp is ONE contiguous run of nact * RB doubles, so the values are staged in tile
+    // order and written with plain lane + 32 k addressing; no gather table, no index arithmetic per element.
+    bool fastflush = false;
+    int nact = 0, rb0 = 0;
+    if constexpr (NCT == 1) {
+        const int rb_prev = __shfl_up_sync(0xffffffffu, rowbase0, 1);
+        fastflush = __all_sync(0xffffffffu, !active || lane == 0 || rowbase0 == rb_prev + RB);
+        nact = __popc(__ballot_sync(0xffffffffu, active)) * RB;
+        rb0 = __shfl_sync(0xffffffffu, rowbase0, 0);
+    }
 #pragma unroll 1
     for (int comb = 0; comb < NCT * NCU; comb++) {
         const int ct = comb / NCU, cu = comb - ct * NCU;
-        if (cu == 0) {
+        if (cu == 0 && !fastflush) {
             // gather table of this T contraction block: element e = q * RB + r' of the warp's column slice, r' in tile order
             const int ca = ct % nca_t, cb = ct / nca_t;
             __syncwarp();
@@ -526,7 +541,10 @@ eri_reg_kernel(const TileParams P)
         }
         // select the accumulator block of this combination (dynamic index -> predicated copies)
         double ef[NEF];
-        if constexpr (ACC_SMEM) {
+        if constexpr (NCT * NCU == 1) {
+#pragma unroll
+            for (int i = 0; i < NEF; i++) ef[i] = acc[i];
+        } else if constexpr (ACC_SMEM) {
 #pragma unroll
             for (int i = 0; i < NEF; i++) ef[i] = s_acc[(comb * NEF + i) * REG_THREADS];
         } else {
@@ -561,20 +579,36 @@ eri_reg_kernel(const TileParams P)
         static_for<DD>([&](auto MD) {
             static_for<DC>([&](auto MC) {
                 constexpr int mc = decltype(MC)::value, md = decltype(MD)::value;
-                static_for<DA>([&](auto MA) {
-                    static_for<DB>([&](auto MB) {
-                        constexpr int ma = decltype(MA)::value, mb = decltype(MB)::value;
-                        s_st[lane * RB + ma * DB + mb] = p4[((ma * DB + mb) * DC + mc) * DD + md];
-                    });
-                });
-                __syncwarp();
                 double *cp = dst + mc * sc + md * sd;
+                if (fastflush) {
+                    double *mine = s_st + lane * RB;
+                    static_for<DA>([&](auto MA) {
+                        static_for<DB>([&](auto MB) {
+                            constexpr int ma = decltype(MA)::value, mb = decltype(MB)::value;
+                            mine[ma * sa + mb * sb] = p4[((ma * DB + mb) * DC + mc) * DD + md];
+                        });
+                    });
+                    __syncwarp();
+                    double *run = cp + rb0 + lane;
 #pragma unroll
-                for (int k = 0; k < RB; k++) {
-                    const int2 t = s_tab[lane + 32 * k];
-                    if (t.x >= 0) cp[t.x] = s_st[t.y];
+                    for (int k = 0; k < RB; k++)
+                        if (lane + 32 * k < nact) run[32 * k] = s_st[lane + 32 * k];
+                    __syncwarp();
+                } else {
+                    static_for<DA>([&](auto MA) {
+                        static_for<DB>([&](auto MB) {
+                            constexpr int ma = decltype(MA)::value, mb = decltype(MB)::value;
+                            s_st[lane * RB + ma * DB + mb] = p4[((ma * DB + mb) * DC + mc) * DD + md];
+                        });
+                    });
+                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < RB; k++) {
+                        const int2 t = s_tab[lane + 32 * k];
+                        if (t.x >= 0) cp[t.x] = s_st[t.y];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             });
         });
     }

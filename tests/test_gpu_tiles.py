@@ -246,3 +246,44 @@ def test_df_tiles_generic_and_sharded():
     check_df_job(2, force_generic=True, max_triples=1500)
     check_df_job(2, nranks=2, max_triples=3000)
     check_df_job(3, nranks=3, chunk_bytes=300_000, max_triples=2000)
+
+
+def test_df_full_size_bench_configuration():
+    # BASELINE.json configs[2] at full size (stand-in auxiliary basis, see libcint_b200/basis.py:c60_df_basis): the whole
+    # density-fitting job exactly as bench.py runs it (one 62 GB tile), sampled blocks against the oracle, the symmetry
+    # (ij|k) == (ji|k)^T between the diagonal-pair blocks, and the 2-GPU column shard of the same job
+    from libcint_b200.basis import c60_df_basis
+    which, _ = ou.best()
+    atm, bas, env, norb = c60_df_basis()
+    nbas = len(bas)
+    ctx = cb.Context(atm, bas, env)
+    st = ctx.int3c2e_all(norb, chunk_bytes=80 << 30)
+    assert st[0] == 175284000 and st[1] == 7795008000 and int(st[9]) == 1
+    assert set(int(r[7]) for r in ctx.launch_rows()) <= {1, 2}          # specialised kernels only
+    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    rng = np.random.default_rng(81)
+    tol = 1e-11 if which == "ref" else 1e-12          # the reference itself carries ~1e-12 relative noise in the h/g Rys roots
+    for n in range(300):
+        i = int(rng.integers(0, norb)); j = int(rng.integers(0, i + 1)); k = int(rng.integers(norb, nbas))
+        r, _ = ctx.pair_offsets(i, j)
+        c = ctx.aux_offset(k)
+        nb = dims[i] * dims[j]
+        got = ctx.block(r, c, nb, dims[k])
+        want, _ = ou.eval_tuple(which, "int3c2e_sph", (i, j, k), atm, bas, env)
+        assert np.abs(got - want.reshape((nb, dims[k]), order="F")).max() <= tol * max(1.0, np.abs(want).max()), (i, j, k)
+        if i == j:                                        # (ii|k) block is symmetric in its two orbital indices
+            blk = got.reshape((dims[i], dims[i], dims[k]), order="F")
+            assert np.abs(blk - blk.transpose(1, 0, 2)).max() < 1e-13
+    ctx.close()
+    ctx = cb.Context(atm, bas, env)
+    st2 = ctx.int3c2e_all(norb, rank=1, nranks=2, chunk_bytes=80 << 30)
+    assert abs(st2[1] * 2 - st[1]) <= 0.02 * st[1]
+    for n in range(60):
+        i = int(rng.integers(0, norb)); j = int(rng.integers(0, i + 1)); k = int(rng.integers(norb, nbas))
+        c = ctx.aux_offset(k)
+        if c < 0:
+            continue
+        r, _ = ctx.pair_offsets(i, j)
+        got = ctx.block(r, c, dims[i] * dims[j], dims[k])
+        want, _ = ou.eval_tuple(which, "int3c2e_sph", (i, j, k), atm, bas, env)
+        assert np.abs(got - want.reshape(got.shape, order="F")).max() <= tol * max(1.0, np.abs(want).max()), (i, j, k)

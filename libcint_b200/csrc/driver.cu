@@ -6,11 +6,14 @@
 //   * shell pairs grouped into pair classes (la, lb, nca, ncb, padded primitive count Q), each list
 //     sorted by the larger shell index so that "k <= i" is a prefix/suffix of a list;
 //   * structure-of-arrays primitive tables per class (coalesced per-thread loads in kern_reg.cuh);
-//   * row numbering (all pairs, enumeration order) and this rank's column numbering (kets are dealt
-//     round-robin inside every class list: static sharding, no communication);
+//   * row numbering (chunk by chunk; inside a chunk class by class in list order, so the quartets of a warp own adjacent
+//     row blocks) and this rank's column numbering (kets are dealt round-robin inside every class list: static
+//     sharding, no communication);
 //   * chunks = ranges of the bra shell index i whose tile fits the device buffer.
-// Per chunk and (T class, U class) one kernel launch: the register kernel if the class has one,
-// else the generic block-per-quartet kernel in tile mode.
+// Per chunk and (T class, U class) up to two kernel launches (kets below the chunk's bra shells / the chunk's own kets):
+// the register kernel if the class has one, else the cooperative kernel, else the generic block-per-quartet kernel in
+// tile mode.  The same machinery runs the density-fitting job (ncenter = 3): rows = orbital pairs, kets = the
+// single-shell pseudo pairs of the auxiliary shells.
 #include <cstdio>
 #include <cstring>
 #include <cmath>

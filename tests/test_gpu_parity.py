@@ -396,3 +396,44 @@ def test_int3c2e_density_fitting_sample():
     v, o, s, nz = ctx.int3c2e_batch(t[:100], kind=cb.CART)
     want = ou.eval_many(which, "int3c2e_cart", t[:100], atm, bas, env)
     assert_blocks_close(split(v, o, s), want, t[:100], tol=1e-11 if which == "ref" else TOL, what="int3c2e cart")
+
+
+def test_dropin_calls_from_concurrent_threads():
+    # SURVEY 8b "Threading": the reference is called concurrently from OpenMP threads with one shared, read-only CINTOpt
+    # (examples/time_c60.c:196-219).  Same pattern here: 8 host threads issue drop-in calls against one optimizer object
+    # (ctypes releases the GIL during the call); every result must equal the oracle's.
+    import ctypes
+    import threading
+    which, _ = ou.best()
+    atm, bas, env = reference_test_basis()
+    lib = cb.load_library()
+    a32, b32, e64 = np.ascontiguousarray(atm, np.int32), np.ascontiguousarray(bas, np.int32), np.ascontiguousarray(env)
+    pa, pb, pe = (x.ctypes.data_as(ctypes.c_void_p) for x in (a32, b32, e64))
+    opt = ctypes.c_void_p()
+    lib.cint2e_sph_optimizer(ctypes.byref(opt), pa, len(a32), pb, len(b32), pe)
+    assert opt.value
+    rng = np.random.default_rng(21)
+    work = [[tuple(int(v) for v in rng.integers(0, 8, 4)) for _ in range(40)] for _ in range(8)]
+    results = [None] * 8
+
+    def run(n):
+        out = []
+        for sh in work[n]:
+            d = cb.shell_dims(b32, sh)
+            buf = np.zeros(int(np.prod(d)))
+            cs = (ctypes.c_int * 4)(*sh)
+            rc = lib.cint2e_sph(buf.ctypes.data_as(ctypes.c_void_p), cs, pa, len(a32), pb, len(b32), pe, opt)
+            out.append((buf, rc))
+        results[n] = out
+
+    th = [threading.Thread(target=run, args=(n,)) for n in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for n in range(8):
+        for sh, (buf, rc) in zip(work[n], results[n]):
+            want, r0 = ou.eval_tuple(which, "int2e_sph", sh, atm, bas, env)
+            assert rc == r0 and np.abs(buf - want).max() <= TOL * max(1.0, np.abs(want).max()), (n, sh)
+    lib.CINTdel_optimizer(ctypes.byref(opt))
+    assert not opt.value

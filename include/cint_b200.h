@@ -108,6 +108,19 @@ int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_
 int cintb200_int3c2e_sph_all(cintb200_ctx *ctx, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
                              double *host_sink, double *stats);
 
+/*
+ * Dense sub-tensor over shell slices -- the shape in which the reference's callers consume integrals (pyscf's fill drivers
+ * loop over shell slices and call the per-quartet function for every combination):
+ *   int2e:   shls_slice = {i0,i1, j0,j1, k0,k1, l0,l1},  out[i + NI (j + NJ (k + NK l))]  (NI*NJ*NK*NL doubles)
+ *   int3c2e: shls_slice = {i0,i1, j0,j1, k0,k1},         out[i + NI (j + NJ k)]
+ * AO indices are relative to the slice starts, column-major, spherical; EVERY combination of the slices is evaluated (no
+ * permutational symmetry is assumed -- pass triangular slices to exploit it).  Runs on the specialised tile kernels
+ * (generic kernel only for classes without one).  out: host pointer (on_device = 0) or device pointer (on_device = 1).
+ * stats as for cintb200_int2e_sph_all_unique (may be NULL).
+ */
+int cintb200_int2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+int cintb200_int3c2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+
 /* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
  * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity
  * tolerance by construction); 0 switches it off.  The bounds are evaluated on the device on first use.

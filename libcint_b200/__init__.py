@@ -190,6 +190,32 @@ class Context:
             raise B200Error("int3c2e_all failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return stats
 
+    def _block(self, fn, ncenter, shls_slice, device_ptr=None):
+        sl = np.ascontiguousarray(shls_slice, dtype=np.int32).reshape(-1)
+        assert sl.size == 2 * ncenter
+        ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in self.bas])])
+        shape = tuple(int(ao[sl[2 * m + 1]] - ao[sl[2 * m]]) for m in range(ncenter))
+        stats = np.zeros(16)
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+        if device_ptr is not None:
+            rc = fn(self.handle, _p(sl), ctypes.c_void_p(device_ptr), 1, _p(stats))
+            out = None
+        else:
+            out = np.zeros(shape, order="F")
+            rc = fn(self.handle, _p(sl), _p(out), 0, _p(stats))
+        if rc < 0:
+            raise B200Error("block failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return out, stats
+
+    def int2e_block(self, shls_slice, device_ptr=None):
+        """Dense (NI,NJ,NK,NL) tensor of int2e_sph over shell slices (i0,i1,j0,j1,k0,k1,l0,l1); returns (array, stats)."""
+        return self._block(self.lib.cintb200_int2e_sph_block, 4, shls_slice, device_ptr)
+
+    def int3c2e_block(self, shls_slice, device_ptr=None):
+        """Dense (NI,NJ,NK) tensor of int3c2e_sph over shell slices (i0,i1,j0,j1,k0,k1)."""
+        return self._block(self.lib.cintb200_int3c2e_sph_block, 3, shls_slice, device_ptr)
+
     def aux_offset(self, k):
         """This rank's column offset of auxiliary shell k in the tiles of int3c2e_all (-1: owned by another rank)."""
         f = self.lib.cintb200_debug_aux_offset

@@ -55,6 +55,9 @@ struct JobPlan {
     int rank = 0, nranks = 1;
     size_t chunk_bytes = 0;
     int ncenter = 4, aux0 = 0;              // 3: rows = orbital pairs of shells [0, aux0), columns = auxiliary shells [aux0, nbas)
+    int rect = 0;                           // dense shell-slice block (build_rect_plan): explicit bra / ket lists, one tile; value =
+                                            // number of centres of the integral (3 or 4)
+    int own_out = 1;                        // d_out[0] belongs to the plan (rect jobs may write into the caller's device buffer)
     std::vector<PairClass> classes;
     std::vector<PairClass> uclasses;        // 3-centre jobs: classes of the single-shell pseudo pairs (kets); 4-centre: unused
     std::vector<long long> colof_aux;       // 3-centre jobs: this rank's column offset of auxiliary shell aux0 + n, or -1
@@ -93,7 +96,8 @@ void jobplan_free(JobPlan *p)
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
         cudaFree(c.d_tq); cudaFree(c.dB_tq); cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
     }
-    cudaFree(p->d_out[0]); cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
+    if (p->own_out) cudaFree(p->d_out[0]);
+    cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (int k = 0; k < JobPlan::NS; k++) { if (p->streams[k]) cudaStreamDestroy(p->streams[k]); if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -505,6 +509,8 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
     return 0;
 }
 
+static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *host_sink, double *stats);
+
 // ncenter = 4: every unique quartet of int2e_sph; ncenter = 3: every triple (ij|k), i >= j < aux0 <= k, of int3c2e_sph
 static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks, size_t chunk_bytes,
                    double *host_sink, double *stats)
@@ -518,7 +524,7 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
     CU_OK(cudaSetDevice(c->device));
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
     JobPlan *plan = c->plan;
-    if (!plan || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic
+    if (!plan || plan->rect || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic
         || plan->schwarz_thr != c->schwarz_thr || plan->ncenter != ncenter || plan->aux0 != (ncenter == 3 ? aux0 : 0)) {
         if (plan) { cudaDeviceSynchronize(); jobplan_free(plan); c->plan = nullptr; }
         plan = new JobPlan();
@@ -534,6 +540,12 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
     if (host_sink && plan->out_doubles * sizeof(double) > chunk_bytes)
         return b200_fail(CINTB200_EINVAL, "host_sink mode: the largest tile (one bra shell x all kets) needs %zu bytes, "
                          "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
+    return execute_plan(c, plan, ncenter, host_sink, stats);
+}
+
+// Launch every kernel of a plan (all chunks), with the optional device->host copy of every finished tile.  Caller holds c->mtx.
+static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *host_sink, double *stats)
+{
     EngineParams EP;
     EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
     EP.expcutoff = (ncenter == 3) ? c->expcutoff3 : c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
@@ -648,6 +660,182 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
 extern "C" int cintb200_int3c2e_sph_all(cintb200_ctx *c, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
                                         double *host_sink, double *stats)
 { return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, host_sink, stats); }
+
+// ------------------------------------------------------------------ dense shell-slice blocks
+// out[i + NI (j + NJ (k + NK l))] for ALL shells i in [i0,i1), j in [j0,j1), k in [k0,k1), l in [l0,l1) (AO indices relative to
+// the slice starts, column-major): the shape in which the reference's callers consume integrals (pyscf's fill drivers
+// loop over shell slices and call the per-quartet function for every combination).  Seen as a tile, rows = AO pairs
+// (i,j) with leading dimension NI*NJ and columns = AO pairs (k,l): the bra / ket lists are explicit, every ket meets
+// every bra, and the tile kernels run unchanged (a pair's block is addressed through its own offset and strides).
+struct RectEntry { int pair; long long off; int s_a, s_b; };      // pair id, block offset (rows or columns), strides of a, b
+
+static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntry> &T, const std::vector<RectEntry> &U,
+                           long long ld, long long ncols, double *dev_out)
+{
+    auto group = [&](const std::vector<RectEntry> &E, std::vector<PairClass> &out, std::vector<std::vector<int>> &members) {
+        std::map<std::vector<int>, int> key2class;
+        for (size_t n = 0; n < E.size(); n++) {
+            const PairHdr &h = c->pairs[E[n].pair];
+            std::vector<int> key = {h.la, h.lb, h.nca, h.ncb};
+            auto it = key2class.find(key);
+            int ci;
+            if (it == key2class.end()) {
+                ci = (int)out.size();
+                key2class[key] = ci;
+                PairClass pc;
+                pc.la = h.la; pc.lb = h.lb; pc.nca = h.nca; pc.ncb = h.ncb; pc.Q = 1;
+                out.push_back(pc);
+                members.push_back({});
+            } else ci = it->second;
+            members[ci].push_back((int)n);
+            out[ci].Q = std::max(out[ci].Q, h.npp);
+        }
+    };
+    std::vector<std::vector<int>> tm, um;
+    group(T, plan->classes, tm);
+    group(U, plan->uclasses, um);
+    plan->chunks.push_back({0, 1});
+    plan->rows_before = {0, ld};
+    plan->chunk_cols.push_back(ncols);
+    plan->out_doubles = (size_t)ld * (size_t)ncols;
+    for (size_t ci = 0; ci < plan->classes.size(); ci++) {
+        PairClass &pc = plan->classes[ci];
+        std::vector<int> &mem = tm[ci];
+        // descending primitive count: neighbouring threads do equal work, a warp's first quartet carries its loop bound
+        std::stable_sort(mem.begin(), mem.end(), [&](int x, int y) { return c->pairs[T[x].pair].npp > c->pairs[T[y].pair].npp; });
+        const size_t NT = mem.size();
+        const int nct = pc.nca * pc.ncb, Q = pc.Q;
+        std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
+        std::vector<long long> trow(NT);
+        std::vector<int> tstride(2 * NT), nppc(NT);
+        for (size_t n = 0; n < NT; n++) {
+            const RectEntry &e = T[mem[n]];
+            const PairHdr &h = c->pairs[e.pair];
+            pc.ids.push_back(e.pair); pc.I.push_back(0); pc.npp.push_back(h.npp);
+            for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
+            for (int q = 0; q < Q; q++) {
+                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
+                if (q < h.npp) {
+                    const PrimPair &pp = c->prims[h.pp_off + q];
+                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
+                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
+                    tprim[5 * F + o] = pp.kij;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
+                } else {
+                    tprim[o] = 1.0; tprim[F + o] = 1.0;
+                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
+                    tprim[5 * F + o] = 0.0;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+                }
+            }
+            tstride[n] = e.s_a; tstride[NT + n] = e.s_b;
+            trow[n] = e.off;
+            nppc[n] = std::max(h.npp, 1);
+        }
+        pc.npp_prefix.assign(NT + 1, 0);
+        for (size_t n = 0; n < NT; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
+        pc.chunk_lo = {0, (int)NT};
+        if (upload(&pc.d_tprim, tprim) || upload(&pc.d_tgeom, tgeom) || upload(&pc.d_trow, trow) || upload(&pc.d_tstride, tstride) ||
+            upload(&pc.d_tI, pc.I) || upload(&pc.d_tpair, pc.ids) || upload(&pc.d_tnpp, nppc))
+            return CINTB200_ENOMEM;
+    }
+    for (size_t ci = 0; ci < plan->uclasses.size(); ci++) {
+        PairClass &pc = plan->uclasses[ci];
+        const std::vector<int> &mem = um[ci];
+        const size_t NU = mem.size();
+        std::vector<long long> ucol(NU);
+        std::vector<int> ustride(2 * NU);
+        for (size_t n = 0; n < NU; n++) {
+            const RectEntry &e = U[mem[n]];
+            pc.ids.push_back(e.pair); pc.I.push_back(0); pc.npp.push_back(c->pairs[e.pair].npp);
+            ucol[n] = e.off; ustride[n] = e.s_a; ustride[NU + n] = e.s_b;
+        }
+        pc.npp_prefix.assign(NU + 1, 0);
+        for (size_t n = 0; n < NU; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
+        pc.chunk_lo = {(int)NU, (int)NU};
+        if (upload(&pc.d_tpair, pc.ids) || upload(&pc.d_tI, pc.I) || upload(&pc.d_ucol, ucol) || upload(&pc.d_ustride, ustride))
+            return CINTB200_ENOMEM;
+    }
+    if (dev_out) { plan->d_out[0] = dev_out; plan->own_out = 0; }
+    else if (cudaMalloc((void **)&plan->d_out[0], sizeof(double) * std::max<size_t>(1, plan->out_doubles)) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cannot allocate the %zu-byte block buffer", sizeof(double) * plan->out_doubles);
+    CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_done[b], cudaEventDisableTiming));
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_copied[b], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < JobPlan::NS; k++) {
+        CU_OK(cudaStreamCreateWithFlags(&plan->streams[k], cudaStreamNonBlocking));
+        CU_OK(cudaEventCreateWithFlags(&plan->ev_join[k], cudaEventDisableTiming));
+    }
+    CU_OK(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+    CU_OK(cudaEventCreate(&plan->ev_t0));
+    CU_OK(cudaEventCreate(&plan->ev_t1));
+    return 0;
+}
+
+// ncenter 4: shls_slice = {i0,i1, j0,j1, k0,k1, l0,l1};  ncenter 3: {i0,i1, j0,j1, k0,k1}
+static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_device, double *stats)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    if (!sl || !out) return b200_fail(CINTB200_EINVAL, "NULL shls_slice/out");
+    for (int m = 0; m < ncenter; m++)
+        if (sl[2 * m] < 0 || sl[2 * m + 1] > c->nbas || sl[2 * m] >= sl[2 * m + 1])
+            return b200_fail(CINTB200_EINVAL, "shell slice %d = [%d, %d) is empty or outside 0..%d", m, sl[2 * m], sl[2 * m + 1], c->nbas);
+    std::lock_guard<std::mutex> lock(c->mtx);
+    CU_OK(cudaSetDevice(c->device));
+    auto ao0 = [&](int sh) { return (long long)c->shells[sh].ao_sph; };
+    auto aoend = [&](int sh) { return (long long)c->shells[sh].ao_sph + (2 * c->shells[sh].l + 1) * c->shells[sh].nctr; };
+    const long long NI = aoend(sl[1] - 1) - ao0(sl[0]), NJ = aoend(sl[3] - 1) - ao0(sl[2]);
+    const long long NK = aoend(sl[5] - 1) - ao0(sl[4]), NL = (ncenter == 4) ? aoend(sl[7] - 1) - ao0(sl[6]) : 1;
+    if (NI * NJ > 0x7fffffffLL) return b200_fail(CINTB200_EINVAL, "bra slice too large: NI*NJ = %lld rows exceed 2^31", NI * NJ);
+    const size_t npair2 = (size_t)c->nbas * (c->nbas + 1) / 2;
+    std::vector<RectEntry> T, U;
+    for (int j = sl[2]; j < sl[3]; j++)
+        for (int i = sl[0]; i < sl[1]; i++) {
+            RectEntry e;
+            e.pair = (int)((i >= j) ? (size_t)i * (i + 1) / 2 + j : (size_t)j * (j + 1) / 2 + i);
+            e.off = (ao0(i) - ao0(sl[0])) + NI * (ao0(j) - ao0(sl[2]));
+            const bool a_is_i = (c->pairs[e.pair].sh_a == i);         // i == j: a = b, the first index is a
+            e.s_a = a_is_i ? 1 : (int)NI; e.s_b = a_is_i ? (int)NI : 1;
+            T.push_back(e);
+        }
+    if (ncenter == 4) {
+        for (int l = sl[6]; l < sl[7]; l++)
+            for (int k = sl[4]; k < sl[5]; k++) {
+                RectEntry e;
+                e.pair = (int)((k >= l) ? (size_t)k * (k + 1) / 2 + l : (size_t)l * (l + 1) / 2 + k);
+                e.off = (ao0(k) - ao0(sl[4])) + NK * (ao0(l) - ao0(sl[6]));
+                const bool a_is_k = (c->pairs[e.pair].sh_a == k);
+                e.s_a = a_is_k ? 1 : (int)NK; e.s_b = a_is_k ? (int)NK : 1;
+                U.push_back(e);
+            }
+    } else {
+        for (int k = sl[4]; k < sl[5]; k++) {
+            RectEntry e;
+            e.pair = (int)(npair2 + k);
+            e.off = ao0(k) - ao0(sl[4]);
+            e.s_a = 1; e.s_b = 0;
+            U.push_back(e);
+        }
+    }
+    if (c->plan) { cudaDeviceSynchronize(); jobplan_free(c->plan); c->plan = nullptr; }
+    JobPlan *plan = new JobPlan();
+    plan->ncenter = 3;                  // rectangular job: separate ket classes, every ket meets every bra (see build_launches)
+    plan->rect = ncenter; plan->aux0 = 0; plan->rank = 0; plan->nranks = 1; plan->chunk_bytes = 0;
+    plan->force_generic = c->force_generic; plan->schwarz_thr = 0;
+    int rc = build_rect_plan(c, plan, T, U, NI * NJ, NK * NL, on_device ? out : nullptr);
+    if (!rc) rc = build_launches(c, plan);
+    if (rc) { jobplan_free(plan); return rc; }
+    c->plan = plan;
+    rc = execute_plan(c, plan, ncenter, on_device ? nullptr : out, stats);
+    return rc;
+}
+
+extern "C" int cintb200_int2e_sph_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 4, shls_slice, out, on_device, stats); }
+extern "C" int cintb200_int3c2e_sph_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 3, shls_slice, out, on_device, stats); }
 
 // Copy a rectangle of the most recent tile of chunk `chunk` ... (verification helper for tests):
 // evaluates ONE chunk and returns it on the host together with its geometry.

@@ -515,7 +515,10 @@ eri_reg_kernel(const TileParams P)
     int nact = 0, rb0 = 0;
     if constexpr (NCT == 1) {
         const int rb_prev = __shfl_up_sync(0xffffffffu, rowbase0, 1);
-        fastflush = __all_sync(0xffffffffu, !active || lane == 0 || rowbase0 == rb_prev + RB);
+        // my block itself must be RB contiguous rows (always true in the whole-job tiles; a dense shell-slice block
+        // strides its second index by the slice's row count) and start where my left neighbour's ends
+        const bool contiguous = (sa == 1 && (DB == 1 || sb == DA)) || (sb == 1 && (DA == 1 || sa == DB));
+        fastflush = __all_sync(0xffffffffu, !active || (contiguous && (lane == 0 || rowbase0 == rb_prev + RB)));
         nact = __popc(__ballot_sync(0xffffffffu, active)) * RB;
         rb0 = __shfl_sync(0xffffffffu, rowbase0, 0);
     }

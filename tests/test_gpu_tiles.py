@@ -287,3 +287,48 @@ def test_df_full_size_bench_configuration():
         got = ctx.block(r, c, dims[i] * dims[j], dims[k])
         want, _ = ou.eval_tuple(which, "int3c2e_sph", (i, j, k), atm, bas, env)
         assert np.abs(got - want.reshape(got.shape, order="F")).max() <= tol * max(1.0, np.abs(want).max()), (i, j, k)
+
+
+def _check_block(ctx, atm, bas, env, sl, name, nsample, rng, tol=1e-12):
+    """dense shell-slice tensor against the oracle, quartet by quartet (all of them, or a random sample)"""
+    which, _ = ou.best()
+    nc = len(sl) // 2
+    arr, st = (ctx.int2e_block(sl) if nc == 4 else ctx.int3c2e_block(sl))
+    ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+    ranges = [range(sl[2 * m], sl[2 * m + 1]) for m in range(nc)]
+    import itertools
+    tuples = list(itertools.product(*ranges))
+    assert st[0] == len(tuples) and st[1] == arr.size
+    if nsample and len(tuples) > nsample:
+        tuples = [tuples[n] for n in rng.choice(len(tuples), nsample, replace=False)]
+    for sh in tuples:
+        want, _ = ou.eval_tuple(which, name, sh, atm, bas, env)
+        idx = tuple(slice(int(ao[s] - ao[sl[2 * m]]), int(ao[s + 1] - ao[sl[2 * m]])) for m, s in enumerate(sh))
+        got = arr[idx]
+        want = want.reshape(got.shape, order="F")
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), (sl, sh)
+    return st
+
+
+def test_dense_shell_slice_blocks():
+    # cintb200_int2e_sph_block / cintb200_int3c2e_sph_block: the dense sub-tensor a fill driver asks for, on the tile kernels
+    rng = np.random.default_rng(17)
+    atm, bas, env = cb.load_fixture("c2h6_ccpvdz")
+    nb = len(bas)
+    ctx = cb.Context(atm, bas, env)
+    st = _check_block(ctx, atm, bas, env, (0, nb, 0, nb, 0, nb, 0, nb), "int2e_sph", 4000, rng)      # the full 58^4 tensor
+    assert set(int(r[7]) for r in ctx.launch_rows()) <= {1, 2}
+    _check_block(ctx, atm, bas, env, (3, 11, 0, 5, 7, nb, 2, 9), "int2e_sph", 3000, rng)             # offset, non-square slices
+    _check_block(ctx, atm, bas, env, (5, 6, 5, 6, 5, 6, 5, 6), "int2e_sph", 0, rng)                  # one quartet
+    atm, bas, env = cb.load_fixture("c2h6_ccpvtz")                                                   # f shells: generic fallback mixed in
+    ctx = cb.Context(atm, bas, env)
+    _check_block(ctx, atm, bas, env, (0, 20, 10, 30, 5, 25, 30, 54), "int2e_sph", 2500, rng)
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis(max_atoms=4)
+    ctx = cb.Context(atm, bas, env)
+    _check_block(ctx, atm, bas, env, (0, norb, 0, norb, norb, len(bas)), "int3c2e_sph", 4000, rng, tol=1e-11)
+    _check_block(ctx, atm, bas, env, (9, 27, 0, 18, norb + 20, norb + 60), "int3c2e_sph", 3000, rng, tol=1e-11)
+    # a larger block on the benchmark molecule: 20 x 20 x 150 x 150 shells = 9e6 quartets, 4.4 GB, in one call
+    atm, bas, env = cb.load_fixture("c60_ccpvdz")
+    ctx = cb.Context(atm, bas, env)
+    _check_block(ctx, atm, bas, env, (100, 120, 20, 40, 0, 150, 150, 300), "int2e_sph", 1500, rng)

@@ -381,6 +381,30 @@ def main():
                 extra["int3c2e_df"]["cpu_baseline"] = {"value": r3["integrals"] / r3["seconds"], "unit": "integrals/s", "cores": r3["threads"],
                                                        "kind": "reference", "sample": "every 2nd orbital shell pair x all auxiliary shells, %.1f s" % r3["seconds"]}
 
+    # ---------------- the general-purpose call: a dense shell-slice block (what a fill driver requests), rank 0 ----------------
+    if rank == 0 and not args.no_df:
+        try:
+            cblk = cb.Context(atm, bas, env, device=local)
+            sl = (0, 30, 0, 60, 0, len(bas), 0, len(bas))
+            ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+            nint = int((ao[sl[1]] - ao[sl[0]]) * (ao[sl[3]] - ao[sl[2]]) * (ao[sl[5]] - ao[sl[4]]) * (ao[sl[7]] - ao[sl[6]]))
+            dbuf = torch.empty(nint, dtype=torch.float64, device="cuda")
+            msb = []
+            for _ in range(2 + args.steps):
+                _, sb = cblk.int2e_block(sl, device_ptr=dbuf.data_ptr())
+                msb.append(float(sb[7]))
+            msb = sum(msb[2:]) / args.steps
+            extra = extra or {}
+            extra["int2e_block"] = {"value": nint / (msb * 1e-3), "unit": "integrals/s", "ms_per_call": msb, "integrals": nint,
+                                    "workload": "C60 cc-pVDZ, cintb200_int2e_sph_block over shell slices %s: dense (84,168,840,840) tensor, no symmetry, "
+                                                "device-resident output, plan built per call" % (sl,),
+                                    "model_tflops": float(sb[6]) / (msb * 1e-3) / 1e12}
+            del dbuf
+            cblk.close()
+        except Exception as e:          # secondary line only
+            extra = extra or {}
+            extra["int2e_block"] = {"error": str(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "integrals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -120,6 +120,8 @@ int cintb200_int3c2e_sph_all(cintb200_ctx *ctx, int aux_shell0, int rank, int nr
  */
 int cintb200_int2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
 int cintb200_int3c2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+/* 2-centre metric (i|k): shls_slice = {i0,i1, k0,k1}, out[i + NI k] (src/cint2c2e.c:351). */
+int cintb200_int2c2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
 
 /* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
  * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity

@@ -216,6 +216,10 @@ class Context:
         """Dense (NI,NJ,NK) tensor of int3c2e_sph over shell slices (i0,i1,j0,j1,k0,k1)."""
         return self._block(self.lib.cintb200_int3c2e_sph_block, 3, shls_slice, device_ptr)
 
+    def int2c2e_block(self, shls_slice, device_ptr=None):
+        """Dense (NI,NK) matrix of int2c2e_sph over shell slices (i0,i1,k0,k1): the density-fitting metric."""
+        return self._block(self.lib.cintb200_int2c2e_sph_block, 2, shls_slice, device_ptr)
+
     def aux_offset(self, k):
         """This rank's column offset of auxiliary shell k in the tiles of int3c2e_all (-1: owned by another rank)."""
         f = self.lib.cintb200_debug_aux_offset

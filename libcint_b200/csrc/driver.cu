@@ -786,11 +786,25 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
     CU_OK(cudaSetDevice(c->device));
     auto ao0 = [&](int sh) { return (long long)c->shells[sh].ao_sph; };
     auto aoend = [&](int sh) { return (long long)c->shells[sh].ao_sph + (2 * c->shells[sh].l + 1) * c->shells[sh].nctr; };
+    const size_t npair2 = (size_t)c->nbas * (c->nbas + 1) / 2;
+    std::vector<RectEntry> T, U;
+    if (ncenter == 2) {
+        // (i|k): bras and kets are the single-shell pseudo pairs; rows = AOs of the i slice, columns = AOs of the k slice
+        const long long NI2 = aoend(sl[1] - 1) - ao0(sl[0]), NK2 = aoend(sl[3] - 1) - ao0(sl[2]);
+        for (int i = sl[0]; i < sl[1]; i++) T.push_back(RectEntry{(int)(npair2 + i), ao0(i) - ao0(sl[0]), 1, 0});
+        for (int k = sl[2]; k < sl[3]; k++) U.push_back(RectEntry{(int)(npair2 + k), ao0(k) - ao0(sl[2]), 1, 0});
+        if (c->plan) { cudaDeviceSynchronize(); jobplan_free(c->plan); c->plan = nullptr; }
+        JobPlan *plan2 = new JobPlan();
+        plan2->ncenter = 3; plan2->rect = 2; plan2->force_generic = c->force_generic; plan2->schwarz_thr = 0;
+        int rc2 = build_rect_plan(c, plan2, T, U, NI2, NK2, on_device ? out : nullptr);
+        if (!rc2) rc2 = build_launches(c, plan2);
+        if (rc2) { jobplan_free(plan2); return rc2; }
+        c->plan = plan2;
+        return execute_plan(c, plan2, 3, on_device ? nullptr : out, stats);      // 2- and 3-centre integrals share the cutoff
+    }
     const long long NI = aoend(sl[1] - 1) - ao0(sl[0]), NJ = aoend(sl[3] - 1) - ao0(sl[2]);
     const long long NK = aoend(sl[5] - 1) - ao0(sl[4]), NL = (ncenter == 4) ? aoend(sl[7] - 1) - ao0(sl[6]) : 1;
     if (NI * NJ > 0x7fffffffLL) return b200_fail(CINTB200_EINVAL, "bra slice too large: NI*NJ = %lld rows exceed 2^31", NI * NJ);
-    const size_t npair2 = (size_t)c->nbas * (c->nbas + 1) / 2;
-    std::vector<RectEntry> T, U;
     for (int j = sl[2]; j < sl[3]; j++)
         for (int i = sl[0]; i < sl[1]; i++) {
             RectEntry e;
@@ -836,6 +850,8 @@ extern "C" int cintb200_int2e_sph_block(cintb200_ctx *c, const int *shls_slice, 
 { return run_block(c, 4, shls_slice, out, on_device, stats); }
 extern "C" int cintb200_int3c2e_sph_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
 { return run_block(c, 3, shls_slice, out, on_device, stats); }
+extern "C" int cintb200_int2c2e_sph_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 2, shls_slice, out, on_device, stats); }
 
 // Copy a rectangle of the most recent tile of chunk `chunk` ... (verification helper for tests):
 // evaluates ONE chunk and returns it on the host together with its geometry.

@@ -529,7 +529,9 @@ eri_reg_kernel(const TileParams P)
             // gather table of this T contraction block: element e = q * RB + r' of the warp's column slice, r' in tile order
             const int ca = ct % nca_t, cb = ct / nca_t;
             __syncwarp();
-            s_meta[lane] = make_int2(active ? rowbase0 + ca * DA * sa + cb * DB * sb : -1, sa == 1 ? sb : -sa);
+            // second field: > 0 -> a is the unit-stride index and the value is b's stride (single-shell pseudo pairs have
+            // no b index and carry stride 0: any positive number will do); < 0 -> b is the unit-stride index, -value = a's stride
+            s_meta[lane] = make_int2(active ? rowbase0 + ca * DA * sa + cb * DB * sb : -1, sa == 1 ? (sb > 0 ? sb : 1) : -sa);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < RB; k++) {

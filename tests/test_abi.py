@@ -24,7 +24,7 @@ def declared_functions():
 def test_headers_declare_the_hot_path():
     names = declared_functions()
     for must in ("int2e_sph", "int2e_cart", "int2e_optimizer", "int3c2e_sph", "cint2e_sph", "CINTdel_optimizer",
-                 "cintb200_create", "cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch", "int2c2e_sph", "cintb200_int2e_sph_block", "cintb200_int3c2e_sph_block", "int2e_ip1_sph", "int3c2e_ip1_sph", "cintb200_int2e_ip1_batch", "CINTgto_norm",
+                 "cintb200_create", "cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch", "int2c2e_sph", "cintb200_int2e_sph_block", "cintb200_int3c2e_sph_block", "cintb200_int2c2e_sph_block", "int2e_ip1_sph", "int3c2e_ip1_sph", "cintb200_int2e_ip1_batch", "CINTgto_norm",
                  "CINTcgto_spheric", "CINTtot_cgto_spheric"):
         assert must in names, must
 

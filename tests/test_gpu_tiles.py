@@ -293,7 +293,7 @@ def _check_block(ctx, atm, bas, env, sl, name, nsample, rng, tol=1e-12):
     """dense shell-slice tensor against the oracle, quartet by quartet (all of them, or a random sample)"""
     which, _ = ou.best()
     nc = len(sl) // 2
-    arr, st = (ctx.int2e_block(sl) if nc == 4 else ctx.int3c2e_block(sl))
+    arr, st = (ctx.int2e_block(sl) if nc == 4 else ctx.int3c2e_block(sl) if nc == 3 else ctx.int2c2e_block(sl))
     ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
     ranges = [range(sl[2 * m], sl[2 * m + 1]) for m in range(nc)]
     import itertools
@@ -328,6 +328,9 @@ def test_dense_shell_slice_blocks():
     ctx = cb.Context(atm, bas, env)
     _check_block(ctx, atm, bas, env, (0, norb, 0, norb, norb, len(bas)), "int3c2e_sph", 4000, rng, tol=1e-11)
     _check_block(ctx, atm, bas, env, (9, 27, 0, 18, norb + 20, norb + 60), "int3c2e_sph", 3000, rng, tol=1e-11)
+    m, _ = ctx.int2c2e_block((norb, len(bas), norb, len(bas)))                                      # the metric (P|Q)
+    assert np.abs(m - m.T).max() < 1e-13 and np.linalg.eigvalsh(m).min() > 0
+    _check_block(ctx, atm, bas, env, (norb, len(bas), norb + 7, len(bas) - 3), "int2c2e_sph", 2500, rng, tol=1e-11)
     # a larger block on the benchmark molecule: 20 x 20 x 150 x 150 shells = 9e6 quartets, 4.4 GB, in one call
     atm, bas, env = cb.load_fixture("c60_ccpvdz")
     ctx = cb.Context(atm, bas, env)

@@ -121,7 +121,9 @@ class Context:
         shls = np.ascontiguousarray(shls, dtype=np.int32).reshape(-1, ncenter)
         n = len(shls)
         cart = kind == CART
-        sizes = np.array([ncomp * int(np.prod(shell_dims(self.bas, s, cart))) for s in shls], dtype=np.uint64)
+        l, nc = self.bas[:, 1].astype(np.int64), self.bas[:, 3].astype(np.int64)
+        dim = ((l + 1) * (l + 2) // 2 if cart else 2 * l + 1) * nc                 # per shell
+        sizes = (ncomp * np.prod(dim[shls], axis=1)).astype(np.uint64) if n else np.zeros(0, np.uint64)
         if out_off is None:
             offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
             total = int(sizes.sum())

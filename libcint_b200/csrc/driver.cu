@@ -20,6 +20,7 @@
 #include <vector>
 #include <map>
 #include <algorithm>
+#include <parallel/algorithm>
 #include <cuda_runtime.h>
 #include "../../include/cint_b200.h"
 #include "types.h"
@@ -440,7 +441,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     P.tprim = T.dB_tprim; P.tgeom = T.dB_tgeom; P.trow = T.dB_trow; P.tstride = T.dB_tstride;
                     P.tI = T.dB_tI; P.tpair = T.dB_tpair; P.tnpp = T.dB_tnpp; P.tq = T.dB_tq;
                 }
-                P.NT = (int)T.ids.size(); P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
+                P.NT = (int)T.ids.size(); P.NTs = P.NT; P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
                 P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca; P.umax = std::max(1, U.Q);
                 P.tri = part;
@@ -660,6 +661,239 @@ extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nran
 extern "C" int cintb200_int3c2e_sph_all(cintb200_ctx *c, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
                                         double *host_sink, double *stats)
 { return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, host_sink, stats); }
+
+// ------------------------------------------------------------------ list mode on the tile kernels
+// Arbitrary lists of shell tuples (cintb200_int2e_batch & co.) used to run on the block-per-tuple generic kernel only
+// (C60: 1.2e8 integrals/s, slower than the reference on 16 cores).  Here every group of tuples with the same bra class and
+// ket class that has a specialised kernel is turned into explicit work items for it: the tuples are sorted by ket, each ket
+// owns a run of T OCCURRENCES (output offset + strides of that tuple, and the row of the bra pair in a per-class pair table
+// shared by all calls), and an item is {ket, first occurrence, count <= 32}.  Groups without a kernel stay with the caller.
+struct ListClass {
+    int la, lb, nca, ncb, Q;
+    std::vector<int> ids;
+    double *d_tprim = nullptr, *d_tgeom = nullptr;
+    int *d_tnpp = nullptr;
+};
+struct ListChoice { RegKernelFn fn; int coop; CoopInfo ci; };
+struct ListTables {
+    std::vector<ListClass> cls;
+    std::vector<int> cls_of, row_of;        // per pair id (shell pairs, then the single-shell pseudo pairs)
+    std::vector<ListChoice> choice;         // [bra class * ncls + ket class]: the specialised kernel, if any
+    void *d_buf = nullptr; size_t cap = 0;  // per-call arrays (grow-only)
+};
+
+void listtables_free(ListTables *lt)
+{
+    if (!lt) return;
+    for (ListClass &lc : lt->cls) { cudaFree(lc.d_tprim); cudaFree(lc.d_tgeom); cudaFree(lc.d_tnpp); }
+    cudaFree(lt->d_buf);
+    delete lt;
+}
+
+static int listtables_build(CINTOpt *c)
+{
+    ListTables *lt = new ListTables();
+    const size_t np = c->pairs.size();
+    lt->cls_of.assign(np, -1); lt->row_of.assign(np, -1);
+    std::map<std::vector<int>, int> key2class;
+    for (size_t p = 0; p < np; p++) {
+        const PairHdr &h = c->pairs[p];
+        std::vector<int> key = {h.la, h.lb, h.nca, h.ncb};
+        auto it = key2class.find(key);
+        int ci;
+        if (it == key2class.end()) {
+            ci = (int)lt->cls.size();
+            key2class[key] = ci;
+            ListClass lc;
+            lc.la = h.la; lc.lb = h.lb; lc.nca = h.nca; lc.ncb = h.ncb; lc.Q = 1;
+            lt->cls.push_back(lc);
+        } else ci = it->second;
+        lt->cls_of[p] = ci;
+        lt->row_of[p] = (int)lt->cls[ci].ids.size();
+        lt->cls[ci].ids.push_back((int)p);
+        lt->cls[ci].Q = std::max(lt->cls[ci].Q, h.npp);
+    }
+    for (ListClass &lc : lt->cls) {
+        const size_t NT = lc.ids.size();
+        const int nct = lc.nca * lc.ncb, Q = lc.Q;
+        std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
+        std::vector<int> nppc(NT);
+        for (size_t n = 0; n < NT; n++) {
+            const PairHdr &h = c->pairs[lc.ids[n]];
+            for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
+            for (int q = 0; q < Q; q++) {
+                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
+                if (q < h.npp) {
+                    const PrimPair &pp = c->prims[h.pp_off + q];
+                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
+                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
+                    tprim[5 * F + o] = pp.kij;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
+                } else {
+                    tprim[o] = 1.0; tprim[F + o] = 1.0;
+                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
+                    tprim[5 * F + o] = 0.0;
+                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+                }
+            }
+            nppc[n] = std::max(h.npp, 1);
+        }
+        if (upload(&lc.d_tprim, tprim) || upload(&lc.d_tgeom, tgeom) || upload(&lc.d_tnpp, nppc)) { listtables_free(lt); return CINTB200_ENOMEM; }
+    }
+    const int ncls = (int)lt->cls.size();
+    lt->choice.resize((size_t)ncls * ncls);
+    for (int cb = 0; cb < ncls; cb++)
+        for (int ck = 0; ck < ncls; ck++) {
+            const ListClass &B = lt->cls[cb], &K = lt->cls[ck];
+            ListChoice &ch = lt->choice[(size_t)cb * ncls + ck];
+            memset(&ch, 0, sizeof ch);
+            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb);
+            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci); ch.coop = ch.fn != nullptr; }
+        }
+    c->ltab = lt;
+    return 0;
+}
+
+// Evaluate the tuples whose (bra class, ket class) has a specialised kernel; handled[t] = 1 for those.  tasks are in the
+// caller's order (Task::off = element offset of the tuple's block in d_out, strides for the packed block).  Spherical,
+// plain Coulomb only.  Caller holds c->mtx; launches go to c->stream (not synchronised here).
+int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled)
+{
+    if (!c->ltab && listtables_build(c)) return CINTB200_ENOMEM;
+    ListTables *lt = c->ltab;
+    typedef ListChoice Choice;
+    const int ncls = (int)lt->cls.size();
+    if ((unsigned long long)ncls * ncls >= (1ull << 22) || n >= (1ull << 32)) return b200_fail(CINTB200_EINVAL, "list too large for the sort key");
+    std::vector<int> gkey(n);                       // bra class * ncls + ket class
+    // sort key: group | ket pair | orientation of the ket block | 127 - primitive count of the bra  (one 64-bit compare)
+    struct SortRec { unsigned long long key; unsigned int t; };
+    std::vector<SortRec> all(n);
+#pragma omp parallel for schedule(static) if (n > 20000)
+    for (long long t = 0; t < (long long)n; t++) {
+        const int g = lt->cls_of[tasks[t].bra] * ncls + lt->cls_of[tasks[t].ket];
+        gkey[t] = g;
+        all[t].t = (unsigned int)t;
+        all[t].key = ~0ull;
+        if (lt->choice[g].fn) {
+            handled[t] = 1;
+            const unsigned long long np_ = (unsigned long long)(127 - std::min(c->pairs[tasks[t].bra].npp, 127));
+            all[t].key = ((unsigned long long)g << 42) | ((unsigned long long)(unsigned int)tasks[t].ket << 8)
+                         | ((unsigned long long)(tasks[t].sc > tasks[t].sd) << 7) | np_;
+        }
+    }
+    std::vector<SortRec> recs;
+    recs.reserve(n);
+    for (size_t t = 0; t < n; t++) if (handled[t]) recs.push_back(all[t]);
+    all.clear(); all.shrink_to_fit();
+    if (recs.empty()) return 0;
+    auto rec_less = [](const SortRec &x, const SortRec &y) { return x.key != y.key ? x.key < y.key : x.t < y.t; };
+    if (recs.size() > 50000) __gnu_parallel::sort(recs.begin(), recs.end(), rec_less);
+    else std::sort(recs.begin(), recs.end(), rec_less);
+    const size_t m = recs.size();
+    std::vector<size_t> idx(m);
+    for (size_t q = 0; q < m; q++) idx[q] = recs[q].t;
+    auto choice = [&](int g) -> const Choice & { return lt->choice[g]; };
+    std::vector<int> tsel(m), tstride(2 * m), upair, ustride;
+    std::vector<long long> trow(m);
+    std::vector<int4> items;
+    struct Group { size_t t0, t1, u0, u1, i0, i1; int key; };
+    std::vector<Group> groups;
+    size_t g0 = 0;
+    while (g0 < m) {
+        size_t g1 = g0;
+        while (g1 < m && gkey[idx[g1]] == gkey[idx[g0]]) g1++;
+        Group G;
+        G.t0 = g0; G.t1 = g1; G.key = gkey[idx[g0]]; G.u0 = upair.size(); G.i0 = items.size();
+        const Choice &ch = choice(G.key);
+        const int per = ch.coop ? 32 / ch.ci.fs : 32;
+        const size_t ng = g1 - g0;
+        size_t k0 = g0;
+        while (k0 < g1) {
+            size_t k1 = k0;
+            const Task &a = tasks[idx[k0]];
+            while (k1 < g1 && tasks[idx[k1]].ket == a.ket && tasks[idx[k1]].sc == a.sc && tasks[idx[k1]].sd == a.sd) k1++;
+            const int u = (int)(upair.size() - G.u0);
+            upair.push_back(a.ket);
+            ustride.push_back((int)a.sc); ustride.push_back((int)a.sd);        // re-laid out per group below
+            for (size_t q = k0; q < k1; q += per)
+                items.push_back(make_int4(u, (int)(q - g0), (int)std::min<size_t>(per, k1 - q), 0));
+            k0 = k1;
+        }
+#pragma omp parallel for schedule(static) if (g1 - g0 > 20000)
+        for (long long q = (long long)g0; q < (long long)g1; q++) {
+            const Task &a = tasks[idx[q]];
+            tsel[q] = lt->row_of[a.bra];
+            trow[q] = a.off;
+            tstride[2 * g0 + (q - g0)] = a.sa;            // group-local layout [2][ng]
+            tstride[2 * g0 + ng + (q - g0)] = a.sb;
+        }
+        G.u1 = upair.size(); G.i1 = items.size();
+        groups.push_back(G);
+        g0 = g1;
+    }
+    // ustride per group as [2][NUg]
+    std::vector<int> ustr2(ustride.size());
+    size_t maxu = 1;
+    for (const Group &G : groups) {
+        const size_t nu = G.u1 - G.u0;
+        maxu = std::max(maxu, nu);
+        for (size_t u = 0; u < nu; u++) { ustr2[2 * G.u0 + u] = ustride[2 * (G.u0 + u)]; ustr2[2 * G.u0 + nu + u] = ustride[2 * (G.u0 + u) + 1]; }
+    }
+    // one device buffer: trow | ucol zeros | items | tsel | tstride | upair | ustride | counters
+    auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_trow = 0, o_ucol = al(o_trow + sizeof(long long) * m), o_items = al(o_ucol + sizeof(long long) * maxu);
+    const size_t o_tsel = al(o_items + sizeof(int4) * items.size()), o_tstr = al(o_tsel + sizeof(int) * m);
+    const size_t o_upair = al(o_tstr + sizeof(int) * 2 * m), o_ustr = al(o_upair + sizeof(int) * upair.size());
+    const size_t o_cnt = al(o_ustr + sizeof(int) * ustr2.size()), bytes = al(o_cnt + sizeof(unsigned int) * groups.size());
+    if (lt->cap < bytes) {
+        cudaFree(lt->d_buf); lt->d_buf = nullptr; lt->cap = 0;
+        if (cudaMalloc(&lt->d_buf, bytes * 2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "list-mode work arrays: %zu bytes", bytes * 2);
+        lt->cap = bytes * 2;
+    }
+    char *d = (char *)lt->d_buf;
+    cudaStream_t st = c->stream;
+    CU_OK(cudaMemsetAsync(d + o_ucol, 0, sizeof(long long) * maxu, st));
+    CU_OK(cudaMemsetAsync(d + o_cnt, 0, sizeof(unsigned int) * groups.size(), st));
+    CU_OK(cudaMemcpyAsync(d + o_trow, trow.data(), sizeof(long long) * m, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(d + o_items, items.data(), sizeof(int4) * items.size(), cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(d + o_tsel, tsel.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(d + o_tstr, tstride.data(), sizeof(int) * 2 * m, cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(d + o_upair, upair.data(), sizeof(int) * upair.size(), cudaMemcpyHostToDevice, st));
+    CU_OK(cudaMemcpyAsync(d + o_ustr, ustr2.data(), sizeof(int) * ustr2.size(), cudaMemcpyHostToDevice, st));
+    CU_OK(cudaStreamSynchronize(st));               // the host vectors go out of scope when we return
+    for (size_t g = 0; g < groups.size(); g++) {
+        const Group &G = groups[g];
+        const Choice &ch = choice(G.key);
+        const ListClass &B = lt->cls[G.key / ncls], &K = lt->cls[G.key % ncls];
+        const int nroots = (B.la + B.lb + K.la + K.lb) / 2 + 1;
+        TileParams P;
+        memset(&P, 0, sizeof P);
+        P.tprim = B.d_tprim; P.tgeom = B.d_tgeom; P.tnpp = B.d_tnpp;
+        P.NT = (int)B.ids.size(); P.Q = B.Q;
+        P.trow = (const long long *)(d + o_trow) + G.t0;
+        P.tstride = (const int *)(d + o_tstr) + 2 * G.t0;
+        P.NTs = (int)(G.t1 - G.t0);
+        P.tsel = (const int *)(d + o_tsel) + G.t0;
+        P.t_begin = 0; P.t_end = (int)(G.t1 - G.t0); P.nca_t = B.nca;
+        P.upair = (const int *)(d + o_upair) + G.u0;
+        P.ucol = (const long long *)(d + o_ucol);
+        P.ustride = (const int *)(d + o_ustr) + 2 * G.u0;
+        P.NU = P.NU_all = (int)(G.u1 - G.u0); P.u_step = 1; P.u_first = 0; P.nca_u = K.nca; P.umax = std::max(1, K.Q);
+        P.out = d_out; P.row0 = 0; P.ld = 1;
+        P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
+        P.rys = (!ch.coop && REG_FAST_RYS && nroots <= RYS_FNMAX && nroots <= REG_FAST_NMAX) ? c->d_rys_fast + rys_fast_off(nroots)
+                                                                                          : c->d_rys + rys_tab_off(nroots);
+        P.items = (const int4 *)(d + o_items) + G.i0;
+        P.nitems = (long long)(G.i1 - G.i0);
+        P.gx = 1;
+        P.counter = (unsigned int *)(d + o_cnt) + g;
+        P.batch = (int)std::max<long long>(1, std::min<long long>(16, P.nitems / (148 * 32 * 4)));
+        if (ch.coop ? coop_kernel_launch(ch.fn, ch.ci, K.nca * K.ncb, P, 1, 1, st) : reg_kernel_launch(ch.fn, nroots, K.nca * K.ncb, P, 1, 1, st))
+            return b200_fail(CINTB200_ENODEV, "list-mode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        c->launches++;
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------ dense shell-slice blocks
 // out[i + NI (j + NJ (k + NK l))] for ALL shells i in [i0,i1), j in [j0,j1), k in [k0,k1), l in [l0,l1) (AO indices relative to

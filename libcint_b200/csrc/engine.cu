@@ -334,6 +334,7 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
     cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_nonzero); cudaFree(c->d_scratch); cudaFree(c->d_counters);
     if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
     if (c->deriv) { cintb200_destroy(c->deriv); c->deriv = nullptr; }
+    if (c->ltab) { listtables_free(c->ltab); c->ltab = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->magic = 0;
@@ -394,10 +395,35 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
     std::vector<ClassKey> keys(n);
     std::vector<size_t> offs(n);
     size_t total = 0;
-    for (size_t t = 0; t < n; t++) {
+    // pass 1 (host threads): validation and block sizes; offsets are a prefix sum unless the caller gave them
+    {
+        long long bad = -1;
+#pragma omp parallel for schedule(static) if (n > 20000)
+        for (long long t = 0; t < (long long)n; t++) {
+            const int *s = shls + t * ncenter;
+            size_t sz = 1;
+            for (int m = 0; m < ncenter; m++) {
+                if (s[m] < 0 || s[m] >= c->nbas) {
+#pragma omp critical
+                    bad = (bad < 0 || t < bad) ? t : bad;
+                    sz = 0;
+                    break;
+                }
+                sz *= shell_dim(c->shells[s[m]], cart || cart_pos == m);
+            }
+            offs[t] = sz;
+        }
+        if (bad >= 0) return b200_fail(CINTB200_EINVAL, "tuple %lld: shell id out of range", bad);
+        for (size_t t = 0; t < n; t++) {
+            const size_t sz = offs[t];
+            offs[t] = out_off ? out_off[t] : total;
+            total = std::max(total, offs[t] + sz);
+        }
+    }
+    // pass 2 (host threads): pair ids, strides, class keys
+#pragma omp parallel for schedule(static) if (n > 20000)
+    for (long long t = 0; t < (long long)n; t++) {
         const int *s = shls + t * ncenter;
-        for (int m = 0; m < ncenter; m++)
-            if (s[m] < 0 || s[m] >= c->nbas) return b200_fail(CINTB200_EINVAL, "tuple %zu: shell id %d out of range", t, s[m]);
         Task &T = tasks[t];
         if (ncenter == 2) {
             // (i|k): both sides are single-shell pseudo pairs (aj = al = 0, src/g2c2e.c:15-100); block (di,dk)
@@ -406,9 +432,7 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
             T.bra = (int)(npair2 + i); T.ket = (int)(npair2 + k);
             T.sa = 1; T.sb = 0; T.sc = di; T.sd = 0;
             if (cart_pos >= 0) T.flags = cart_pos == 0 ? 1 : 4;
-            offs[t] = out_off ? out_off[t] : total;
             T.off = (long long)offs[t];
-            total = std::max(total, offs[t] + (size_t)(di * dk));
             const PairHdr &hb = c->pairs[T.bra], &hk = c->pairs[T.ket];
             keys[t] = ClassKey{hb.la, hb.lb, hk.la, hk.lb, hb.nca * hb.ncb, hk.nca * hk.ncb};
             continue;
@@ -435,26 +459,35 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
             if (cart_pos == 2) T.flags = 4;
         }
         const PairHdr &hk = c->pairs[T.ket];
-        offs[t] = out_off ? out_off[t] : total;
         T.off = (long long)offs[t];
-        total = std::max(total, offs[t] + (size_t)(di * dj * dk * dl));
+        (void)dl;
         keys[t] = ClassKey{hb.la, hb.lb, hk.la, hk.lb, hb.nca * hb.ncb, hk.nca * hk.ncb};
     }
-    // class-sorted order
-    std::vector<size_t> order(n);
-    for (size_t t = 0; t < n; t++) order[t] = t;
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
-    std::vector<Task> sorted(n);
-    for (size_t t = 0; t < n; t++) sorted[t] = tasks[order[t]];
-
-    if (ctx_reserve(c, (void **)&c->d_tasks, &c->cap_tasks, sizeof(Task) * n, false)) return CINTB200_ENOMEM;
-    if (ctx_reserve(c, (void **)&c->d_nonzero, &c->cap_nonzero, sizeof(int) * n, false)) return CINTB200_ENOMEM;
     double *d_out = out;
     if (!on_device) {
         if (ctx_reserve(c, (void **)&c->d_out, &c->cap_out, sizeof(double) * total, false)) return CINTB200_ENOMEM;
         d_out = c->d_out;
     }
-    CUDA_OK(cudaMemcpyAsync(c->d_tasks, sorted.data(), sizeof(Task) * n, cudaMemcpyHostToDevice, c->stream));
+    // fast path: tuples whose classes have a specialised tile kernel run there (driver.cu:list_mode_run); spherical,
+    // plain Coulomb, packed output below 2^31 elements (the kernels keep row offsets in 32 bits)
+    std::vector<unsigned char> handled(n, 0);
+    static const bool list_fast = getenv("CINTB200_LIST_GENERIC") == nullptr;
+    if (list_fast && !cart && cart_pos < 0 && c->omega == 0 && !c->force_generic && total < ((size_t)1 << 31)) {
+        if (list_mode_run(c, tasks.data(), n, d_out, handled.data())) return CINTB200_ENODEV;
+    }
+    // the rest: class-sorted order for the generic kernel
+    const size_t n_all = n;
+    std::vector<size_t> order;
+    order.reserve(n);
+    for (size_t t = 0; t < n; t++) if (!handled[t]) order.push_back(t);
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+    n = order.size();
+    std::vector<Task> sorted(n);
+    for (size_t t = 0; t < n; t++) sorted[t] = tasks[order[t]];
+
+    if (ctx_reserve(c, (void **)&c->d_tasks, &c->cap_tasks, sizeof(Task) * std::max<size_t>(1, n), false)) return CINTB200_ENOMEM;
+    if (ctx_reserve(c, (void **)&c->d_nonzero, &c->cap_nonzero, sizeof(int) * std::max<size_t>(1, n), false)) return CINTB200_ENOMEM;
+    if (n) CUDA_OK(cudaMemcpyAsync(c->d_tasks, sorted.data(), sizeof(Task) * n, cudaMemcpyHostToDevice, c->stream));
 
     EngineParams P;
     P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef; P.rys_coef = c->d_rys; P.c2s = c->d_c2s;
@@ -489,14 +522,18 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         CUDA_OK(cudaMemcpyAsync(c->h_stage, d_out, sizeof(double) * total, cudaMemcpyDeviceToHost, c->stream));
     }
     std::vector<int> nz;
-    if (nonzero) {
+    if (nonzero && n) {
         nz.resize(n);
         CUDA_OK(cudaMemcpyAsync(nz.data(), c->d_nonzero, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
+    {
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) return b200_fail(CINTB200_ENODEV, "kernel execution failed: %s", cudaGetErrorString(le));
+    }
     if (!on_device) {
         if (out_off) {
-            for (size_t t = 0; t < n; t++) {
+            for (size_t t = 0; t < n_all; t++) {
                 size_t len = cintb200_block_size(c, kind, shls + t * ncenter, ncenter);
                 if (cart_pos >= 0) len = len / shell_dim(c->shells[shls[t * ncenter + cart_pos]], cart) * shell_dim(c->shells[shls[t * ncenter + cart_pos]], 1);
                 memcpy(out + offs[t], (double *)c->h_stage + offs[t], sizeof(double) * len);
@@ -505,8 +542,12 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
             memcpy(out, c->h_stage, sizeof(double) * total);
         }
     }
-    if (nonzero) for (size_t t = 0; t < n; t++) nonzero[order[t]] = nz[t];
-    return (long)n;
+    if (nonzero) {
+        // tile kernels screen at the pair level only: a block is non-empty when both pairs kept a primitive
+        for (size_t t = 0; t < n_all; t++) if (handled[t]) nonzero[t] = c->pairs[tasks[t].bra].npp > 0 && c->pairs[tasks[t].ket].npp > 0;
+        for (size_t t = 0; t < n; t++) nonzero[order[t]] = nz[t];
+    }
+    return (long)n_all;
 }
 
 extern "C" long cintb200_int2e_batch(cintb200_ctx *c, int kind, const int *shls, size_t n, const size_t *out_off,

@@ -42,6 +42,7 @@ struct CINTOpt {
     unsigned long long *d_counters = nullptr;
     long long launches = 0;
     struct JobPlan *plan = nullptr;     // cached whole-job plan (driver.cu)
+    struct ListTables *ltab = nullptr;  // per-class pair tables of the list-mode fast path (driver.cu:list_mode_run)
     CINTOpt *deriv = nullptr;           // first-derivative helper context: shells [nbas, 2 nbas) = l+1 with coefficients -2 a c,
                                         // [2 nbas, 3 nbas) = l-1 (engine.cu:ctx_deriv), built on first use
     int profile = 0;                    // record per-launch events in the whole-job driver
@@ -52,6 +53,9 @@ struct CINTOpt {
 
 struct JobPlan;
 void jobplan_free(JobPlan *p);
+struct ListTables;
+void listtables_free(ListTables *lt);
+int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled);
 int ctx_compute_schwarz(CINTOpt *c);
 int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
     double *s_u = s_rys + nint * rys_smem_stride(N) + (size_t)warp * P.umax * USTR;        // this WARP's ket primitives [nppu <= umax]
     double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
-    const long long total = (long long)P.gx * P.NU;
+    const long long total = P.items ? P.nitems : (long long)P.gx * P.NU;
     int cur_by = -1, t_lo = P.t_begin;
     PairHdr hu;
     __syncthreads();                    // table staged; warps are independent from here on (see kern_reg.cuh)
@@ -90,8 +90,14 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
     if (item0 >= total) break;
     const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
     for (long long item = item0; item < item1; item++) {
-    const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
-    const int u = P.u_first + P.u_step * by;
+    int by, bx = 0, u, t_hi = P.t_end, t0l = 0;
+    if (P.items) {                      // list mode, see kern_reg.cuh
+        const int4 it = P.items[item];
+        by = u = it.x; t0l = it.y; t_hi = it.y + it.z;
+    } else {
+        by = (int)(item / P.gx); bx = (int)(item - (long long)by * P.gx);
+        u = P.u_first + P.u_step * by;
+    }
     if (by != cur_by) {
         __syncwarp();
         hu = P.pairs[P.upair[u]];
@@ -113,11 +119,12 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             t_lo = lo;
         }
     }
-    const int t0 = t_lo + bx * QPW;
-    if (t0 >= P.t_end) continue;         // warp-uniform
+    const int t0 = P.items ? t0l : t_lo + bx * QPW;
+    if (t0 >= t_hi) continue;            // warp-uniform
     const int t = t0 + (q - warp * QPW);
-    const bool active = t < P.t_end;
-    const int tt = active ? t : P.t_end - 1;
+    const bool active = t < t_hi;
+    const int to = active ? t : t_hi - 1;                   // T occurrence / row of the pair table, see kern_reg.cuh
+    const int tt = P.tsel ? P.tsel[to] : to;
     // Schwarz: if every quartet of this warp is bounded below the threshold, skip the primitive loops -- the
     // accumulators stay zero and the epilogue zero-fills the blocks (what the reference does for empty blocks)
     const bool negligible = P.schwarz_thr > 0 && P.tq[tt] * P.uq[u] < P.schwarz_thr;
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
 
     // --- epilogue ---
     // strides: (a,b) = register side, (c,d) = lane side, mapped onto rows (T) / columns (U) of the tile
-    const int tsa = P.tstride[tt], tsb = P.tstride[NT + tt];
+    const int tsa = P.tstride[to], tsb = P.tstride[P.NTs + to];
     const long long usc = (long long)P.ustride[u] * P.ld, usd = (long long)P.ustride[P.NU_all + u] * P.ld;
     const long long s_a = REG_IS_T ? tsa : usc, s_b = REG_IS_T ? tsb : usd;
     const long long s_c = REG_IS_T ? usc : tsa, s_d = REG_IS_T ? usd : tsb;
@@ -300,7 +307,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
     double abR[3], abL[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) { abR[d] = REG_IS_T ? abT[d] : abU[d]; abL[d] = REG_IS_T ? abU[d] : abT[d]; }
-    double *obase = P.out + (P.trow[tt] - P.row0) + P.ucol[u] * P.ld;
+    double *obase = P.out + (P.trow[to] - P.row0) + P.ucol[u] * P.ld;
 #pragma unroll 1
     for (int comb = 0; comb < NCOMB; comb++) {
         const int cl = comb / NCR, cr = comb - cl * NCR;

@@ -303,7 +303,7 @@ eri_reg_kernel(const TileParams P)
                    + (reg_acc_in_smem(NCT, NCT * NCU * NEF) ? (size_t)NCT * NCU * NEF * REG_THREADS : 0) + (size_t)warp * reg_stage_doubles(RB);
     int2 *s_tab = (int2 *)(s_st + 32 * RB);                     // [32*RB] {row offset in the tile or -1, index into s_st}
     int2 *s_meta = s_tab + 32 * RB;                             // [32] {row base or -1, +di if a is the first index else -di}
-    const long long total = (long long)P.gx * P.NU;
+    const long long total = P.items ? P.nitems : (long long)P.gx * P.NU;
     int cur_by = -1, t_lo = P.t_begin;
     PairHdr hu;
     __syncthreads();                    // table staged; from here on the warps run independently (no block barriers)
@@ -316,8 +316,14 @@ eri_reg_kernel(const TileParams P)
     if (item0 >= total) break;
     const long long item1 = (item0 + P.batch < total) ? item0 + P.batch : total;
     for (long long item = item0; item < item1; item++) {
-    const int by = (int)(item / P.gx), bx = (int)(item - (long long)by * P.gx);
-    const int u = P.u_first + P.u_step * by;
+    int by, bx = 0, u, t_hi = P.t_end, t0l = 0;
+    if (P.items) {                      // list mode: explicit items, consecutive items of a ket share its staged primitives
+        const int4 it = P.items[item];
+        by = u = it.x; t0l = it.y; t_hi = it.y + it.z;
+    } else {
+        by = (int)(item / P.gx); bx = (int)(item - (long long)by * P.gx);
+        u = P.u_first + P.u_step * by;
+    }
     if (by != cur_by) {
         __syncwarp();                   // previous ket's primitives no longer in use by this warp
         hu = P.pairs[P.upair[u]];
@@ -351,11 +357,12 @@ eri_reg_kernel(const TileParams P)
             t_lo = lo;
         }
     }
-    const int t0 = t_lo + bx * 32;
-    if (t0 >= P.t_end) continue;        // warp-uniform
+    const int t0 = P.items ? t0l : t_lo + bx * 32;
+    if (t0 >= t_hi) continue;           // warp-uniform
     const int t = t0 + lane;
-    const bool active = t < P.t_end;
-    const int tt = active ? t : P.t_end - 1;
+    const bool active = t < t_hi;
+    const int to = active ? t : t_hi - 1;                   // my T occurrence (output placement)
+    const int tt = P.tsel ? P.tsel[to] : to;                // its row in the class' pair table
     // warp-uniform primitive loop bound: the largest count among the warp's T pairs (shorter pairs are padded with
     // zero-weight primitives; neighbouring list entries have similar counts by construction)
     // Schwarz: if every quartet of this warp is bounded below the threshold, skip the primitive loops -- the
@@ -503,9 +510,9 @@ eri_reg_kernel(const TileParams P)
     // (measured: every single-primitive class saturated at ~900 GB/s of 8-byte sector writes).  Per column the 32 threads
     // stage their RB row values, then the warp writes the 32*RB values in tile order (runs of >= DA or DB doubles,
     // the whole RB when the pair is uncontracted; neighbouring quartets own neighbouring row blocks by construction).
-    const int sa = P.tstride[tt], sb = P.tstride[NT + tt];
+    const int sa = P.tstride[to], sb = P.tstride[P.NTs + to];
     const long long sc = (long long)P.ustride[u] * P.ld, sd = (long long)P.ustride[P.NU_all + u] * P.ld;
-    const int rowbase0 = (int)(P.trow[tt] - P.row0);
+    const int rowbase0 = (int)(P.trow[to] - P.row0);
     double *obase = P.out + P.ucol[u] * P.ld;
     const int nca_t = P.nca_t, nca_u = P.nca_u;
     // Fast flush (uncontracted T pairs whose 32 row blocks are adjacent -- the normal case thanks to the class-contiguous

@@ -11,6 +11,7 @@
 // src/optimizer.c:288-342); screening uses the same cce estimate.
 #pragma once
 #include <stdint.h>
+#include <cuda_runtime.h>
 #include <stddef.h>
 
 #define B200_LMAX 6            // per-shell angular momentum limit of this build
@@ -77,6 +78,12 @@ struct TileParams {
     const int *tnpp;           // [NT] primitive pairs per T pair (>= 1); lists are sorted by descending count inside a chunk
     int NT, Q;                 // pairs in class, primitives per pair (padded)
     int t_begin, t_end;        // range of this chunk inside the class list
+    // list mode (engine.cu:run_batch fast path): explicit work items {ket index u, first T occurrence, valid count, -} and an
+    // indirection from T occurrences to the rows of the class' pair table; NULL / 0 in tile mode
+    const int4 *items;
+    long long nitems;
+    const int *tsel;           // [occurrences] row of tprim / tgeom / tnpp used by occurrence t (trow / tstride are per occurrence)
+    int NTs;                   // length of one row of tstride (= NT in tile mode)
     unsigned int *counter;     // per-launch work-item counter (zeroed before every job)
     int batch;                 // work items fetched per atomic (sized on the host so that every launch has >= ~8 batches per SM)
     int gx;                    // work items per ket = ceil((t_end - t_begin) / pairs per block)

@@ -16,3 +16,21 @@ for nq in (20000, 200000, 1000000):
         ctx.int2e_batch(q, device_ptr=buf.data_ptr())
         torch.cuda.synchronize(); dt = time.time() - t0
     print("list-mode batch: %d quartets, %.3g integrals in %.1f ms -> %.3g quartets/s, %.3g integrals/s" % (nq, tot, dt * 1e3, nq / dt, tot / dt))
+# structured list: every bra of a set with every ket of a set (what screened direct-SCF lists look like), same API
+import ctypes
+nb = len(bas)
+pairs = np.array([(i, j) for i in range(nb) for j in range(i + 1)], np.int32)
+for nbra, nket in ((2000, 500), (20000, 100)):
+    bra = pairs[rng.choice(len(pairs), nbra, replace=False)]
+    ket = pairs[rng.choice(len(pairs), nket, replace=False)]
+    q = np.concatenate([np.repeat(bra, nket, axis=0), np.tile(ket, (nbra, 1))], axis=1).astype(np.int32)
+    perm = rng.permutation(len(q))
+    q = np.ascontiguousarray(q[perm])                      # order of the list does not matter
+    tot = int(np.prod(dim[q], axis=1).sum())
+    buf = torch.empty(tot, dtype=torch.float64, device="cuda")
+    for it in range(2):
+        torch.cuda.synchronize(); t0 = time.time()
+        ctx.int2e_batch(q, device_ptr=buf.data_ptr())
+        torch.cuda.synchronize(); dt = time.time() - t0
+    print("structured list %d bras x %d kets: %d quartets, %.3g integrals in %.1f ms -> %.3g quartets/s, %.3g integrals/s" % (
+        nbra, nket, len(q), tot, dt * 1e3, len(q) / dt, tot / dt))

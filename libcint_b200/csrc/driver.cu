@@ -713,7 +713,25 @@ static int listtables_build(CINTOpt *c)
         lt->cls[ci].ids.push_back((int)p);
         lt->cls[ci].Q = std::max(lt->cls[ci].Q, h.npp);
     }
-    for (ListClass &lc : lt->cls) {
+    const int ncls = (int)lt->cls.size();
+    lt->choice.resize((size_t)ncls * ncls);
+    for (int cb = 0; cb < ncls; cb++)
+        for (int ck = 0; ck < ncls; ck++) {
+            const ListClass &B = lt->cls[cb], &K = lt->cls[ck];
+            ListChoice &ch = lt->choice[(size_t)cb * ncls + ck];
+            memset(&ch, 0, sizeof ch);
+            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb);
+            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci); ch.coop = ch.fn != nullptr; }
+        }
+    c->ltab = lt;
+    return 0;
+}
+
+// structure-of-arrays primitive table of one bra class, uploaded the first time a list uses the class
+static int listclass_upload(CINTOpt *c, ListClass &lc)
+{
+    if (lc.d_tprim) return 0;
+    {
         const size_t NT = lc.ids.size();
         const int nct = lc.nca * lc.ncb, Q = lc.Q;
         std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
@@ -738,19 +756,8 @@ static int listtables_build(CINTOpt *c)
             }
             nppc[n] = std::max(h.npp, 1);
         }
-        if (upload(&lc.d_tprim, tprim) || upload(&lc.d_tgeom, tgeom) || upload(&lc.d_tnpp, nppc)) { listtables_free(lt); return CINTB200_ENOMEM; }
+        if (upload(&lc.d_tprim, tprim) || upload(&lc.d_tgeom, tgeom) || upload(&lc.d_tnpp, nppc)) return CINTB200_ENOMEM;
     }
-    const int ncls = (int)lt->cls.size();
-    lt->choice.resize((size_t)ncls * ncls);
-    for (int cb = 0; cb < ncls; cb++)
-        for (int ck = 0; ck < ncls; ck++) {
-            const ListClass &B = lt->cls[cb], &K = lt->cls[ck];
-            ListChoice &ch = lt->choice[(size_t)cb * ncls + ck];
-            memset(&ch, 0, sizeof ch);
-            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb);
-            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci); ch.coop = ch.fn != nullptr; }
-        }
-    c->ltab = lt;
     return 0;
 }
 
@@ -864,6 +871,7 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
     for (size_t g = 0; g < groups.size(); g++) {
         const Group &G = groups[g];
         const Choice &ch = choice(G.key);
+        if (listclass_upload(c, lt->cls[G.key / ncls])) return CINTB200_ENOMEM;
         const ListClass &B = lt->cls[G.key / ncls], &K = lt->cls[G.key % ncls];
         const int nroots = (B.la + B.lb + K.la + K.lb) / 2 + 1;
         TileParams P;

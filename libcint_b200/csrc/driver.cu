@@ -468,11 +468,13 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 L.ntasks = (long long)(t_end - t_begin) * nu_mine;      // generic: rectangle, invalid quartets skipped in-kernel
                 L.key[0] = T.la; L.key[1] = T.lb; L.key[2] = U.la; L.key[3] = U.lb; L.key[4] = T.nca * T.ncb; L.key[5] = U.nca * U.ncb;
                 L.quartets = q_here; L.prim = prim_here; L.flops = prim_here * fp + q_here * fq; L.integrals = q_here * blk; L.part = part;
-                // the specialised kernels implement the plain Coulomb operator; range-separated runs use the generic kernel
-                const bool generic_only = c->force_generic || c->omega != 0;
-                L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb);
+                // range-separated operators run on the RS instantiations of the same kernels (TileParams::rs_*)
+                const bool generic_only = c->force_generic;
+                const int rs = c->omega != 0;
+                P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega > 0 ? 1.0 : -1.0; P.rs_pass0 = c->omega > 0 ? 1 : 0;
+                L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, rs);
                 if (!L.fn && !generic_only) {
-                    L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci);
+                    L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci, rs);
                     L.coop = L.fn != nullptr;
                 }
                 if (L.fn && !L.coop && REG_FAST_RYS && L.nroots <= RYS_FNMAX && L.nroots <= REG_FAST_NMAX)
@@ -720,8 +722,9 @@ static int listtables_build(CINTOpt *c)
             const ListClass &B = lt->cls[cb], &K = lt->cls[ck];
             ListChoice &ch = lt->choice[(size_t)cb * ncls + ck];
             memset(&ch, 0, sizeof ch);
-            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb);
-            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci); ch.coop = ch.fn != nullptr; }
+            const int rs = c->omega != 0;
+            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, rs);
+            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci, rs); ch.coop = ch.fn != nullptr; }
         }
     c->ltab = lt;
     return 0;
@@ -891,6 +894,7 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
         P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
         P.rys = (!ch.coop && REG_FAST_RYS && nroots <= RYS_FNMAX && nroots <= REG_FAST_NMAX) ? c->d_rys_fast + rys_fast_off(nroots)
                                                                                           : c->d_rys + rys_tab_off(nroots);
+        P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega > 0 ? 1.0 : -1.0; P.rs_pass0 = c->omega > 0 ? 1 : 0;
         P.items = (const int4 *)(d + o_items) + G.i0;
         P.nitems = (long long)(G.i1 - G.i0);
         P.gx = 1;

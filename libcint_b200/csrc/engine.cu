@@ -472,7 +472,7 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
     // plain Coulomb, packed output below 2^31 elements (the kernels keep row offsets in 32 bits)
     std::vector<unsigned char> handled(n, 0);
     static const bool list_fast = getenv("CINTB200_LIST_GENERIC") == nullptr;
-    if (list_fast && n >= 32 && !cart && cart_pos < 0 && c->omega == 0 && !c->force_generic && total < ((size_t)1 << 31)) {   // single calls: generic kernel (lower latency)
+    if (list_fast && n >= 32 && !cart && cart_pos < 0 && !c->force_generic && total < ((size_t)1 << 31)) {   // single calls: generic kernel (lower latency)
         if (list_mode_run(c, tasks.data(), n, d_out, handled.data())) return CINTB200_ENODEV;
     }
     // the rest: class-sorted order for the generic kernel

@@ -39,7 +39,7 @@ __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, in
     return (a > b ? a : b) | 1;
 }
 
-template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T>
+template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T, bool RS = false>
 __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
@@ -188,17 +188,33 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             }
             const double a0 = aT * aU * inv;
             const double x = a0 * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
-            const double fac = common * kT * su[8] * iaT * iaU * rs;
+            const double fac0 = common * kT * su[8] * iaT * iaU * rs;
+            // one contraction combination: the coefficient is folded into the z column and the products are added
+            // straight into the accumulators (no per-primitive val[] block: NE registers and NE FMAs less)
+            double val[NCOMB == 1 ? 1 : NE];
+            if constexpr (NCOMB > 1) {
+#pragma unroll
+                for (int e = 0; e < NE; e++) val[e] = 0.0;
+            }
+            const double cc1 = (NCOMB == 1) ? ccT[0] * su[9] : 1.0;
+            // range-separated Coulomb: pass 1 = attenuated rule (theta x, theta t^2, weight sign sqrt(theta)), pass 0 = full
+            // Coulomb (skipped for the long-range operator); the plain operator runs the loop body once
+            double th_ = 1.0, sq_ = 1.0;
+            if constexpr (RS) { th_ = P.rs_w2 / (P.rs_w2 + a0); sq_ = sqrt(th_) * P.rs_sign; }
+#pragma unroll 1
+            for (int pass = RS ? P.rs_pass0 : 1; pass < 2; pass++) {
+            const bool att = RS && pass == 1;
+            const double xq = att ? x * th_ : x, fac = att ? fac0 * sq_ : fac0, thp = att ? th_ : 1.0;
             // --- roots: one polynomial per lane ---
             for (int p = lane; p < 2 * N; p += FS) {
                 double v;
-                if (x >= 35.0 + 5.0 * N) {
+                if (xq >= 35.0 + 5.0 * N) {
                     const int k = N * (N - 1) / 2 + (p >> 1);
-                    v = (p & 1) ? c_rys_lx_v[k] * rsqrt(x) : c_rys_lx_r[k] / x;
+                    v = (p & 1) ? c_rys_lx_v[k] * rsqrt(xq) : c_rys_lx_r[k] / xq;
                 } else {
                     int idx;
                     double y;
-                    rys_locate(x, idx, y);
+                    rys_locate(xq, idx, y);
                     asm("" : "+r"(idx));        // opaque index: no 24-bit overflow of the folded grid offset in the LDS immediates
                     const double *cf = s_rys + idx * rys_smem_stride(N) + p;
                     // Estrin (depth 4) instead of Horner (depth 9): this phase is a dependent chain on a few busy lanes
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             const double rho_l = aL * inv, rho_r = aR * inv;
             for (int task = lane; task < 3 * N; task += FS) {
                 const int r = task / 3, d = task - 3 * r;
-                const double s = s_rw[2 * r];
+                const double s = RS ? s_rw[2 * r] * thp : s_rw[2 * r];
                 const double sl = s * rho_l, sr = s * rho_r;
                 const double b00 = 0.5 * s * inv;
                 const double b10 = (0.5 - 0.5 * sl) * iaR;
@@ -252,14 +268,6 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             }
             __syncwarp();
             // --- quadrature sum for my f ---
-            // one contraction combination: the coefficient is folded into the z column and the products are added
-            // straight into the accumulators (no per-primitive val[] block: NE registers and NE FMAs less)
-            double val[NCOMB == 1 ? 1 : NE];
-            if constexpr (NCOMB > 1) {
-#pragma unroll
-                for (int e = 0; e < NE; e++) val[e] = 0.0;
-            }
-            const double cc1 = (NCOMB == 1) ? ccT[0] * su[9] : 1.0;
             static_for<N>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
                 const double *gx = s_q + (size_t)(3 * r) * GT + fx;
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
                     else val[e] = fma(cx[ex] * cy[ey], cz[ez], val[e]);
                 });
             });
+            }       // passes
             if constexpr (NCOMB == 1) {
             } else {
                 static_for<NCL>([&](auto CL) {

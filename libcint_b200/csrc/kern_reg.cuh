@@ -267,7 +267,7 @@ template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart
 // and lets three blocks share an SM instead of two.
 __host__ __device__ constexpr bool reg_acc_in_smem(int nct, int nacc) { return nct > 1 && nacc <= REG_ACC_SMEM_MAX; }
 
-template <int LA, int LB, int LC, int LD, int NCT, int NCU>
+template <int LA, int LB, int LC, int LD, int NCT, int NCU, bool RS = false>
 __global__ void __launch_bounds__(REG_THREADS, reg_acc_in_smem(NCT, NCT * NCU * cx_nrange(LA, LA + LB) * cx_nrange(LC, LC + LD)) ? 3 : REG_MIN_BLOCKS)
 eri_reg_kernel(const TileParams P)
 {
@@ -426,18 +426,20 @@ eri_reg_kernel(const TileParams P)
             const double a0 = aT * aU * inv;
             const double x = a0 * (pq[0] * pq[0] + pq[1] * pq[1] + pq[2] * pq[2]);
             const double fac = common * kT * su[8] * iaT * iaU * rs;
-            double t2[N], w[N];
-            if constexpr (FASTRYS) rys_roots_smem_fast<N>(s_rys, x, t2, w);
-            else rys_roots_smem<N>(s_rys, nint, x, t2, w);
             const double rho_u = aU * inv, rho_t = aT * inv;
             double val[(NCU == 1) ? 1 : NEF];
             if constexpr (NCU > 1) {
 #pragma unroll
                 for (int i = 0; i < NEF; i++) val[i] = 0.0;
             }
+            // one quadrature rule: roots at xx, weights scaled by ff, t^2 scaled by thp (1 unless range-separated)
+            auto quad = [&](const double xx, const double ff, const double thp) {
+            double t2[N], w[N];
+            if constexpr (FASTRYS) rys_roots_smem_fast<N>(s_rys, xx, t2, w);
+            else rys_roots_smem<N>(s_rys, nint, xx, t2, w);
             static_for<N>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
-                const double s = t2[r];
+                const double s = RS ? t2[r] * thp : t2[r];
                 const double su_ = s * rho_u, st_ = s * rho_t;
                 const double b00 = 0.5 * s * inv;
                 const double b10 = (0.5 - 0.5 * su_) * iaT;
@@ -447,7 +449,7 @@ eri_reg_kernel(const TileParams P)
                     constexpr int d = decltype(DDm)::value;
                     const double c00 = pa[d] - su_ * pq[d];
                     const double c0p = qc[d] + st_ * pq[d];
-                    g[d][0][0] = (d == 2) ? w[r] * fac : 1.0;
+                    g[d][0][0] = (d == 2) ? w[r] * ff : 1.0;
                     if constexpr (NMAX > 0) g[d][1][0] = c00 * g[d][0][0];
                     static_for<(NMAX > 1 ? NMAX - 1 : 0)>([&](auto NN) {
                         constexpr int n = decltype(NN)::value + 1;
@@ -482,6 +484,16 @@ eri_reg_kernel(const TileParams P)
                     });
                 });
             });
+            };      // quad
+            if constexpr (RS) {
+                const double th = P.rs_w2 / (P.rs_w2 + a0);
+                const double sq = sqrt(th) * P.rs_sign;
+#pragma unroll 1
+                for (int pass = P.rs_pass0; pass < 2; pass++)
+                    quad(pass ? x * th : x, pass ? fac * sq : fac, pass ? th : 1.0);
+            } else {
+                quad(x, fac, 1.0);
+            }
             if constexpr (NCU > 1) {
 #pragma unroll
                 for (int c = 0; c < NCU; c++) {

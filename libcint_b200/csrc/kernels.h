@@ -30,7 +30,7 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
 
 // register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
 typedef void (*RegKernelFn)(const TileParams);
-RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu);
+RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu, int rs = 0);     // rs: range-separated variant
 int rys_tab_nint(int nroots);
 int rys_fast_nint(int nroots);
 int rys_fast_off(int nroots);
@@ -38,5 +38,5 @@ int reg_kernel_launch(RegKernelFn fn, int nroots, int ncu, const TileParams &P, 
 
 // cooperative kernels (kern_coop_inst*.cu): FS lanes per quartet
 struct CoopInfo { int fs, xsz, nroots; };
-RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info);
+RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info, int rs = 0);
 int coop_kernel_launch(RegKernelFn fn, const CoopInfo &info, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);

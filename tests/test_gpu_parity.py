@@ -341,7 +341,7 @@ def test_range_separated_coulomb():
                 scale = max(1.0, np.abs(full[blk]).max())
                 assert np.abs(lr[blk] - want_lr[n]).max() <= 1e-12 * scale, (name, omega, "lr", tuple(q[n]))
                 assert np.abs(sr[blk] - want_sr[n]).max() <= 1e-12 * scale, (name, omega, "sr", tuple(q[n]))
-    # whole-job driver with omega != 0 goes through the generic kernel in tile mode
+    # whole-job driver with omega != 0: RS instantiations of the tile kernels
     atm, bas, env = cb.load_fixture("c2h6_631g")
     env = env.copy()
     env[8] = -0.5

@@ -9,9 +9,14 @@ import libcint_b200 as cb
 pytestmark = pytest.mark.gpu
 
 
-def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 30, max_quartets=None, tol=1e-12):
+def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 30, max_quartets=None, tol=1e-12, omega=None):
     which, _ = ou.best()
     atm, bas, env = cb.load_fixture(name)
+    if omega is not None:
+        env = env.copy()
+        env[8] = omega                      # PTR_RANGE_OMEGA: > 0 long range (erf), < 0 short range (erfc)
+        if omega < 0:
+            which = "port"                  # the port evaluates erfc as full - erf in extended precision roots
     nbas = len(bas)
     dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
     total_q = 0
@@ -74,6 +79,14 @@ def test_tiles_two_and_three_ranks():
 def test_tiles_c2h6_ccpvtz_mixed_kernels():
     # f shells: the s/p/d classes use the specialised kernels, everything with an f shell the generic kernel
     check_job("c2h6_ccpvtz", max_quartets=6000)
+
+
+def test_tiles_range_separated_specialised_kernels():
+    # config 5 through the whole-job driver: the RS instantiations of the register / cooperative kernels (long range:
+    # one attenuated rule; short range: full + negated attenuated rule), every block against the oracle
+    check_job("c2h6_ccpvdz", omega=0.3, max_quartets=40000)
+    check_job("c2h6_ccpvdz", omega=-0.3, max_quartets=40000, tol=1e-11)
+    check_job("c2h6_ccpvtz", omega=0.3, max_quartets=5000)
 
 
 def test_tiles_multi_chunk():

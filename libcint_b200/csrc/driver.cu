@@ -471,7 +471,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 // range-separated operators run on the RS instantiations of the same kernels (TileParams::rs_*)
                 const bool generic_only = c->force_generic;
                 const int rs = c->omega != 0;
-                P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega > 0 ? 1.0 : -1.0; P.rs_pass0 = c->omega > 0 ? 1 : 0;
+                P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega;      /* sign * |omega| */ P.rs_pass0 = c->omega > 0 ? 1 : 0;
                 L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, rs);
                 if (!L.fn && !generic_only) {
                     L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci, rs);
@@ -894,7 +894,7 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
         P.pairs = c->d_pairs; P.prims = c->d_prims; P.pcoef = c->d_pcoef;
         P.rys = (!ch.coop && REG_FAST_RYS && nroots <= RYS_FNMAX && nroots <= REG_FAST_NMAX) ? c->d_rys_fast + rys_fast_off(nroots)
                                                                                           : c->d_rys + rys_tab_off(nroots);
-        P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega > 0 ? 1.0 : -1.0; P.rs_pass0 = c->omega > 0 ? 1 : 0;
+        P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega;      /* sign * |omega| */ P.rs_pass0 = c->omega > 0 ? 1 : 0;
         P.items = (const int4 *)(d + o_items) + G.i0;
         P.nitems = (long long)(G.i1 - G.i0);
         P.gx = 1;

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             // range-separated Coulomb: pass 1 = attenuated rule (theta x, theta t^2, weight sign sqrt(theta)), pass 0 = full
             // Coulomb (skipped for the long-range operator); the plain operator runs the loop body once
             double th_ = 1.0, sq_ = 1.0;
-            if constexpr (RS) { th_ = P.rs_w2 / (P.rs_w2 + a0); sq_ = sqrt(th_) * P.rs_sign; }
+            if constexpr (RS) { const double rr = fast_rsqrt(P.rs_w2 + a0); th_ = P.rs_w2 * rr * rr; sq_ = P.rs_sign * rr; }
 #pragma unroll 1
             for (int pass = RS ? P.rs_pass0 : 1; pass < 2; pass++) {
             const bool att = RS && pass == 1;

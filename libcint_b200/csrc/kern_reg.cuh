@@ -486,8 +486,9 @@ eri_reg_kernel(const TileParams P)
             });
             };      // quad
             if constexpr (RS) {
-                const double th = P.rs_w2 / (P.rs_w2 + a0);
-                const double sq = sqrt(th) * P.rs_sign;
+                const double rr = fast_rsqrt(P.rs_w2 + a0);      // theta = omega^2 / (omega^2 + a0), src/g2e.c:4445
+                const double th = P.rs_w2 * rr * rr;
+                const double sq = P.rs_sign * rr;                // sign * |omega| * rr = sign * sqrt(theta)
 #pragma unroll 1
                 for (int pass = P.rs_pass0; pass < 2; pass++)
                     quad(pass ? x * th : x, pass ? fac * sq : fac, pass ? th : 1.0);

@@ -87,7 +87,7 @@ struct TileParams {
     // range-separated Coulomb (kernels instantiated with RS = true; env[PTR_RANGE_OMEGA] != 0, src/g2e.c:4443-4492):
     // pass 1 = erf-attenuated rule at theta x with t^2 -> theta t^2 and weight rs_sign sqrt(theta); pass 0 = full Coulomb.
     // long range (omega > 0): pass 1 only, sign +1;  short range (omega < 0): both passes, sign -1 (erfc = 1 - erf)
-    double rs_w2, rs_sign;
+    double rs_w2, rs_sign;     // omega^2 and sign * |omega| (theta = w2 r^2, sign sqrt(theta) = rs_sign r with r = rsqrt(w2 + a0))
     int rs_pass0;
     unsigned int *counter;     // per-launch work-item counter (zeroed before every job)
     int batch;                 // work items fetched per atomic (sized on the host so that every launch has >= ~8 batches per SM)

@@ -582,7 +582,21 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
             const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
             const size_t bytes = sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->chunk_cols[ch];
             CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_done[b], 0));
-            CU_OK(cudaMemcpyAsync(host_sink, plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
+            static const int d2h_split = getenv("CINTB200_D2H_SPLIT") ? atoi(getenv("CINTB200_D2H_SPLIT")) : 1;
+            if (d2h_split > 1 && bytes > ((size_t)64 << 20)) {
+                // experiment knob: the tile goes out as `d2h_split` copies on side streams (several DMA engines in flight)
+                const size_t part = (bytes / d2h_split + 255) & ~(size_t)255;
+                const int ns = std::min(d2h_split, (int)JobPlan::NS);
+                for (int k = 0; k < ns; k++) {
+                    const size_t o = part * k, len = (k == ns - 1) ? bytes - o : part;
+                    CU_OK(cudaStreamWaitEvent(plan->streams[k], plan->ev_done[b], 0));
+                    CU_OK(cudaMemcpyAsync((char *)host_sink + o, (char *)plan->d_out[b] + o, len, cudaMemcpyDeviceToHost, plan->streams[k]));
+                    CU_OK(cudaEventRecord(plan->ev_join[k], plan->streams[k]));
+                    CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_join[k], 0));
+                }
+            } else {
+                CU_OK(cudaMemcpyAsync(host_sink, plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
+            }
             CU_OK(cudaEventRecord(plan->ev_copied[b], plan->copy_stream));
             d2h += (double)bytes;
         }

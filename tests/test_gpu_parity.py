@@ -167,6 +167,26 @@ def test_df_gradient_integrals():
         assert_blocks_close(split(v, o, s), ou.eval_many(which, name, t, atm, bas, env), t, tol=1e-11 if which == "ref" else TOL, what="df " + name)
 
 
+def test_golden_derivatives_and_metric():
+    # committed golden vectors of the new integral types (tests/golden/derivs.npz) through the batch entry points
+    g = np.load(os.path.join(GOLD, "derivs.npz"))
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    ctx = cb.Context(atm, bas, env)
+    calls = {"int2c2e_sph": (ctx.int2c2e_batch, cb.SPH), "int2c2e_ip1_sph": (ctx.int2c2e_ip1_batch, cb.SPH),
+             "int2c2e_ip2_sph": (ctx.int2c2e_ip2_batch, cb.SPH), "int3c2e_ip1_sph": (ctx.int3c2e_ip1_batch, cb.SPH),
+             "int3c2e_ip2_sph": (ctx.int3c2e_ip2_batch, cb.SPH), "int2e_ip1_sph": (ctx.int2e_ip1_batch, cb.SPH),
+             "int2e_ip1_cart": (ctx.int2e_ip1_batch, cb.CART)}
+    for name, (fn, kind) in calls.items():
+        q, f = g["q_" + name], g["f_" + name]
+        v, o, s, _ = fn(q, kind=kind)
+        for n in range(len(q)):
+            assert np.allclose(fp(v[o[n]:o[n] + s[n]]), f[n], rtol=1e-11, atol=1e-11), (name, tuple(q[n]))
+    for n in range(int(g["nfull"])):
+        name, sh, want = str(g["full%d_name" % n]), g["full%d_shls" % n], g["full%d_vals" % n]
+        v, o, s, _ = calls[name][0](sh.reshape(1, -1), kind=calls[name][1])
+        assert np.abs(v - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (name, tuple(sh))
+
+
 def test_ip1_on_c60_sample():
     # gradient integrals on the benchmark molecule: contracted s shells, p/d shells, distant centres
     which, _ = ou.best()

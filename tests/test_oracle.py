@@ -130,6 +130,22 @@ def test_port_vs_golden_testbasis():
         assert np.allclose(fp(v), fr, rtol=1e-11, atol=1e-11), ("lr", s)
 
 
+def test_port_vs_golden_derivatives_and_metric():
+    # tests/golden/derivs.npz (tools/make_golden.py derivs, from the compiled reference): 2-centre metric and first derivatives
+    g = np.load(os.path.join(GOLD, "derivs.npz"))
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    for name in ("int2c2e_sph", "int2c2e_ip1_sph", "int2c2e_ip2_sph", "int3c2e_ip1_sph", "int3c2e_ip2_sph", "int2e_ip1_sph", "int2e_ip1_cart"):
+        q, f = g["q_" + name], g["f_" + name]
+        step = 4 if name.startswith("int2e") or name.startswith("int3c2e") else 1
+        for s, fr in zip(q[::step], f[::step]):
+            v, _ = ou.eval_tuple("port", name, s, atm, bas, env)
+            assert np.allclose(fp(v), fr, rtol=1e-11, atol=1e-11), (name, s)
+    for n in range(int(g["nfull"])):
+        name, sh, want = str(g["full%d_name" % n]), g["full%d_shls" % n], g["full%d_vals" % n]
+        v, _ = ou.eval_tuple("port", name, sh, atm, bas, env)
+        assert np.abs(v - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), (name, sh)
+
+
 def test_port_vs_golden_c60():
     g = np.load(os.path.join(GOLD, "c60_blocks.npz"))
     atm, bas, env = load_fixture("c60_ccpvdz")

@@ -6,6 +6,8 @@
   testbasis.npz      per-quartet checksums (sum|v|, sum v*cos(n)) of int2e_sph over ALL 8^4 quartets of the
                      reference test basis (testsuite/test_cint.py:46-137), int3c2e_sph over all 8^3 triples,
                      int2e_cart for a subset, and the LR (omega=0.5) variant
+  derivs.npz         checksums of int2c2e_sph, int2c2e_ip1/ip2_sph, int3c2e_ip1/ip2_sph, int2e_ip1_sph/_cart over the test basis and
+                     a few full blocks
   rys_mpmath.npz     Rys roots/weights from the reference's 100-digit mpmath implementation
                      (scripts/rys_roots.py:197) for nroots 1..11 on a grid of x
 """
@@ -57,6 +59,26 @@ def testbasis():
                         qlr=np.array(ql, np.int32), flr=fl, omega_lr=0.5)
 
 
+def derivs():
+    """derivs.npz: per-tuple checksums of the 2-centre metric and of the first-derivative integrals over the reference
+    test basis (all 8^2 / 8^3 tuples, every 9th of the 8^4 quartets) + full blocks of a few tuples"""
+    import itertools
+    atm, bas, env = reference_test_basis(with_fit_shells=True)
+    out = {}
+    for name, nc, step in (("int2c2e_sph", 2, 1), ("int2c2e_ip1_sph", 2, 1), ("int2c2e_ip2_sph", 2, 1), ("int3c2e_ip1_sph", 3, 1),
+                           ("int3c2e_ip2_sph", 3, 1), ("int2e_ip1_sph", 4, 9), ("int2e_ip1_cart", 4, 31)):
+        t = list(itertools.product(range(8), repeat=nc))[::step]
+        out["q_" + name] = np.array(t, np.int32)
+        out["f_" + name] = np.array([fp(v) for v in ou.eval_many("ref", name, t, atm, bas, env)])
+    full = [("int2e_ip1_sph", (1, 2, 5, 3)), ("int2e_ip1_sph", (3, 0, 2, 7)), ("int3c2e_ip2_sph", (2, 5, 3)), ("int2c2e_sph", (3, 2))]
+    for n, (name, sh) in enumerate(full):
+        out["full%d_name" % n] = name
+        out["full%d_shls" % n] = np.array(sh, np.int32)
+        out["full%d_vals" % n] = ou.eval_tuple("ref", name, sh, atm, bas, env)[0]
+    out["nfull"] = len(full)
+    np.savez_compressed(os.path.join(OUT, "derivs.npz"), **out)
+
+
 def rys():
     sys.path.insert(0, "/root/reference/scripts")
     import rys_roots as rr
@@ -73,7 +95,7 @@ def rys():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c60", "testbasis", "rys"]
+    which = sys.argv[1:] or ["c60", "testbasis", "derivs", "rys"]
     for w in which:
         globals()[w]()
         print("wrote", w)

@@ -23,8 +23,13 @@ def _worker(rank, world, port, name, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    atm, bas, env = cb.load_fixture(name)
-    s = cb.plan_summary(atm, bas, env, rank=rank, nranks=world)
+    if name == "c60_df":                 # density-fitting job: shards over the auxiliary columns
+        from libcint_b200.basis import c60_df_basis
+        atm, bas, env, norb = c60_df_basis()
+        s = cb.plan_summary(atm, bas, env, rank=rank, nranks=world, chunk_bytes=80 << 30, aux_shell0=norb)
+    else:
+        atm, bas, env = cb.load_fixture(name)
+        s = cb.plan_summary(atm, bas, env, rank=rank, nranks=world)
     t = torch.tensor([s["quartets"], s["integrals"], s["prim_quartets"], s["model_flops"], s["columns"]], dtype=torch.float64)
     mx = t.clone()
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -35,7 +40,7 @@ def _worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["c60_ccpvdz", "c2h6_ccpvtz"])
+@pytest.mark.parametrize("name", ["c60_ccpvdz", "c2h6_ccpvtz", "c60_df"])
 def test_two_rank_sharding_gloo(name):
     world = 2
     ctx = mp.get_context("spawn")
@@ -48,6 +53,13 @@ def test_two_rank_sharding_gloo(name):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    if name == "c60_df":
+        from libcint_b200.basis import c60_df_basis
+        atm, bas, env, norb = c60_df_basis()
+        one = cb.plan_summary(atm, bas, env, chunk_bytes=80 << 30, aux_shell0=norb)
+        assert tot[0] == one["quartets"] and tot[1] == one["integrals"] and tot[4] == one["columns"] == 4800
+        assert mx[3] / one["model_flops"] < 0.51
+        return
     atm, bas, env = cb.load_fixture(name)
     one = cb.plan_summary(atm, bas, env)
     # the shards partition the job exactly ...

@@ -63,3 +63,36 @@ def test_no_gpu_fails_loudly():
         libcint_b200.Context(atm, bas, env)
     out, rc = libcint_b200.int2e_sph((0, 0, 0, 0), atm, bas, env)
     assert rc == 0
+
+
+def test_error_codes_without_context():
+    # argument validation happens before any device work: a NULL / foreign context is rejected with CINTB200_EINVAL (-2)
+    # and a readable message, for every batched entry point (no GPU needed)
+    import numpy as np
+    import libcint_b200
+    lib = libcint_b200.load_library()
+    shls = np.zeros(8, np.int32)
+    out = np.zeros(16)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for name in ("cintb200_int2e_batch", "cintb200_int3c2e_batch", "cintb200_int2c2e_batch", "cintb200_int2e_ip1_batch",
+                 "cintb200_int3c2e_ip1_batch", "cintb200_int3c2e_ip2_batch", "cintb200_int2c2e_ip1_batch", "cintb200_int2c2e_ip2_batch"):
+        f = getattr(lib, name)
+        f.restype = ctypes.c_long
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        assert f(None, 0, p(shls), 1, None, p(out), 0, None) == -2, name
+        assert b"context" in lib.cintb200_last_error()
+    for name in ("cintb200_int2e_sph_block", "cintb200_int3c2e_sph_block", "cintb200_int2c2e_sph_block"):
+        f = getattr(lib, name)
+        f.restype = ctypes.c_int
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        assert f(None, p(shls), p(out), 0, None) == -2, name
+    stats = np.zeros(16)
+    lib.cintb200_int2e_sph_all_unique.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    lib.cintb200_int2e_sph_all_unique.restype = ctypes.c_int
+    assert lib.cintb200_int2e_sph_all_unique(None, 0, 1, 0, None, p(stats)) == -2
+    # host-only planning validates its arguments too
+    atm, bas, env = libcint_b200.load_fixture("c2h6_631g")
+    with pytest.raises(libcint_b200.B200Error):
+        libcint_b200.plan_summary(atm, bas, env, rank=3, nranks=2)
+    with pytest.raises(libcint_b200.B200Error):
+        libcint_b200.plan_summary(atm, bas, env, aux_shell0=len(bas) + 5)

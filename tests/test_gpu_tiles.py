@@ -89,6 +89,24 @@ def test_tiles_range_separated_specialised_kernels():
     check_job("c2h6_ccpvtz", omega=0.3, max_quartets=5000)
 
 
+def test_range_separated_density_fitting_and_blocks():
+    # long-range (erf) 3-centre integrals through the whole-job driver and the dense block calls (RS kernels incl. f / g)
+    worst, kinds = check_df_job(2, omega=0.3, max_triples=2500)
+    assert kinds <= {1, 2}, kinds
+    rng = np.random.default_rng(23)
+    atm, bas, env = cb.load_fixture("c2h6_ccpvdz")
+    env = env.copy()
+    env[8] = 0.4
+    ctx = cb.Context(atm, bas, env)
+    _check_block(ctx, atm, bas, env, (0, 14, 3, 20, 5, 28, 0, 9), "int2e_sph", 2500, rng)
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis(max_atoms=2)
+    env = env.copy()
+    env[8] = 0.4
+    ctx = cb.Context(atm, bas, env)
+    _check_block(ctx, atm, bas, env, (norb, len(bas), norb, len(bas)), "int2c2e_sph", 1500, rng, tol=1e-11)
+
+
 def test_tiles_multi_chunk():
     # tiny chunk budget -> many chunks; the last two are verified, the quartet count covers all of them
     check_job("c2h6_ccpvdz", chunk_bytes=200_000)
@@ -205,12 +223,15 @@ def test_c60_full_size_bench_configuration():
             assert np.abs(tr - got.T).max() < 1e-13
 
 
-def check_df_job(max_atoms, nranks=1, force_generic=False, chunk_bytes=1 << 30, max_triples=None, aux_lmax=4):
+def check_df_job(max_atoms, nranks=1, force_generic=False, chunk_bytes=1 << 30, max_triples=None, aux_lmax=4, omega=None):
     """int3c2e whole-job driver (cintb200_int3c2e_sph_all) on the first atoms of the config-3 stand-in: every block of
     the last tile against the oracle, triple and integral counts over all chunks and ranks."""
     from libcint_b200.basis import c60_df_basis
     which, _ = ou.best()
     atm, bas, env, norb = c60_df_basis(max_atoms=max_atoms, aux_lmax=aux_lmax)
+    if omega is not None:
+        env = env.copy()
+        env[8] = omega
     nbas = len(bas)
     dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
     rng = np.random.default_rng(5)
@@ -239,7 +260,7 @@ def check_df_job(max_atoms, nranks=1, force_generic=False, chunk_bytes=1 << 30, 
             got = tile[r:r + nb, c:c + dims[k]]
             err = np.abs(got - want.reshape((nb, dims[k]), order="F")).max()
             scale = max(1.0, np.abs(want).max())
-            assert err <= 1e-12 * scale, (rank, (i, j, k), err, scale)
+            assert err <= (1e-12 if omega is None else 1e-11) * scale, (rank, (i, j, k), err, scale)
             worst = max(worst, err / scale)
         ctx.close()
     assert tot_triples == norb * (norb + 1) // 2 * (nbas - norb)

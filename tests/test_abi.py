@@ -96,3 +96,30 @@ def test_error_codes_without_context():
         libcint_b200.plan_summary(atm, bas, env, rank=3, nranks=2)
     with pytest.raises(libcint_b200.B200Error):
         libcint_b200.plan_summary(atm, bas, env, aux_shell0=len(bas) + 5)
+
+
+def _build_example(tmp_path):
+    import subprocess
+    import libcint_b200
+    exe = os.path.join(str(tmp_path), "fill_block")
+    libdir = os.path.dirname(libcint_b200.LIB_PATH)
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "fill_block.c"),
+                           "-L" + libdir, "-l:libcint_b200.so", "-lm", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    return subprocess.run([exe], capture_output=True, text=True, env=env, timeout=300)
+
+
+def test_c_example_links_against_the_headers(tmp_path):
+    # examples/fill_block.c is the C-side binding shown in INTEGRATION.md: it must compile against include/*.h with -Wall
+    # -Werror and link; without a GPU it has to stop with the library's own error message (no CPU path)
+    import torch
+    r = _build_example(tmp_path)
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_example_runs_on_the_gpu(tmp_path):
+    r = _build_example(tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "nonzero = 1" in r.stdout and "(00|00) =" in r.stdout

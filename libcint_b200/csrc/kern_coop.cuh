@@ -23,6 +23,9 @@
 #ifndef COOP_THREADS
 #define COOP_THREADS 128
 #endif
+#ifndef COOP_FUSED_ROOTS
+#define COOP_FUSED_ROOTS 0      // 1: experiment prepared for round 2, NOT validated on a GPU yet
+#endif
 #ifndef COOP_MB16
 #define COOP_MB16 4
 #endif
@@ -205,34 +208,43 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             for (int pass = RS ? P.rs_pass0 : 1; pass < 2; pass++) {
             const bool att = RS && pass == 1;
             const double xq = att ? x * th_ : x, fac = att ? fac0 * sq_ : fac0, thp = att ? th_ : 1.0;
-            // --- roots: one polynomial per lane ---
-            for (int p = lane; p < 2 * N; p += FS) {
-                double v;
+            // value of root/weight polynomial p (p = 2k: t_k^2, p = 2k + 1: w_k) at xq
+            auto rys_eval = [&](const int p) -> double {
                 if (xq >= 35.0 + 5.0 * N) {
                     const int k = N * (N - 1) / 2 + (p >> 1);
-                    v = (p & 1) ? c_rys_lx_v[k] * rsqrt(xq) : c_rys_lx_r[k] / xq;
-                } else {
-                    int idx;
-                    double y;
-                    rys_locate(xq, idx, y);
-                    asm("" : "+r"(idx));        // opaque index: no 24-bit overflow of the folded grid offset in the LDS immediates
-                    const double *cf = s_rys + idx * rys_smem_stride(N) + p;
-                    // Estrin (depth 4) instead of Horner (depth 9): this phase is a dependent chain on a few busy lanes
-                    static_assert(RYS_DEG == 9, "Estrin scheme written for degree 9");
-                    const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
-                    const double p01 = fma(cf[1 * 2 * N], y, cf[0]), p23 = fma(cf[3 * 2 * N], y, cf[2 * 2 * N]);
-                    const double p45 = fma(cf[5 * 2 * N], y, cf[4 * 2 * N]), p67 = fma(cf[7 * 2 * N], y, cf[6 * 2 * N]);
-                    const double p89 = fma(cf[9 * 2 * N], y, cf[8 * 2 * N]);
-                    v = fma(p89, y8, fma(fma(p67, y2, p45), y4, fma(p23, y2, p01)));
+                    return (p & 1) ? c_rys_lx_v[k] * rsqrt(xq) : c_rys_lx_r[k] / xq;
                 }
-                s_rw[p] = v;
-            }
+                int idx;
+                double y;
+                rys_locate(xq, idx, y);
+                asm("" : "+r"(idx));        // opaque index: no 24-bit overflow of the folded grid offset in the LDS immediates
+                const double *cf = s_rys + idx * rys_smem_stride(N) + p;
+                // Estrin (depth 4) instead of Horner (depth 9): this phase is a dependent chain on a few busy lanes
+                static_assert(RYS_DEG == 9, "Estrin scheme written for degree 9");
+                const double y2 = y * y, y4 = y2 * y2, y8 = y4 * y4;
+                const double p01 = fma(cf[1 * 2 * N], y, cf[0]), p23 = fma(cf[3 * 2 * N], y, cf[2 * 2 * N]);
+                const double p45 = fma(cf[5 * 2 * N], y, cf[4 * 2 * N]), p67 = fma(cf[7 * 2 * N], y, cf[6 * 2 * N]);
+                const double p89 = fma(cf[9 * 2 * N], y, cf[8 * 2 * N]);
+                return fma(p89, y8, fma(fma(p67, y2, p45), y4, fma(p23, y2, p01)));
+            };
+#if !COOP_FUSED_ROOTS
+            // --- roots: one polynomial per lane ---
+            for (int p = lane; p < 2 * N; p += FS) s_rw[p] = rys_eval(p);
             __syncwarp();
+#endif
             // --- VRR: one (root, axis) per lane ---
             const double rho_l = aL * inv, rho_r = aR * inv;
             for (int task = lane; task < 3 * N; task += FS) {
                 const int r = task / 3, d = task - 3 * r;
-                const double s = RS ? s_rw[2 * r] * thp : s_rw[2 * r];
+#if COOP_FUSED_ROOTS
+                // untested experiment: every VRR lane evaluates the root it consumes, the z lane also the
+                // weight -- no separate root phase, one smem round trip and one warp sync less per primitive
+                const double t2r = rys_eval(2 * r);
+                const double wr = (d == 2) ? rys_eval(2 * r + 1) : 0.0;
+#else
+                const double t2r = s_rw[2 * r];
+#endif
+                const double s = RS ? t2r * thp : t2r;
                 const double sl = s * rho_l, sr = s * rho_r;
                 const double b00 = 0.5 * s * inv;
                 const double b10 = (0.5 - 0.5 * sl) * iaR;
@@ -243,7 +255,11 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
                 const double c00 = pad - sl * pqd;
                 const double c0p = qcd + sr * pqd;
                 double g[NMAX + 1][MMAX + 1];
+#if COOP_FUSED_ROOTS
+                g[0][0] = (d == 2) ? wr * fac : 1.0;
+#else
                 g[0][0] = (d == 2) ? s_rw[2 * r + 1] * fac : 1.0;
+#endif
                 if constexpr (NMAX > 0) g[1][0] = c00 * g[0][0];
                 static_for<(NMAX > 1 ? NMAX - 1 : 0)>([&](auto NN) {
                     constexpr int n = decltype(NN)::value + 1;

@@ -89,13 +89,76 @@ size_t cintb200_block_size(const cintb200_ctx *ctx, int kind, const int *shls, i
  * (no communication).  If `host_sink` != NULL every finished chunk is copied to it (pinned host
  * buffer of at least chunk_bytes) inside the call -- the end-to-end mode.
  *   stats[0] shell quartets evaluated     stats[1] integrals written
- *   stats[2] primitive quartets executed  stats[3] sum of all integrals (checksum)
+ *   stats[2] primitive quartets executed  stats[3] sum of all integrals (with checksums on, see below)
  *   stats[4] kernel launches              stats[5] device->host bytes
  *   stats[6] model FLOPs of the executed primitive quartets (SURVEY 8d formula)
  *   stats[7] GPU milliseconds of the ERI kernels (CUDA events on the launch stream)
  */
 int cintb200_int2e_sph_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes,
                                   double *host_sink, double *stats);
+/*
+ * Notes on the whole-job drivers:
+ *  - stats[3] is filled when checksums are switched on (cintb200_set_checksums), else it is 0.
+ *  - chunk boundaries do not depend on nranks: every rank count walks the same chunks with 1/nranks of the columns, so a
+ *    rank's tiles are about chunk_bytes / nranks.
+ *  - a single `host_sink` is a throughput mode: every tile is copied to the SAME buffer, so after the call only the last
+ *    tile can be read.  To CONSUME every tile use the *_tiles variants below (ring of sinks + callback).
+ *  - tile entries of quartets outside the loop (K > I, only possible for the kets of the chunk's own bra shells, columns
+ *    >= cintb200_tile.ncols_below) are zero in host sinks; in the device-resident tile they are left unwritten.
+ */
+
+/* One finished tile, column-major values[row + nrows * col]: rows = AO pairs of the bra shell pairs with i in [i0, i1)
+ * (global row numbers row0 .. row0 + nrows), columns = AO pairs of this rank's kets with k < i1 (the first ncols columns of
+ * the rank's column numbering; the first ncols_below of them belong to kets with k < i0, for which every row is in the
+ * loop).  cintb200_job_row_map / cintb200_job_col_map translate rows and columns to shells and block positions. */
+typedef struct {
+    int chunk, nchunks, rank, nranks, i0, i1;
+    long long row0, nrows, ncols, ncols_below;
+} cintb200_tile;
+/* Called on the thread that made the whole-job call, once per tile, in chunk order, after the tile has arrived in host memory
+ * and before its sink is reused; `values` points into one of the caller's sinks.  Return non-zero to abort the job. */
+typedef int (*cintb200_tile_fn)(void *user, const cintb200_tile *tile, const double *values);
+
+/* cintb200_int2e_sph_all_unique / cintb200_int3c2e_sph_all with every tile delivered to the caller: tile k is copied into
+ * sinks[k % nsinks] (pinned host buffers of at least chunk_bytes each) while the kernels of tile k+1 run, then `fn` is called
+ * (fn may be NULL: copies only).  nsinks >= 2 lets copy, kernels and the consumer overlap; stats[5] = bytes copied. */
+int cintb200_int2e_sph_all_unique_tiles(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
+                                        cintb200_tile_fn fn, void *user, double *stats);
+int cintb200_int3c2e_sph_all_tiles(cintb200_ctx *ctx, int aux_shell0, int rank, int nranks, size_t chunk_bytes, double *const *sinks,
+                                   int nsinks, cintb200_tile_fn fn, void *user, double *stats);
+
+/*
+ * Coulomb and exchange matrices built on the device from the tiles of the whole int2e_sph job -- the consumer the reference's
+ * callers wrap around the per-quartet call; no integral leaves the GPU:
+ *     vj[a,b] = sum_cd (ab|cd) dm[c,d]        vk[a,c] = sum_bd (ab|cd) dm[b,d]
+ * dm: SYMMETRIC nao x nao density (spherical AOs in shell order); vj, vk: nao x nao (either may be NULL).  Host pointers
+ * (on_device = 0) or device pointers (on_device = 1).  Only the 8-fold unique quartets (ij >= kl) are digested, with the
+ * usual symmetry factors; rank `rank` of `nranks` digests its ket shard and returns PARTIAL matrices -- the caller adds them
+ * over the ranks (one all-reduce of 2 nao^2 doubles; the only collective of the path).  stats as for the whole-job driver.
+ */
+int cintb200_int2e_sph_jk(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes, const double *dm, double *vj, double *vk,
+                          int on_device, double *stats);
+
+/*
+ * Whole-job checksums.  When switched on, every finished tile is reduced on the device to per-row sums of its in-loop entries,
+ * and stats[3] returns the sum of all integrals.  cintb200_job_checksums returns, per bra shell pair p = i(i+1)/2 + j, this
+ * rank's partial sums over its kets of
+ *     S[p] = sum v,   A[p] = sum |v|,   F[p] = sum v cos(0.91 r + 0.3) cos(0.37 c + 0.61 d + 0.5)
+ * (r = position mi + di mj of the row inside the (i,j) block, c / d = global spherical AO indices of the ket functions;
+ * 3-centre jobs: c = index of the auxiliary function counted from the first auxiliary AO, d = 0).  Summed over the ranks
+ * they are independent of chunking and sharding -- the quantities oracle/ref_golden.c computes from the reference.
+ * Any of S, A, F may be NULL; returns the number of pairs.
+ */
+int cintb200_set_checksums(cintb200_ctx *ctx, int on);
+int cintb200_job_checksums(cintb200_ctx *ctx, double *S, double *A, double *F);
+
+/* Geometry of the cached whole-job plan (after any whole-job call):
+ * geom[0..8] = i0, i1, row0, nrows, ncols, number of chunks, total rows, this rank's total columns, ncols_below. */
+int cintb200_job_geometry(cintb200_ctx *ctx, int chunk, long long *geom);
+/* per row of chunk `chunk`: bra shells i >= j and the position mi + di mj inside the (i,j) block (arrays of nrows ints, may be NULL) */
+int cintb200_job_row_map(cintb200_ctx *ctx, int chunk, int *sh_i, int *sh_j, int *pos);
+/* per column: ket shells k >= l (3-centre jobs: auxiliary shell k, l = -1) and the position mk + dk ml (arrays of ncols ints) */
+int cintb200_job_col_map(cintb200_ctx *ctx, int chunk, int *sh_k, int *sh_l, int *pos);
 
 /*
  * Whole-job driver for density fitting: every shell triple (ij|k) of int3c2e_sph (src/cint3c2e.c:693) with orbital
@@ -144,6 +207,8 @@ int cintb200_plan_summary_3c(const int *atm, int natm, const int *bas, int nbas,
 /* Measured FP64 FMA peak of the device in TFLOP/s (DFMA-chain microbenchmark run for about `seconds`);
  * the roofline denominator of bench.py, since MEASURED_PEAKS.json has no FP64 entry. */
 int cintb200_fp64_peak(int device, double seconds, double *tflops);
+/* SMs x 64 FP64 lanes x 2 flops x SM clock (sm_mhz <= 0: the device's maximum clock), for comparison with the measured figure. */
+int cintb200_fp64_peak_theoretical(int device, double sm_mhz, double *tflops);
 
 /* Last error text of the calling thread ("" if none). */
 const char *cintb200_last_error(void);

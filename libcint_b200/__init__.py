@@ -81,6 +81,28 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+class TileInfo(ctypes.Structure):
+    """cintb200_tile of include/cint_b200.h."""
+    _fields_ = [("chunk", ctypes.c_int), ("nchunks", ctypes.c_int), ("rank", ctypes.c_int), ("nranks", ctypes.c_int),
+                ("i0", ctypes.c_int), ("i1", ctypes.c_int), ("row0", ctypes.c_longlong), ("nrows", ctypes.c_longlong),
+                ("ncols", ctypes.c_longlong), ("ncols_below", ctypes.c_longlong)]
+
+
+TILE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(TileInfo), ctypes.POINTER(ctypes.c_double))
+
+
+def job_weights(nao, maxrb=1):
+    """Weights of the whole-job fingerprints (formulas of oracle/ref_golden.c and csrc/digest.cu): h[r] per block row position,
+    g[c, d] per ket AO pair, the formula density D[a, b] and the probe matrix U[nao, 8] of the committed J/K goldens."""
+    r = np.arange(maxrb)
+    a = np.arange(nao)
+    h = np.cos(0.91 * r + 0.3)
+    g = np.cos(0.37 * a[:, None] + 0.61 * a[None, :] + 0.5)
+    D = np.cos(0.37 * (a[:, None] + a[None, :]) + 0.2) + 0.5 * np.cos(0.11 * (a[:, None] - a[None, :]))
+    U = np.cos(0.13 * (a[:, None] + 1) * (np.arange(8)[None, :] + 1) + 0.7)
+    return h, g, D, U
+
+
 def _as_basis(atm, bas, env):
     atm = np.ascontiguousarray(atm, dtype=np.int32).reshape(-1, 6)
     bas = np.ascontiguousarray(bas, dtype=np.int32).reshape(-1, 8)
@@ -180,6 +202,98 @@ class Context:
             raise B200Error("all_unique failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return stats
 
+
+    # ---- consumers of the whole-job tiles ----
+    def set_checksums(self, on=True):
+        """Reduce every finished tile to per-row sums on the device (cintb200_set_checksums); stats[3] = sum of all integrals."""
+        self.lib.cintb200_set_checksums.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        self.lib.cintb200_set_checksums(self.handle, int(on))
+
+    def job_checksums(self):
+        """(S, A, F) per bra shell pair i(i+1)/2+j of the last whole-job run with checksums on: this rank's partial sums."""
+        f = self.lib.cintb200_job_checksums
+        f.argtypes = [ctypes.c_void_p] * 4
+        f.restype = ctypes.c_int
+        n = f(self.handle, None, None, None)
+        if n < 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        S, A, F = np.zeros(n), np.zeros(n), np.zeros(n)
+        f(self.handle, _p(S), _p(A), _p(F))
+        return S, A, F
+
+    def job_geometry(self, chunk=0):
+        g = np.zeros(9, dtype=np.int64)
+        self.lib.cintb200_job_geometry.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        if self.lib.cintb200_job_geometry(self.handle, chunk, _p(g)) != 0:
+            raise B200Error(self.lib.cintb200_last_error().decode())
+        return dict(zip(("i0", "i1", "row0", "nrows", "ncols", "nchunks", "total_rows", "total_cols", "ncols_below"), (int(v) for v in g)))
+
+    def job_maps(self, chunk):
+        """((sh_i, sh_j, pos) per row, (sh_k, sh_l, pos) per column) of chunk `chunk` of the cached whole-job plan."""
+        g = self.job_geometry(chunk)
+        rows = [np.zeros(g["nrows"], dtype=np.int32) for _ in range(3)]
+        cols = [np.zeros(g["ncols"], dtype=np.int32) for _ in range(3)]
+        for fn, arrs in ((self.lib.cintb200_job_row_map, rows), (self.lib.cintb200_job_col_map, cols)):
+            fn.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+            if fn(self.handle, chunk, *[_p(a) for a in arrs]) != 0:
+                raise B200Error(self.lib.cintb200_last_error().decode())
+        return rows, cols
+
+    def all_unique_tiles(self, sinks, callback=None, rank=0, nranks=1, chunk_bytes=0, aux_shell0=None):
+        """Whole job with every tile delivered to the host: `sinks` = list of pinned-buffer addresses (ints), `callback(tile
+        dict, values ndarray[nrows, ncols] F-order view into the sink)` is called once per tile in chunk order."""
+        err = []
+
+        def tramp(user, tile, values):
+            try:
+                t = tile.contents
+                info = {k: getattr(t, k) for k, _ in TileInfo._fields_}
+                if callback is not None:
+                    n = info["nrows"] * info["ncols"]
+                    arr = np.ctypeslib.as_array(values, shape=(n,)).reshape((info["nrows"], info["ncols"]), order="F") if n else np.zeros((0, 0))
+                    callback(info, arr)
+                return 0
+            except Exception as e:          # never unwind through C
+                err.append(e)
+                return 1
+        cb = TILE_FN(tramp)
+        arr = (ctypes.c_void_p * len(sinks))(*sinks)
+        stats = np.zeros(16)
+        if aux_shell0 is None:
+            f = self.lib.cintb200_int2e_sph_all_unique_tiles
+            f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, TILE_FN, ctypes.c_void_p, ctypes.c_void_p]
+            f.restype = ctypes.c_int
+            rc = f(self.handle, rank, nranks, chunk_bytes, arr, len(sinks), cb, None, _p(stats))
+        else:
+            f = self.lib.cintb200_int3c2e_sph_all_tiles
+            f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, TILE_FN, ctypes.c_void_p, ctypes.c_void_p]
+            f.restype = ctypes.c_int
+            rc = f(self.handle, aux_shell0, rank, nranks, chunk_bytes, arr, len(sinks), cb, None, _p(stats))
+        if err:
+            raise err[0]
+        if rc < 0:
+            raise B200Error("all_unique_tiles failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return stats
+
+    def jk(self, dm=None, rank=0, nranks=1, chunk_bytes=0, with_k=True, device_ptrs=None):
+        """Coulomb / exchange matrices digested on the device (cintb200_int2e_sph_jk): returns (vj, vk, stats) -- this rank's
+        PARTIAL matrices when nranks > 1.  device_ptrs = (dm, vj, vk) device addresses -> results stay on the device."""
+        f = self.lib.cintb200_int2e_sph_jk
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        stats = np.zeros(16)
+        if device_ptrs is not None:
+            d, j, k = device_ptrs
+            rc = f(self.handle, rank, nranks, chunk_bytes, ctypes.c_void_p(d), ctypes.c_void_p(j), ctypes.c_void_p(k) if (k and with_k) else None, 1, _p(stats))
+            vj = vk = None
+        else:
+            dm = np.ascontiguousarray(dm, dtype=np.float64)
+            vj = np.zeros_like(dm)
+            vk = np.zeros_like(dm) if with_k else None
+            rc = f(self.handle, rank, nranks, chunk_bytes, _p(dm), _p(vj), _p(vk) if with_k else None, 0, _p(stats))
+        if rc < 0:
+            raise B200Error("jk failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return vj, vk, stats
 
     def int3c2e_all(self, aux_shell0, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
         """Whole density-fitting job: every (ij|k), orbital shells i >= j < aux_shell0 <= k (cintb200_int3c2e_sph_all)."""
@@ -371,6 +485,16 @@ def fp64_peak_tflops(device=-1, seconds=0.5):
     lib = load_library()
     v = ctypes.c_double()
     if lib.cintb200_fp64_peak(device, seconds, ctypes.byref(v)) != 0:
+        raise B200Error(lib.cintb200_last_error().decode())
+    return v.value
+
+
+def fp64_peak_theoretical_tflops(device=-1, sm_mhz=0.0):
+    """SMs x 64 FP64 lanes x 2 x clock (sm_mhz <= 0: maximum SM clock of the device)."""
+    lib = load_library()
+    lib.cintb200_fp64_peak_theoretical.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    v = ctypes.c_double()
+    if lib.cintb200_fp64_peak_theoretical(device, sm_mhz, ctypes.byref(v)) != 0:
         raise B200Error(lib.cintb200_last_error().decode())
     return v.value
 

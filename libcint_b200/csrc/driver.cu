@@ -34,59 +34,7 @@ extern const int *engine_c2s_off();
 #define CU_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
     return b200_fail(CINTB200_ENODEV, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
 
-struct PairClass {
-    int la, lb, nca, ncb, Q;
-    std::vector<int> ids, I, npp;
-    std::vector<long long> npp_prefix;      // prefix sums of npp over the list
-    double *d_tprim = nullptr, *d_tgeom = nullptr;
-    long long *d_trow = nullptr, *d_ucol = nullptr;
-    int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr, *d_tnpp = nullptr;
-    std::vector<int> chunk_lo;              // first list index of every chunk (+ end)
-    // second ordering of the same pairs for the DIAGONAL kets of a chunk (K inside the chunk's bra shell range):
-    // sorted by the larger shell index (then by primitive count), so the valid bras of a ket are a suffix
-    std::vector<int> idsB, IB, nppB;
-    double *dB_tprim = nullptr, *dB_tgeom = nullptr;
-    long long *dB_trow = nullptr;
-    int *dB_tstride = nullptr, *dB_tI = nullptr, *dB_tpair = nullptr, *dB_tnpp = nullptr;
-    double *d_tq = nullptr, *dB_tq = nullptr;   // Schwarz bounds in both orderings
-};
-
-struct LaunchRec;
-struct JobPlan {
-    int rank = 0, nranks = 1;
-    size_t chunk_bytes = 0;
-    int ncenter = 4, aux0 = 0;              // 3: rows = orbital pairs of shells [0, aux0), columns = auxiliary shells [aux0, nbas)
-    int rect = 0;                           // dense shell-slice block (build_rect_plan): explicit bra / ket lists, one tile; value =
-                                            // number of centres of the integral (3 or 4)
-    int own_out = 1;                        // d_out[0] belongs to the plan (rect jobs may write into the caller's device buffer)
-    std::vector<PairClass> classes;
-    std::vector<PairClass> uclasses;        // 3-centre jobs: classes of the single-shell pseudo pairs (kets); 4-centre: unused
-    std::vector<long long> colof_aux;       // 3-centre jobs: this rank's column offset of auxiliary shell aux0 + n, or -1
-    std::vector<long long> rowoff;          // per pair id
-    std::vector<long long> rows_before;     // [nbas+1] rows of pairs with I < i
-    std::vector<long long> cols_before;     // [nbas+1] this rank's columns of kets with K < i
-    std::vector<std::pair<int, int>> chunks;
-    std::vector<long long> chunk_cols;      // this rank's columns needed by chunk k (kets with K < i1)
-    double *d_out[2] = {nullptr, nullptr};
-    size_t out_doubles = 0;
-    long long *d_uprefix = nullptr; size_t cap_uprefix = 0;
-    unsigned int *d_counters = nullptr;     // one work-item counter per launch
-    double *d_scratch = nullptr; size_t cap_scratch = 0;
-    int force_generic = 0;
-    double schwarz_thr = 0;
-    int host_only = 0;                      // planning without a device (cintb200_plan_summary)
-    std::vector<long long> colof;           // per pair id: this rank's column offset or -1
-    std::vector<struct LaunchRec> launches;
-    double st_quartets = 0, st_integrals = 0, st_prim = 0, st_flops = 0;
-    cudaStream_t copy_stream = nullptr;
-#ifndef B200_NSTREAMS
-#define B200_NSTREAMS 8
-#endif
-    static const int NS = B200_NSTREAMS;    // concurrent launch streams (independent classes overlap)
-    cudaStream_t streams[NS] = {nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[NS] = {nullptr};
-    cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr}, ev_t0 = nullptr, ev_t1 = nullptr;
-};
+#include "driver.h"
 
 void jobplan_free(JobPlan *p)
 {
@@ -108,6 +56,7 @@ void jobplan_free(JobPlan *p)
     }
     if (p->ev_t0) cudaEventDestroy(p->ev_t0);
     if (p->ev_t1) cudaEventDestroy(p->ev_t1);
+    digest_free(p->digest);
     delete p;
 }
 
@@ -188,7 +137,10 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     //    per-chunk reordering, the buffer is then sized from the exact maximum)
     const size_t cap = plan->chunk_bytes / sizeof(double);
     const long long slack = maxdim * (long long)plan->classes.size() * 2;
-    auto est_cols = [&](int i1) { return (size_t)((three ? aux_cols : tcols_before[i1]) / nranks + slack); };
+    // The chunk boundaries do NOT depend on the number of ranks (the estimate below is the single-rank one): every rank count
+    // walks the same chunk sequence with 1/nranks of the columns, so the share of diagonal-ket work, the launch list and the
+    // copied rectangle per chunk stay the same from 1 to 8 GPUs (a rank's tile is then ~chunk_bytes / nranks).
+    auto est_cols = [&](int i1) { return (size_t)((three ? aux_cols : tcols_before[i1]) + slack); };
     int i0 = 0;
     while (i0 < nbas) {
         int i1 = i0 + 1;
@@ -308,6 +260,32 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     }
     plan->cols_before[nbas] = cols;
     plan->out_doubles = need;
+    // 4b. geometry maps for the consumers of the tiles (digest.cu, host callbacks): bra pair + position of every row,
+    //     ket pair (3-centre: auxiliary shell) + position of every column of this rank
+    plan->row_pair.assign((size_t)rows, -1); plan->row_pos.assign((size_t)rows, 0);
+    for (int i = 0; i < nbas; i++)
+        for (int j = 0; j <= i; j++) {
+            const size_t p = (size_t)i * (i + 1) / 2 + j;
+            const long long n = pair_dim(i, j), r0 = plan->rowoff[p];
+            for (long long r = 0; r < n; r++) { plan->row_pair[r0 + r] = (int)p; plan->row_pos[r0 + r] = (int)r; }
+        }
+    plan->col_pair.assign((size_t)cols, -1); plan->col_pos.assign((size_t)cols, 0);
+    if (three) {
+        for (int k = plan->aux0; k < c->nbas; k++) {
+            const long long c0 = plan->colof_aux[k - plan->aux0];
+            if (c0 < 0) continue;
+            const int dk = (2 * c->shells[k].l + 1) * c->shells[k].nctr;
+            for (int r = 0; r < dk; r++) { plan->col_pair[c0 + r] = k; plan->col_pos[c0 + r] = r; }
+        }
+    } else {
+        for (int i = 0; i < nbas; i++)
+            for (int j = 0; j <= i; j++) {
+                const size_t p = (size_t)i * (i + 1) / 2 + j;
+                if (colof[p] < 0) continue;
+                const long long n = pair_dim(i, j);
+                for (long long r = 0; r < n; r++) { plan->col_pair[colof[p] + r] = (int)p; plan->col_pos[colof[p] + r] = (int)r; }
+            }
+    }
     // 5. device tables per class, for both orderings
     for (PairClass &pc : plan->classes) {
         const size_t NT = pc.ids.size();
@@ -387,19 +365,6 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     return 0;
 }
 
-struct LaunchRec {
-    int chunk;
-    TileParams P;               // out / row0 / ld filled per run (buffer alternates)
-    RegKernelFn fn;             // nullptr -> generic kernel
-    int coop; CoopInfo ci;      // fn is a cooperative kernel
-    int nroots, ncu, gx, gy;
-    GenericClass GC; GenericLaunch GL;
-    long long ntasks;           // generic: number of quartets
-    size_t uprefix_off;         // generic: offset into plan->d_uprefix
-    int key[6];                 // la lb lc ld nct ncu
-    double quartets, prim, flops, integrals;
-    int part;                   // 0: kets below the chunk's bra shells, 1: the chunk's own kets
-};
 
 static int build_launches(CINTOpt *c, JobPlan *plan)
 {
@@ -477,6 +442,11 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci, rs);
                     L.coop = L.fn != nullptr;
                 }
+                // deeply contracted kets (all-electron heavy-element bases) can push the staged ket primitives past the
+                // shared memory a block may have: such classes go to the generic kernel instead of failing at launch
+                if (L.fn && !plan->host_only && (L.coop ? coop_kernel_smem(L.ci, L.ncu, P.umax) : reg_kernel_smem(L.fn, L.nroots, L.ncu, P.umax)) > (size_t)tile_smem_limit()) {
+                    L.fn = nullptr; L.coop = 0;
+                }
                 if (L.fn && !L.coop && REG_FAST_RYS && L.nroots <= RYS_FNMAX && L.nroots <= REG_FAST_NMAX)
                     P.rys = c->d_rys_fast + rys_fast_off(L.nroots);   // register kernels of low order read the degree-6 tables
                 if (L.fn) {
@@ -512,19 +482,37 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
     return 0;
 }
 
-static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *host_sink, double *stats);
+// How the finished tiles leave the device (or do not): host sinks, per-tile callback, device-side consumers
+struct TileSink {
+    double *const *sinks = nullptr;         // ring of pinned host buffers (each >= the largest tile); NULL: tiles stay on the device
+    int nsinks = 0;
+    cintb200_tile_fn fn = nullptr;          // called on the calling thread when a tile has arrived in its sink
+    void *user = nullptr;
+    DigestJob job;                          // device-side consumers (digest.cu)
+    const double *dm_dev = nullptr;         // J/K: density matrix (device), results (device)
+    double *vj_dev = nullptr, *vk_dev = nullptr;
+};
+
+static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileSink &sink, double *stats);
 
 // ncenter = 4: every unique quartet of int2e_sph; ncenter = 3: every triple (ij|k), i >= j < aux0 <= k, of int3c2e_sph
 static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks, size_t chunk_bytes,
-                   double *host_sink, double *stats)
+                   const TileSink &sink, double *stats)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (nranks < 1 || rank < 0 || rank >= nranks) return b200_fail(CINTB200_EINVAL, "bad rank %d of %d", rank, nranks);
     if (ncenter == 3 && (aux0 < 1 || aux0 >= c->nbas))
         return b200_fail(CINTB200_EINVAL, "first auxiliary shell %d outside 1..%d", aux0, c->nbas - 1);
+    if (sink.sinks) {
+        if (sink.nsinks < 1) return b200_fail(CINTB200_EINVAL, "host sinks given but nsinks = %d", sink.nsinks);
+        for (int k = 0; k < sink.nsinks; k++) if (!sink.sinks[k]) return b200_fail(CINTB200_EINVAL, "host sink %d is NULL", k);
+    } else if (sink.fn) return b200_fail(CINTB200_EINVAL, "a tile callback needs at least one host sink");
     if (ncenter == 4 && c->schwarz_thr > 0 && c->omega == 0 && !c->force_generic && ctx_compute_schwarz(c)) return CINTB200_ENODEV;
     std::lock_guard<std::mutex> lock(c->mtx);
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
     CU_OK(cudaSetDevice(c->device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
     JobPlan *plan = c->plan;
     if (!plan || plan->rect || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic
@@ -538,16 +526,19 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
         if (rc) { jobplan_free(plan); return rc; }
         c->plan = plan;
     }
-    if (host_sink && !plan->d_out[1] && cudaMalloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles) != cudaSuccess)
+    if (sink.sinks && !plan->d_out[1] && cudaMalloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate the second %zu-byte tile buffer", sizeof(double) * plan->out_doubles);
-    if (host_sink && plan->out_doubles * sizeof(double) > chunk_bytes)
-        return b200_fail(CINTB200_EINVAL, "host_sink mode: the largest tile (one bra shell x all kets) needs %zu bytes, "
+    if (sink.sinks && plan->out_doubles * sizeof(double) > chunk_bytes)
+        return b200_fail(CINTB200_EINVAL, "host sinks: the largest tile (one bra shell x all of this rank's kets) needs %zu bytes, "
                          "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
-    return execute_plan(c, plan, ncenter, host_sink, stats);
+    return execute_plan(c, plan, ncenter, sink, stats);
 }
 
-// Launch every kernel of a plan (all chunks), with the optional device->host copy of every finished tile.  Caller holds c->mtx.
-static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *host_sink, double *stats)
+// Launch every kernel of a plan (all chunks); finished tiles go to the device-side consumers and / or to the host sinks.
+// With host sinks the tiles alternate between two device buffers and chunk k is copied to sinks[k % nsinks] while the kernels
+// of chunk k+1 run; the callback for chunk k is made on the calling thread once that copy has completed and before the sink
+// is reused, so a consumer sees every tile.  Caller holds c->mtx.
+static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileSink &sink, double *stats)
 {
     EngineParams EP;
     EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
@@ -556,10 +547,11 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
     double d2h = 0;
     long long nlaunch = 0, reg_launches = 0;
     const bool prof = c->profile != 0;
+    const bool host = sink.sinks != nullptr;
     cudaStream_t st = c->stream;
     CU_OK(cudaEventRecord(plan->ev_t0, st));
     CU_OK(cudaMemsetAsync(plan->d_counters, 0, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size()), st));
-    int buf = 0, cur_chunk = -1;
+    if (digest_begin(c, plan, sink.job, sink.dm_dev, st)) return CINTB200_ENODEV;
     const int NS = prof ? 1 : JobPlan::NS;
     auto fork = [&]() -> int {                 // side streams start after everything queued on the main stream
         if (NS == 1) return 0;
@@ -575,31 +567,35 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
         }
         return 0;
     };
-    auto finish_chunk = [&](int ch, int b) -> int {
+    auto tile_bytes = [&](int ch) {
+        const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
+        return sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->chunk_cols[ch];
+    };
+    // chunk done on the device: consumers, then the copy to host sink number `slot`
+    auto finish_chunk = [&](int ch, int b, int slot) -> int {
         if (join()) return CINTB200_ENODEV;
+        if (digest_tile(c, plan, sink.job, ch, plan->d_out[b], st)) return CINTB200_ENODEV;
         CU_OK(cudaEventRecord(plan->ev_done[b], st));
-        if (host_sink) {
-            const int i0 = plan->chunks[ch].first, i1 = plan->chunks[ch].second;
-            const size_t bytes = sizeof(double) * (size_t)(plan->rows_before[i1] - plan->rows_before[i0]) * (size_t)plan->chunk_cols[ch];
+        if (host) {
+            const size_t bytes = tile_bytes(ch);
             CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_done[b], 0));
-            static const int d2h_split = getenv("CINTB200_D2H_SPLIT") ? atoi(getenv("CINTB200_D2H_SPLIT")) : 1;
-            if (d2h_split > 1 && bytes > ((size_t)64 << 20)) {
-                // experiment knob: the tile goes out as `d2h_split` copies on side streams (several DMA engines in flight)
-                const size_t part = (bytes / d2h_split + 255) & ~(size_t)255;
-                const int ns = std::min(d2h_split, (int)JobPlan::NS);
-                for (int k = 0; k < ns; k++) {
-                    const size_t o = part * k, len = (k == ns - 1) ? bytes - o : part;
-                    CU_OK(cudaStreamWaitEvent(plan->streams[k], plan->ev_done[b], 0));
-                    CU_OK(cudaMemcpyAsync((char *)host_sink + o, (char *)plan->d_out[b] + o, len, cudaMemcpyDeviceToHost, plan->streams[k]));
-                    CU_OK(cudaEventRecord(plan->ev_join[k], plan->streams[k]));
-                    CU_OK(cudaStreamWaitEvent(plan->copy_stream, plan->ev_join[k], 0));
-                }
-            } else {
-                CU_OK(cudaMemcpyAsync(host_sink, plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
-            }
+            CU_OK(cudaMemcpyAsync(sink.sinks[slot], plan->d_out[b], bytes, cudaMemcpyDeviceToHost, plan->copy_stream));
             CU_OK(cudaEventRecord(plan->ev_copied[b], plan->copy_stream));
             d2h += (double)bytes;
         }
+        return 0;
+    };
+    // hand a tile that has been queued for copying to the caller
+    auto deliver = [&](int ch, int b, int slot) -> int {
+        if (!sink.fn) return 0;
+        CU_OK(cudaEventSynchronize(plan->ev_copied[b]));
+        cintb200_tile t;
+        memset(&t, 0, sizeof t);
+        t.chunk = ch; t.nchunks = (int)plan->chunks.size(); t.rank = plan->rank; t.nranks = plan->nranks;
+        t.i0 = plan->chunks[ch].first; t.i1 = plan->chunks[ch].second;
+        t.row0 = plan->rows_before[t.i0]; t.nrows = plan->rows_before[t.i1] - t.row0; t.ncols = plan->chunk_cols[ch];
+        t.ncols_below = (plan->ncenter == 3) ? t.ncols : plan->cols_before[t.i0];
+        if (sink.fn(sink.user, &t, sink.sinks[slot]) != 0) return b200_fail(CINTB200_EINVAL, "tile callback asked to stop at chunk %d", ch);
         return 0;
     };
     std::vector<cudaEvent_t> pev;
@@ -608,13 +604,34 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
         for (auto &e : pev) CU_OK(cudaEventCreate(&e));
     }
     size_t li = 0;
-    for (LaunchRec &L : plan->launches) {
-        if (L.chunk != cur_chunk) {
-            if (cur_chunk >= 0) { if (finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV; if (host_sink) buf ^= 1; }
-            cur_chunk = L.chunk;
-            if (host_sink) CU_OK(cudaStreamWaitEvent(st, plan->ev_copied[buf], 0));   // buffer drained?
+    int group = -1, cur_chunk = -1, buf = 0, pend_ch = -1, pend_buf = 0, pend_slot = 0;
+    const size_t nl = plan->launches.size();
+    for (size_t k = 0; k <= nl; k++) {
+        const bool last = (k == nl);
+        if (last || plan->launches[k].chunk != cur_chunk) {
+            if (cur_chunk >= 0) {
+                // the kernels of cur_chunk are queued: while they run, hand over the previous tile, then queue this one's copy
+                if (pend_ch >= 0) { if (deliver(pend_ch, pend_buf, pend_slot)) return CINTB200_EINVAL; pend_ch = -1; }
+                const int slot = host ? group % sink.nsinks : 0;
+                if (finish_chunk(cur_chunk, buf, slot)) return CINTB200_ENODEV;
+                if (host) { pend_ch = cur_chunk; pend_buf = buf; pend_slot = slot; }
+            }
+            if (last) break;
+            cur_chunk = plan->launches[k].chunk;
+            group++;
+            buf = host ? (group & 1) : 0;
+            if (host) {
+                CU_OK(cudaStreamWaitEvent(st, plan->ev_copied[buf], 0));   // device buffer drained?
+                // entries of the chunk's own kets with K > I are not written by the kernels: hand out zeros, not stale values
+                const int i0 = plan->chunks[cur_chunk].first, i1 = plan->chunks[cur_chunk].second;
+                const long long ld = plan->rows_before[i1] - plan->rows_before[i0];
+                const long long cb = (plan->ncenter == 3) ? plan->chunk_cols[cur_chunk] : plan->cols_before[i0];
+                if (!plan->rect && plan->chunk_cols[cur_chunk] > cb)
+                    CU_OK(cudaMemsetAsync(plan->d_out[buf] + ld * cb, 0, sizeof(double) * (size_t)ld * (size_t)(plan->chunk_cols[cur_chunk] - cb), st));
+            }
             if (fork()) return CINTB200_ENODEV;
         }
+        LaunchRec &L = plan->launches[k];
         L.P.out = plan->d_out[buf];
         cudaStream_t ls = (NS == 1) ? st : plan->streams[nlaunch % NS];
         if (prof) CU_OK(cudaEventRecord(pev[li++], st));
@@ -632,10 +649,11 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
         nlaunch++;
     }
     if (prof) CU_OK(cudaEventRecord(pev[li], st));
-    if (cur_chunk >= 0 && finish_chunk(cur_chunk, buf)) return CINTB200_ENODEV;
+    if (digest_end(c, plan, sink.job, sink.vj_dev, sink.vk_dev, st)) return CINTB200_ENODEV;
     CU_OK(cudaEventRecord(plan->ev_t1, st));
+    if (pend_ch >= 0 && deliver(pend_ch, pend_buf, pend_slot)) return CINTB200_EINVAL;
     CU_OK(cudaStreamSynchronize(st));
-    if (host_sink) CU_OK(cudaStreamSynchronize(plan->copy_stream));
+    if (host) CU_OK(cudaStreamSynchronize(plan->copy_stream));
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return b200_fail(CINTB200_ENODEV, "kernel execution failed: %s", cudaGetErrorString(le));
     float ms = 0;
@@ -661,7 +679,9 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
         for (auto &e : pev) cudaEventDestroy(e);
     }
     if (stats) {
-        stats[0] = plan->st_quartets; stats[1] = plan->st_integrals; stats[2] = plan->st_prim; stats[3] = 0;
+        double total = 0;                   // sum of all integrals: available when the checksum consumer ran
+        if (sink.job.checksums && digest_fetch_checksums(c, plan, nullptr, nullptr, nullptr, &total) < 0) return CINTB200_ENODEV;
+        stats[0] = plan->st_quartets; stats[1] = plan->st_integrals; stats[2] = plan->st_prim; stats[3] = total;
         stats[4] = (double)nlaunch; stats[5] = d2h; stats[6] = plan->st_flops; stats[7] = ms;
         stats[8] = (double)reg_launches; stats[9] = (double)plan->chunks.size();
         stats[10] = (double)plan->out_doubles * 8; stats[11] = (double)plan->classes.size();
@@ -672,11 +692,146 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, double *hos
 
 extern "C" int cintb200_int2e_sph_all_unique(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes,
                                              double *host_sink, double *stats)
-{ return run_job(c, 4, 0, rank, nranks, chunk_bytes, host_sink, stats); }
+{
+    TileSink s;
+    double *one[1] = {host_sink};
+    if (host_sink) { s.sinks = one; s.nsinks = 1; }
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
+}
 
 extern "C" int cintb200_int3c2e_sph_all(cintb200_ctx *c, int aux_shell0, int rank, int nranks, size_t chunk_bytes,
                                         double *host_sink, double *stats)
-{ return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, host_sink, stats); }
+{
+    TileSink s;
+    double *one[1] = {host_sink};
+    if (host_sink) { s.sinks = one; s.nsinks = 1; }
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, s, stats);
+}
+
+// Same jobs with every tile handed to the caller: ring of pinned sinks + callback (include/cint_b200.h)
+extern "C" int cintb200_int2e_sph_all_unique_tiles(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
+                                                   cintb200_tile_fn fn, void *user, double *stats)
+{
+    if (!sinks || nsinks < 1) return b200_fail(CINTB200_EINVAL, "cintb200_int2e_sph_all_unique_tiles needs at least one host sink");
+    TileSink s;
+    s.sinks = sinks; s.nsinks = nsinks; s.fn = fn; s.user = user;
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
+}
+
+extern "C" int cintb200_int3c2e_sph_all_tiles(cintb200_ctx *c, int aux_shell0, int rank, int nranks, size_t chunk_bytes, double *const *sinks,
+                                              int nsinks, cintb200_tile_fn fn, void *user, double *stats)
+{
+    if (!sinks || nsinks < 1) return b200_fail(CINTB200_EINVAL, "cintb200_int3c2e_sph_all_tiles needs at least one host sink");
+    TileSink s;
+    s.sinks = sinks; s.nsinks = nsinks; s.fn = fn; s.user = user;
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, s, stats);
+}
+
+// Coulomb / exchange matrices digested on the device from the tiles of the whole job (digest.cu); dm, vj, vk are nao x nao
+extern "C" int cintb200_int2e_sph_jk(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes, const double *dm, double *vj, double *vk,
+                                     int on_device, double *stats)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    if (!dm || (!vj && !vk)) return b200_fail(CINTB200_EINVAL, "cintb200_int2e_sph_jk: dm and at least one of vj, vk are required");
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    CU_OK(cudaSetDevice(c->device));
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    const size_t n2 = (size_t)c->nao_sph * c->nao_sph;
+    double *d_io = nullptr;
+    TileSink s;
+    s.job.jk = 1; s.job.want_k = vk != nullptr; s.job.checksums = c->checksums;
+    if (on_device) { s.dm_dev = dm; s.vj_dev = vj; s.vk_dev = vk; }
+    else {
+        if (cudaMalloc((void **)&d_io, sizeof(double) * 3 * n2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "J/K: cannot allocate device matrices");
+        if (cudaMemcpy(d_io, dm, sizeof(double) * n2, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d_io); return b200_fail(CINTB200_ENODEV, "J/K: upload of dm failed"); }
+        s.dm_dev = d_io; s.vj_dev = vj ? d_io + n2 : nullptr; s.vk_dev = vk ? d_io + 2 * n2 : nullptr;
+    }
+    int rc = run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
+    if (!rc && !on_device) {
+        if (vj && cudaMemcpy(vj, d_io + n2, sizeof(double) * n2, cudaMemcpyDeviceToHost) != cudaSuccess) rc = b200_fail(CINTB200_ENODEV, "J/K: download failed");
+        if (vk && cudaMemcpy(vk, d_io + 2 * n2, sizeof(double) * n2, cudaMemcpyDeviceToHost) != cudaSuccess) rc = b200_fail(CINTB200_ENODEV, "J/K: download failed");
+    }
+    cudaFree(d_io);
+    return rc;
+}
+
+// ---- job geometry and checksums for the consumers of the tiles ----
+extern "C" int cintb200_set_checksums(cintb200_ctx *c, int on)
+{
+    if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
+    c->checksums = on != 0;
+    return 0;
+}
+
+extern "C" int cintb200_job_checksums(cintb200_ctx *c, double *S, double *A, double *F)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan) return b200_fail(CINTB200_EINVAL, "no whole-job run to take checksums from");
+    std::lock_guard<std::mutex> lock(c->mtx);
+    return digest_fetch_checksums(c, c->plan, S, A, F, nullptr);
+}
+
+// geom: {i0, i1, row0, nrows, ncols, nchunks, total rows, this rank's total columns, columns of kets below the chunk's bra shells}
+extern "C" int cintb200_job_geometry(cintb200_ctx *c, int chunk, long long *geom)
+{
+    if (!c || c->magic != B200_CTX_MAGIC || !c->plan || c->plan->rect) return b200_fail(CINTB200_EINVAL, "no whole-job plan (run a whole-job call first)");
+    JobPlan *plan = c->plan;
+    if (chunk < 0 || chunk >= (int)plan->chunks.size() || !geom) return b200_fail(CINTB200_EINVAL, "chunk %d out of range", chunk);
+    const int i0 = plan->chunks[chunk].first, i1 = plan->chunks[chunk].second;
+    geom[0] = i0; geom[1] = i1; geom[2] = plan->rows_before[i0]; geom[3] = plan->rows_before[i1] - plan->rows_before[i0];
+    geom[4] = plan->chunk_cols[chunk]; geom[5] = (long long)plan->chunks.size();
+    geom[6] = (long long)plan->row_pair.size(); geom[7] = (long long)plan->col_pair.size();
+    geom[8] = (plan->ncenter == 3) ? plan->chunk_cols[chunk] : plan->cols_before[i0];
+    return 0;
+}
+
+static inline void pair_to_shells(int p, int *i, int *j)
+{
+    int ii = (int)((sqrt(8.0 * p + 1.0) - 1.0) / 2.0);
+    while ((long long)(ii + 1) * (ii + 2) / 2 <= p) ii++;
+    while ((long long)ii * (ii + 1) / 2 > p) ii--;
+    *i = ii; *j = p - ii * (ii + 1) / 2;
+}
+
+// rows of chunk `chunk` (nrows entries each): bra shells i >= j of the row and its position mi + di * mj inside the (i,j) block
+extern "C" int cintb200_job_row_map(cintb200_ctx *c, int chunk, int *sh_i, int *sh_j, int *pos)
+{
+    long long g[9];
+    if (cintb200_job_geometry(c, chunk, g)) return CINTB200_EINVAL;
+    JobPlan *plan = c->plan;
+    for (long long r = 0; r < g[3]; r++) {
+        int i, j;
+        pair_to_shells(plan->row_pair[g[2] + r], &i, &j);
+        if (sh_i) sh_i[r] = i;
+        if (sh_j) sh_j[r] = j;
+        if (pos) pos[r] = plan->row_pos[g[2] + r];
+    }
+    return 0;
+}
+
+// columns of chunk `chunk` (ncols entries each): ket shells k >= l (3-centre jobs: auxiliary shell k, l = -1) and position mk + dk * ml
+extern "C" int cintb200_job_col_map(cintb200_ctx *c, int chunk, int *sh_k, int *sh_l, int *pos)
+{
+    long long g[9];
+    if (cintb200_job_geometry(c, chunk, g)) return CINTB200_EINVAL;
+    JobPlan *plan = c->plan;
+    for (long long q = 0; q < g[4]; q++) {
+        const int p = plan->col_pair[q];
+        if (plan->ncenter == 3) { if (sh_k) sh_k[q] = p; if (sh_l) sh_l[q] = -1; }
+        else {
+            int k, l;
+            pair_to_shells(p, &k, &l);
+            if (sh_k) sh_k[q] = k;
+            if (sh_l) sh_l[q] = l;
+        }
+        if (pos) pos[q] = plan->col_pos[q];
+    }
+    return 0;
+}
 
 // ------------------------------------------------------------------ list mode on the tile kernels
 // Arbitrary lists of shell tuples (cintb200_int2e_batch & co.) used to run on the block-per-tuple generic kernel only
@@ -739,6 +894,10 @@ static int listtables_build(CINTOpt *c)
             const int rs = c->omega != 0;
             ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, rs);
             if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci, rs); ch.coop = ch.fn != nullptr; }
+            const int nroots_ = (B.la + B.lb + K.la + K.lb) / 2 + 1, ncu_ = K.nca * K.ncb, umax_ = std::max(1, K.Q);
+            if (ch.fn && (ch.coop ? coop_kernel_smem(ch.ci, ncu_, umax_) : reg_kernel_smem(ch.fn, nroots_, ncu_, umax_)) > (size_t)tile_smem_limit()) {
+                ch.fn = nullptr; ch.coop = 0;       // ket too deeply contracted for the staged primitives: generic kernel
+            }
         }
     c->ltab = lt;
     return 0;
@@ -1060,7 +1219,8 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
         if (!rc2) rc2 = build_launches(c, plan2);
         if (rc2) { jobplan_free(plan2); return rc2; }
         c->plan = plan2;
-        return execute_plan(c, plan2, 3, on_device ? nullptr : out, stats);      // 2- and 3-centre integrals share the cutoff
+        { TileSink ts; double *one[1] = {out}; if (!on_device) { ts.sinks = one; ts.nsinks = 1; }
+          return execute_plan(c, plan2, 3, ts, stats); }      // 2- and 3-centre integrals share the cutoff
     }
     const long long NI = aoend(sl[1] - 1) - ao0(sl[0]), NJ = aoend(sl[3] - 1) - ao0(sl[2]);
     const long long NK = aoend(sl[5] - 1) - ao0(sl[4]), NL = (ncenter == 4) ? aoend(sl[7] - 1) - ao0(sl[6]) : 1;
@@ -1102,7 +1262,8 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
     if (!rc) rc = build_launches(c, plan);
     if (rc) { jobplan_free(plan); return rc; }
     c->plan = plan;
-    rc = execute_plan(c, plan, ncenter, on_device ? nullptr : out, stats);
+    { TileSink ts; double *one[1] = {out}; if (!on_device) { ts.sinks = one; ts.nsinks = 1; }
+      rc = execute_plan(c, plan, ncenter, ts, stats); }
     return rc;
 }
 

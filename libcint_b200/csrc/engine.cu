@@ -1023,17 +1023,85 @@ int rys_tab_off(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_T
 int rys_fast_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_NINT[nroots] : 0; }
 int rys_fast_off(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_OFF[nroots] : 0; }
 
+// ------------------------------------------------------------------ launch geometry of the persistent tile kernels
+int tile_smem_limit()
+{
+    static int lim = 0;
+    if (!lim) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) v = 48 * 1024;
+        lim = v;
+    }
+    return lim;
+}
+
+int tile_grid_blocks(const void *fn, int threads, size_t smem, long long total)
+{
+    struct Info { size_t smem_set = 0; int occ = 0; };
+    static std::mutex mtx;
+    static std::map<std::pair<int, const void *>, Info> cache;      // function attributes are per device
+    static std::map<int, int> sm_count;
+    static int per_sm = -1;                     // 0 = occupancy-sized grid, > 0 = that many blocks per SM
+    std::lock_guard<std::mutex> lock(mtx);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (per_sm < 0) {
+        const char *e = getenv("CINTB200_PBLOCKS");
+        per_sm = (e && !strcmp(e, "occ")) ? 0 : (e && atoi(e) > 0) ? atoi(e) : 16;
+    }
+    int &sms = sm_count[dev];
+    if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;
+    Info &in = cache[std::make_pair(dev, fn)];
+    if (smem > in.smem_set || !in.smem_set) {
+        int lim = 0;
+        if (cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || lim <= 0) lim = 48 * 1024;
+        if (smem > (size_t)lim) return -1;
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        in.smem_set = smem > 0 ? smem : 1;
+        in.occ = 0;
+    }
+    int blocks_per_sm = per_sm;
+    if (per_sm == 0) {
+        if (!in.occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&in.occ, fn, threads, smem) != cudaSuccess) in.occ = 1;
+        blocks_per_sm = in.occ > 0 ? in.occ : 1;
+    }
+    const long long cap = (long long)blocks_per_sm * sms;
+    return (int)(total < cap ? (total > 0 ? total : 1) : cap);
+}
+
 // ------------------------------------------------------------------ FP64 roofline denominator
-// MEASURED_PEAKS.json carries no FP64 entry, so the bench measures the DFMA peak itself: 8 independent
-// FMA chains per thread, 2 flops per FMA, enough resident warps to saturate the FP64 pipes.
+// MEASURED_PEAKS.json carries no FP64 entry, so the bench measures the DFMA peak itself: 16 independent FMA chains per
+// thread, the loop unrolled 16x (one loop-control sequence per 256 DFMAs), 2 flops per FMA, 8 warps per scheduler.
+// cintb200_fp64_peak_theoretical gives SMs x 64 FP64 lanes x 2 x the SM clock for comparison.
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b)
 {
-    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = threadIdx.x + k;
+#pragma unroll 16
     for (int i = 0; i < iters; i++) {
-        v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
-        v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = fma(v[k], a, b);
     }
-    out[blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += v[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int cintb200_fp64_peak_theoretical(int device, double sm_mhz, double *tflops)
+{
+    if (device >= 0) CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    const double mhz = sm_mhz > 0 ? sm_mhz : khz * 1e-3;
+    *tflops = prop.multiProcessorCount * 64.0 * 2.0 * mhz * 1e6 / 1e12;        // 64 FP64 FMA lanes per SM on sm_100
+    return 0;
 }
 
 extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
@@ -1043,7 +1111,7 @@ extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
     int dev;
     CUDA_OK(cudaGetDevice(&dev));
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
     double *buf;
     CUDA_OK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
@@ -1059,7 +1127,7 @@ extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
         CUDA_OK(cudaEventSynchronize(e1));
         float ms;
         CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
-        const double tf = 2.0 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        const double tf = 2.0 * 16 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
         if (tf > best) best = tf;
         spent += ms * 1e-3;
     }

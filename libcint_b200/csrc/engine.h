@@ -48,6 +48,7 @@ struct CINTOpt {
     int profile = 0;                    // record per-launch events in the whole-job driver
     std::vector<double> profile_rows;
     int force_generic = 0;              // tests: route every class through the generic kernel
+    int checksums = 0;                  // whole-job driver: reduce every tile to per-row sums (cintb200_set_checksums)
     std::mutex mtx;
 };
 

@@ -26,7 +26,12 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
                    long long ntasks, double *out, int *nonzero, unsigned long long *counters, cudaStream_t stream,
                    const TileParams *tile = nullptr, const long long *uprefix = nullptr);
 
-#define B200_PERSISTENT_BLOCKS (148 * 16)      // blocks per launch of the tile kernels (each walks many work items)
+// Grid of a persistent tile-kernel launch (engine.cu): raises the function's dynamic shared-memory limit when needed (fails with
+// -1 if `smem` exceeds what the device offers -- callers route such classes to the generic kernel) and returns
+// min(total work items, blocks per SM x number of SMs).  Blocks per SM: CINTB200_PBLOCKS (default 16: every block stages its
+// Rys table and then pulls work items from the launch's counter; "occ" = exactly the resident capacity of the function).
+int tile_grid_blocks(const void *fn, int threads, size_t smem, long long total);
+int tile_smem_limit();                        // largest dynamic shared memory per block the device allows (opt-in), bytes
 
 // register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
 typedef void (*RegKernelFn)(const TileParams);
@@ -35,8 +40,10 @@ int rys_tab_nint(int nroots);
 int rys_fast_nint(int nroots);
 int rys_fast_off(int nroots);
 int reg_kernel_launch(RegKernelFn fn, int nroots, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);
+size_t reg_kernel_smem(RegKernelFn fn, int nroots, int ncu, int umax);       // dynamic shared memory such a launch needs
 
 // cooperative kernels (kern_coop_inst*.cu): FS lanes per quartet
 struct CoopInfo { int fs, xsz, nroots; };
 RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info, int rs = 0);
 int coop_kernel_launch(RegKernelFn fn, const CoopInfo &info, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);
+size_t coop_kernel_smem(const CoopInfo &info, int ncu, int umax);

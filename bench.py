@@ -11,9 +11,11 @@ The integral count follows the reference driver (`tot = ncgto^4/8`, examples/tim
   python bench.py --impl reference --steps K --warmup W     the reference's CPU path on the host cores
 
 Keys beyond the base contract: `roofline` (FP64 FMA roofline of the dominant kernel class, measured live
-with CUDA events), `cpu_baseline` (oracle/_ref timed on a bounded sample), `e2e` (same job through the C ABI
-with every integral delivered to pinned HOST memory, context creation and host<->device copies inside the
-timed region), `gpu_launches`, `clocks`.
+with CUDA events), `cpu_baseline` (oracle/_ref timed on a bounded sample), `checksum` (one extra pass whose per-bra-pair
+fingerprints, all-reduced over the ranks, are compared with the reference goldens: every block of the job is value-checked),
+`e2e` (same job through the C ABI from HOST arrays to HOST results: context build, density matrix H2D, all kernels, J/K
+digestion on the device, all-reduce over the ranks, J and K D2H; `e2e.tiles_to_host` keeps the PCIe-bound variant that
+delivers every integral to pinned host memory through the ring of sinks), `gpu_launches`, `clocks`.
 """
 import argparse
 import json
@@ -145,6 +147,161 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+C2H6_BASES = (("c2h6_631g", "6-31G"), ("c2h6_6311gss", "6-311G**"), ("c2h6_ccpvdz", "cc-pVDZ"), ("c2h6_ccpvtz", "cc-pVTZ"), ("c2h6_ccpvqz", "cc-pVQZ"))
+
+
+def sweep_classes(lmax):
+    """Symmetry-unique angular classes (li >= lj, lk >= ll, (li,lj) >= (lk,ll)) for l = 0..lmax."""
+    pairs = [(a, b) for a in range(lmax + 1) for b in range(a + 1)]
+    return [(p[0], p[1], q[0], q[1]) for n, p in enumerate(pairs) for q in pairs[:n + 1]]
+
+
+def sweep_reps(cls, nctr, budget):
+    """Copies of one quartet per class: ~budget integrals of work, scaled down for high angular momentum."""
+    n = 1
+    for l in cls:
+        n *= (2 * l + 1) * nctr
+    return int(max(8, min(20000, budget / (n * (1 + sum(cls) / 2.0)))))
+
+
+def run_reference_sweep(atm, bas, env, rows, threads=None, affinity=None):
+    """oracle/_ref/time_ref in class-sweep mode: rows = [(i, j, k, l, reps)]; returns [(seconds, integrals per quartet)]."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "time_ref")
+    lib = os.path.join(ROOT, "oracle", "_ref", "libcint_ref.so")
+    if not (os.path.exists(exe) and os.path.exists(lib)):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        bb, lst = os.path.join(tmp, "basis.bin"), os.path.join(tmp, "list.txt")
+        dump_basis_bin(bb, np.asarray(atm), np.asarray(bas), np.asarray(env))
+        with open(lst, "w") as f:
+            for r in rows:
+                f.write("%d %d %d %d %d\n" % tuple(r))
+        e = dict(os.environ)
+        if threads:
+            e["OMP_NUM_THREADS"] = str(threads)
+        out = subprocess.run([exe, lib, bb, "sweep", lst], capture_output=True, text=True, env=e, timeout=1800,
+                             preexec_fn=(lambda: os.sched_setaffinity(0, affinity)) if affinity else None)
+        if out.returncode != 0:
+            return None
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        return [(r[5], r[6]) for r in j["rows"]], j["threads"]
+
+
+def extra_workloads(cb, torch, local, steps, cpu_threads, affinity, with_cpu):
+    """Secondary lines of the driver-run bench (rank 0, one GPU): BASELINE configs[0] (C2H6, five bases), configs[4]
+    (range-separated int2e_sph on C2H6 cc-pVTZ), configs[3] (class sweep s..h) and the list-mode batched entry point."""
+    out = {}
+    # ---- configs[0]: C2H6 full unique ERI tensor, five bases (examples/time_c2h6.c) ----
+    rows = {}
+    for name, label in C2H6_BASES:
+        atm, bas, env = cb.load_fixture(name)
+        c = cb.Context(atm, bas, env, device=local)
+        ms = []
+        for k in range(2 + steps):
+            st = c.all_unique(chunk_bytes=8 << 30)
+            ms.append(float(st[7]))
+        ms = sum(ms[2:]) / steps
+        tot = reference_count(bas)
+        rows[label] = {"value": tot / (ms * 1e-3), "ms": ms, "integrals_counted": tot, "shell_quartets": int(st[0]), "launches": int(st[4]),
+                       "model_tflops": float(st[6]) / (ms * 1e-3) / 1e12}
+        if with_cpu:
+            r = run_reference_sample(atm, bas, env, 1, 0, cpu_threads, affinity=affinity)
+            if r is not None:
+                rows[label]["cpu_baseline"] = {"value": r["integrals"] * (tot / max(1.0, float(st[1]))) / r["seconds"], "cores": r["threads"],
+                                               "kind": "reference", "sample": "the whole loop, %.2f s" % r["seconds"]}
+        c.close()
+    out["c2h6"] = {"unit": "integrals/s", "workload": "C2H6 int2e_sph, all unique shell quartets i>=j, k>=l, k<=i per step (examples/time_c2h6.c geometry and bases), "
+                   "device-resident tiles, CUDA events", "bases": rows}
+    # ---- configs[4]: range-separated Coulomb on C2H6 cc-pVTZ ----
+    atm, bas, env0 = cb.load_fixture("c2h6_ccpvtz")
+    tot = reference_count(bas)
+    rs = {}
+    for label, omega in (("full", 0.0), ("long_range_erf", 0.3), ("short_range_erfc", -0.3)):
+        env = env0.copy()
+        env[8] = omega
+        c = cb.Context(atm, bas, env, device=local)
+        ms = []
+        for k in range(2 + steps):
+            st = c.all_unique(chunk_bytes=8 << 30)
+            ms.append(float(st[7]))
+        ms = sum(ms[2:]) / steps
+        rs[label] = {"omega": omega, "value": tot / (ms * 1e-3), "ms": ms}
+        if with_cpu:
+            r = run_reference_sample(atm, bas, env, 1, 0, cpu_threads, affinity=affinity)
+            if r is not None:
+                rs[label]["cpu_baseline"] = {"value": r["integrals"] * (tot / max(1.0, float(st[1]))) / r["seconds"], "cores": r["threads"],
+                                             "kind": "reference", "sample": "the whole loop, %.2f s" % r["seconds"]}
+        c.close()
+    out["range_separated"] = {"unit": "integrals/s", "workload": "C2H6 cc-pVTZ int2e_sph with env[PTR_RANGE_OMEGA] = 0 / +0.3 / -0.3, all unique shell quartets", "cases": rs}
+    # ---- the batched entry point on explicit lists (cintb200_int2e_batch, device-resident packed output) ----
+    atm, bas, env = cb.load_fixture(WORKLOAD)
+    c = cb.Context(atm, bas, env, device=local)
+    rng = np.random.default_rng(7)
+    nq = 1000000
+    lists = {"random": rng.integers(0, len(bas), size=(nq, 4)).astype(np.int32)}
+    i = rng.integers(0, len(bas), size=nq // 1000)
+    j = rng.integers(0, len(bas), size=nq // 1000)
+    kl = rng.integers(0, len(bas), size=(1000, 2))
+    lists["structured"] = np.concatenate([np.column_stack([np.full(1000, a), np.full(1000, b), kl]) for a, b in zip(i, j)]).astype(np.int32)
+    dims = np.array([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])
+    lm = {}
+    for label, q in lists.items():
+        nint = int(np.prod(dims[q], axis=1).sum())
+        dbuf = torch.empty(nint, dtype=torch.float64, device="cuda")
+        ts = []
+        for k in range(1 + steps):
+            t0 = time.perf_counter()
+            c.int2e_batch(q, device_ptr=dbuf.data_ptr())
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        t = sum(ts[1:]) / steps
+        lm[label] = {"value": nint / t, "quartets_per_s": len(q) / t, "s_per_call": t, "quartets": len(q), "integrals": nint}
+        del dbuf
+    c.close()
+    out["list_mode"] = {"unit": "integrals/s", "workload": "cintb200_int2e_batch on 1e6 C60 cc-pVDZ shell quartets (random / 1000 bra pairs x 1000 kets), host shell list in, "
+                        "packed device-resident output, wall clock incl. the host-side sorting of the list", "cases": lm}
+    # ---- configs[3]: class sweep s..h, one contracted quartet (3 primitives x 2 contractions per shell) per class, many copies ----
+    from libcint_b200.basis import class_sweep_basis
+    lmax = 5
+    atm, bas, env = class_sweep_basis(lmax=lmax)
+    c = cb.Context(atm, bas, env, device=local)
+    classes = sweep_classes(lmax)
+    sw = []
+    ref_rows = []
+    for cls in classes:
+        sh = [cen * (lmax + 1) + l for cen, l in enumerate(cls)]
+        reps = sweep_reps(cls, 2, 4e8)
+        q = np.tile(np.array(sh, np.int32), (reps, 1))
+        n1 = int(np.prod([(2 * l + 1) * 2 for l in cls]))
+        dbuf = torch.empty(n1 * reps, dtype=torch.float64, device="cuda")
+        ts = []
+        for k in range(3):
+            t0 = time.perf_counter()
+            c.int2e_batch(q, device_ptr=dbuf.data_ptr())
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        del dbuf
+        t = min(ts[1:])
+        sw.append({"class": "(%s%s|%s%s)" % tuple("spdfgh"[l] for l in cls), "reps": reps, "value": n1 * reps / t, "us_per_quartet": 1e6 * t / reps})
+        ref_rows.append(tuple(sh) + (max(8, reps // 50),))
+    if with_cpu:
+        rr = run_reference_sweep(atm, bas, env, ref_rows, cpu_threads, affinity)
+        if rr is not None:
+            for row, (sec, n1), rrow in zip(sw, rr[0], ref_rows):
+                row["cpu_value"] = n1 * rrow[4] / sec
+                row["speedup"] = row["value"] / row["cpu_value"]
+            out_threads = rr[1]
+    c.close()
+    slow = sorted(sw, key=lambda r: r.get("speedup", 1e30))[:5]
+    out["class_sweep"] = {"unit": "integrals/s", "workload": "one contracted shell quartet per symmetry-unique angular class (li>=lj, lk>=ll, ij>=kl), l = s..h, 4 centres of "
+                          "testsuite/test_cint.py:51-58, 3 primitives x 2 contractions per shell; `reps` copies per class through cintb200_int2e_batch "
+                          "(device-resident output, wall clock incl. host list handling); cpu_value = the reference on the host cores, reps/50 copies",
+                          "classes": len(sw), "cpu_cores": out_threads if with_cpu and rr is not None else None,
+                          "geomean_speedup": float(np.exp(np.mean([np.log(r["speedup"]) for r in sw]))) if sw and "speedup" in sw[0] else None,
+                          "slowest_vs_cpu": slow, "rows": sw}
+    return out
+
+
 def reference_arm(args):
     """`--impl reference`: the reference's own CPU implementation on all host cores, bounded samples."""
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +354,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--e2e-steps", type=int, default=1, help="timed end-to-end steps (each moves ~505/N GB to the host)")
+    ap.add_argument("--e2e-steps", type=int, default=3, help="timed end-to-end steps (host arrays in, J/K out)")
+    ap.add_argument("--e2e-tile-steps", type=int, default=1, help="timed steps of the tiles-to-host variant (each moves ~505/N GB over PCIe; 0 = skip)")
+    ap.add_argument("--no-check", action="store_true", help="skip the whole-job checksum pass")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (C2H6, range-separated, list mode, class sweep)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-df", action="store_true", help="skip the secondary density-fitting workload (int3c2e)")
@@ -298,7 +458,8 @@ def main():
         roofline = {
             "bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
             "traffic_note": traffic_note,
-            "peak_source": "in-bench DFMA-chain microbenchmark on this GPU (MEASURED_PEAKS.json has no FP64 entry; B200 datasheet ~37-40)",
+            "peak_source": "in-bench DFMA microbenchmark on this GPU (16 chains, unrolled; MEASURED_PEAKS.json has no FP64 entry)",
+            "peak_theoretical": cb.fp64_peak_theoretical_tflops(local), "frac_of_theoretical": ach / cb.fp64_peak_theoretical_tflops(local),
             "kernel": "eri %s kernel, class (%d%d|%d%d) nct=%d ncu=%d" % (kinds[int(top[6])], top[0], top[1], top[2], top[3], top[4], top[5]),
             "kernel_share_of_step": top[7] / tot_ms,
             "kernel_ms_per_step": top[7], "kernel_launches_per_step": int(top[11]),
@@ -311,34 +472,95 @@ def main():
                           "note": "algorithmic store traffic only (8 B per integral written, per GPU)"},
         }
 
-    # ---------------- end to end: host arrays in, every integral delivered to pinned host memory ----------------
+    # ---------------- whole-job value check: fingerprints of EVERY bra pair, all-reduced over the ranks, vs the reference goldens ---
+    checksum = None
+    gold_path = os.path.join(ROOT, "tests", "golden", "job_%s.npz" % WORKLOAD)
+    if not args.no_check and os.path.exists(gold_path):
+        gold = np.load(gold_path)
+        ctx.set_checksums(True)
+        stc = ctx.all_unique(rank=rank, nranks=world, chunk_bytes=chunk)
+        ctx.set_checksums(False)
+        parts = torch.tensor(np.stack(ctx.job_checksums()), device="cuda")         # [3, npair]: S, A, F partial sums of this rank's kets
+        if dist is not None:
+            dist.all_reduce(parts, op=dist.ReduceOp.SUM)
+        S, A, F = parts.cpu().numpy()
+        scale = np.maximum(gold["A"], 1.0)
+        errs = {k: float((np.abs(v - gold[k]) / scale).max()) for k, v in (("S", S), ("A", A), ("F", F))}
+        checksum = {"ok": bool(max(errs.values()) <= 2e-12), "max_err_over_sum_abs": errs, "tolerance": 2e-12, "pairs": int(len(S)),
+                    "sum_all_integrals": sum_over_ranks(float(stc[3])), "golden_sum": float(gold["S"].sum()),
+                    "checksum_pass_ms": max_over_ranks(float(stc[7])),
+                    "golden": "tests/golden/job_%s.npz: per-bra-pair sums over all kets from the unmodified reference (oracle/ref_golden.c)" % WORKLOAD}
+
+    # ---------------- end to end: host arrays in, host results out (J/K digestion on the device) ----------------
     e2e = None
     if not args.no_e2e:
-        e2e_chunk = int(args.e2e_chunk_gb * (1 << 30))          # one bra shell x all kets of C60 needs 11.9 GB
-        sink = torch.empty(e2e_chunk // 8, dtype=torch.float64, pin_memory=True)
-        h2d = atm.nbytes + bas.nbytes + env.nbytes
+        nao = int(sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas))
+        _, _, Dm, Uprobe = cb.job_weights(nao)
+        dm_host = torch.from_numpy(np.ascontiguousarray(Dm)).pin_memory()
+        jk_host = torch.empty((2, nao, nao), dtype=torch.float64).pin_memory()
+        e2e_chunk = int(args.e2e_chunk_gb * (1 << 30))          # tiles-to-host variant: tile = pinned sink size
+        h2d = atm.nbytes + bas.nbytes + env.nbytes + dm_host.numel() * 8
 
         def e2e_step():
             c2 = cb.Context(atm, bas, env, device=local)          # host arrays -> device tables
-            s2 = c2.all_unique(rank=rank, nranks=world, chunk_bytes=e2e_chunk, host_sink=sink.data_ptr())
+            d_dm = dm_host.to("cuda", non_blocking=True)          # density matrix H2D from pinned memory
+            d_jk = torch.empty((2, nao, nao), dtype=torch.float64, device="cuda")
+            torch.cuda.current_stream().synchronize()
+            _, _, s2 = c2.jk(rank=rank, nranks=world, chunk_bytes=chunk, device_ptrs=(d_dm.data_ptr(), d_jk[0].data_ptr(), d_jk[1].data_ptr()))
+            if dist is not None:
+                dist.all_reduce(d_jk, op=dist.ReduceOp.SUM)       # the path's only collective: partial J/K of the ket shards
+            jk_host.copy_(d_jk)                                   # J, K D2H (every rank; rank 0's copy is the result)
+            torch.cuda.synchronize()
             c2.close()
             return s2
-        e2e_step()                                             # warm-up (pinned pages, plan)
+        e2e_step()                                             # warm-up
         barrier()
         t0 = time.perf_counter()
-        d2h = 0.0
         for _ in range(args.e2e_steps):
             s2 = e2e_step()
-            d2h += s2[5]
         barrier()
         e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
-        d2h_tot = sum_over_ranks(d2h / args.e2e_steps)
+        vj, vk = jk_host[0].numpy(), jk_host[1].numpy()
+        jk_ok = None
+        if os.path.exists(gold_path):
+            gold = np.load(gold_path)
+            jk_err = {k: float(np.abs(m @ Uprobe - gold[k + "U"]).max() / np.abs(gold[k + "U"]).max()) for k, m in (("J", vj), ("K", vk))}
+            jk_ok = {"ok": bool(max(jk_err.values()) <= 1e-11), "max_rel_err_of_probe_products": jk_err, "tolerance": 1e-11}
         e2e = {"value": tot / e2e_s, "unit": "integrals/s", "h2d_bytes_per_step": int(h2d * world),
-               "d2h_bytes_per_step": int(d2h_tot), "s_per_step": e2e_s, "d2h_gbs_per_gpu": d2h_tot / world / e2e_s / 1e9,
-               "host_numa_cpus": ("%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus)) if numa_cpus else "unchanged",
+               "d2h_bytes_per_step": int(2 * nao * nao * 8 * world), "s_per_step": e2e_s, "steps": args.e2e_steps,
+               "gpu_ms_per_step": max_over_ranks(float(s2[7])), "chunk_gb": args.chunk_gb,
+               "result": "Coulomb and exchange matrices J[a,b] = sum (ab|cd) D[c,d], K[a,c] = sum (ab|cd) D[b,d] of a fixed symmetric density, "
+                         "digested from the tiles on the device (cintb200_int2e_sph_jk), all-reduced over the ranks", "result_check": jk_ok,
+               "includes": "context build from host atm/bas/env, pair tables + plan upload, density matrix H2D from pinned memory, all ERI kernels, "
+                           "J/K digestion kernels, NCCL all-reduce of the partial J/K (N > 1), J and K D2H into pinned memory, context teardown"}
+        # the PCIe-bound variant: every integral delivered to pinned host memory through the ring of sinks
+        if args.e2e_tile_steps > 0:
+            sinks = [torch.empty(e2e_chunk // 8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            seen = []
 
-               "includes": "context build from host atm/bas/env + pair tables upload, all kernels, D2H of every tile into pinned host memory"}
-        del sink
+            def on_tile(info, values):
+                seen.append((info["chunk"], float(values[0, 0]), float(values[-1, -1])))       # the consumer: touch every tile
+
+            def tile_step():
+                c2 = cb.Context(atm, bas, env, device=local)
+                s3 = c2.all_unique_tiles([t.data_ptr() for t in sinks], on_tile, rank=rank, nranks=world, chunk_bytes=e2e_chunk)
+                c2.close()
+                return s3
+            tile_step()
+            barrier()
+            t0 = time.perf_counter()
+            d2h = 0.0
+            for _ in range(args.e2e_tile_steps):
+                s3 = tile_step()
+                d2h += s3[5]
+            barrier()
+            t_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_tile_steps)
+            d2h_tot = sum_over_ranks(d2h / args.e2e_tile_steps)
+            e2e["tiles_to_host"] = {"value": tot / t_s, "unit": "integrals/s", "s_per_step": t_s, "d2h_bytes_per_step": int(d2h_tot),
+                                    "d2h_gbs_per_gpu": d2h_tot / world / t_s / 1e9, "tiles_delivered_per_step": len(seen) // (1 + args.e2e_tile_steps),
+                                    "host_numa_cpus": ("%d CPUs local to the GPU (NVML affinity)" % len(numa_cpus)) if numa_cpus else "unchanged",
+                                    "includes": "context build, all kernels, D2H of every tile into a ring of two pinned sinks, per-tile callback"}
+            del sinks
 
     # ---------------- CPU baseline: the compiled reference on this box's cores (rank 0, N = 1 only) ----------------
     cpu = None
@@ -388,6 +610,7 @@ def main():
             sl = (0, 30, 0, 60, 0, len(bas), 0, len(bas))
             ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
             nint = int((ao[sl[1]] - ao[sl[0]]) * (ao[sl[3]] - ao[sl[2]]) * (ao[sl[5]] - ao[sl[4]]) * (ao[sl[7]] - ao[sl[6]]))
+            cb.release_cached_memory(local)                 # the 80 GB result tensor below comes from torch's allocator
             dbuf = torch.empty(nint, dtype=torch.float64, device="cuda")
             msb = []
             for _ in range(2 + args.steps):
@@ -405,6 +628,15 @@ def main():
             extra = extra or {}
             extra["int2e_block"] = {"error": str(e)[:200]}
 
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            cb.release_cached_memory(local)
+            extra = extra or {}
+            extra.update(extra_workloads(cb, torch, local, max(1, min(args.steps, 3)), len(orig_affinity), orig_affinity, not args.no_cpu))
+        except Exception as e:          # secondary lines only
+            extra = extra or {}
+            extra["extra_error"] = repr(e)[:300]
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "integrals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -414,7 +646,7 @@ def main():
                        "integrals_counted": tot, "integrals_written": produced, "parallelism": "kets dealt round-robin per pair class over %d GPU(s), no collective" % world,
                        "l2": "each step streams %.0f GB of output through L2 (>> 126 MB); pair tables (~20 MB) stay L2-resident by design" % (8 * produced / 1e9),
                        "chunk_gb": args.chunk_gb, "wall_ms_per_step": wall_ms},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(), "extra": extra,
         }
         print(json.dumps(line))

@@ -489,6 +489,13 @@ def fp64_peak_tflops(device=-1, seconds=0.5):
     return v.value
 
 
+def release_cached_memory(device=-1):
+    """Return the tile buffers cached in the device memory pool to the driver (cintb200_release_cached_memory)."""
+    lib = load_library()
+    lib.cintb200_release_cached_memory.argtypes = [ctypes.c_int]
+    return lib.cintb200_release_cached_memory(device)
+
+
 def fp64_peak_theoretical_tflops(device=-1, sm_mhz=0.0):
     """SMs x 64 FP64 lanes x 2 x clock (sm_mhz <= 0: maximum SM clock of the device)."""
     lib = load_library()

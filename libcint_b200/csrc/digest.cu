@@ -51,7 +51,7 @@ void digest_free(DigestState *d)
     if (!d) return;
     cudaFree(d->d_rowI); cudaFree(d->d_colK); cudaFree(d->d_colg); cudaFree(d->d_rowsums);
     cudaFree(d->d_rowinfo); cudaFree(d->d_colinfo); cudaFree(d->d_colc); cudaFree(d->d_cold); cudaFree(d->d_units); cudaFree(d->d_entries);
-    cudaFree(d->d_dm); cudaFree(d->d_Dab); cudaFree(d->d_Dcd); cudaFree(d->d_PA); cudaFree(d->d_PB);
+    cudaFree(d->d_dm); cudaFree(d->d_Dab); cudaFree(d->d_Dcd); b200_big_free(d->d_PA); b200_big_free(d->d_PB);
     cudaFree(d->d_Jp); cudaFree(d->d_Kp); cudaFree(d->d_jrow); cudaFree(d->d_jcol);
     delete d;
 }
@@ -146,53 +146,80 @@ struct JKArgs {
 // is needed and nothing is scattered.  Tile loads are coalesced (consecutive threads = consecutive rows of one column).
 // The partial sums go to private slots PA / PB[x][row] and are folded over the rows sharing a (or b) by jk_fold_kernel.
 // The Coulomb row part J'[a,b] += 2 s (ab|cd) D[c,d] rides along in the visit from the ket's first shell.
+#define JK_RPT 2                 // tile rows per thread: twice the loads in flight, the per-entry decoding shared by both
 template <int NX>
 __global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
 {
-    const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
-    const bool active = row < A.ld;
-    const int4 ri = active ? A.rowinfo[A.row0 + row] : make_int4(0, 0, -1, 0);
-    const int a = ri.x, b = ri.y, ij = ri.z;
-    const double fij = ri.w ? 0.5 : 1.0;
-    const int maxij = __reduce_max_sync(0xffffffffu, ij);
-    const double *trow = A.tile + (active ? row : 0);
-    double jr = 0.0;
+    const long long row0 = (long long)blockIdx.x * (128 * JK_RPT) + threadIdx.x;
+    bool active[JK_RPT];
+    int a[JK_RPT], b[JK_RPT], ij[JK_RPT];
+    double fij[JK_RPT], jr[JK_RPT];
+    const double *trow[JK_RPT];
+    int maxij = -1;
+#pragma unroll
+    for (int q = 0; q < JK_RPT; q++) {
+        const long long row = row0 + 128 * q;
+        active[q] = row < A.ld;
+        const int4 ri = active[q] ? A.rowinfo[A.row0 + row] : make_int4(0, 0, -1, 0);
+        a[q] = ri.x; b[q] = ri.y; ij[q] = ri.z; fij[q] = ri.w ? 0.5 : 1.0; jr[q] = 0.0;
+        trow[q] = A.tile + (active[q] ? row : 0);
+        maxij = max(maxij, ij[q]);
+    }
+    maxij = __reduce_max_sync(0xffffffffu, maxij);
     for (int u = A.ubeg + blockIdx.y; u < A.uend; u += gridDim.y) {
         const JKUnit un = A.units[u];
-        double kA[NX], kB[NX];
+        double kA[JK_RPT][NX], kB[JK_RPT][NX];
 #pragma unroll
-        for (int x = 0; x < NX; x++) kA[x] = kB[x] = 0.0;
+        for (int q = 0; q < JK_RPT; q++)
+#pragma unroll
+            for (int x = 0; x < NX; x++) kA[q][x] = kB[q][x] = 0.0;
         for (int e = un.ebeg; e < un.eend; e++) {
             const JKEntry en = A.entries[e];
             if (en.kl > maxij) break;                       // entries are sorted by kl: nothing further is valid for this warp
-            const bool valid = en.kl <= ij;
-            const double w = valid ? (en.kl == ij ? 0.5 * fij : fij) : 0.0;
+            bool valid[JK_RPT];
+            double w[JK_RPT];
+#pragma unroll
+            for (int q = 0; q < JK_RPT; q++) {
+                valid[q] = en.kl <= ij[q];
+                w[q] = valid[q] ? (en.kl == ij[q] ? 0.5 * fij[q] : fij[q]) : 0.0;
+            }
             const int dy = en.info & 255, dk = (en.info >> 8) & 255, xk = en.info >> 16;
             const long long sx = (xk ? 1 : dk) * A.ld, sy = (xk ? dk : 1) * A.ld;
-            const double *t0 = trow + (long long)en.colbase * A.ld;
+            const long long o0 = (long long)en.colbase * A.ld;
             for (int y = 0; y < dy; y++) {
                 const double *Dy = A.dm + (size_t)(en.aoY + y) * A.nao;
-                const double dA = Dy[a], dB = Dy[b];
-                const double *ty = t0 + y * sy;
+                double v[JK_RPT][NX];
 #pragma unroll
-                for (int x = 0; x < NX; x++) {
-                    const double v = valid ? ty[x * sx] : 0.0;      // never read entries the ERI kernels did not write
-                    const double vw = v * w;
-                    kA[x] = fma(vw, dB, kA[x]);
-                    kB[x] = fma(vw, dA, kB[x]);
-                    if (xk) jr = fma(vw, A.Dcd[en.colbase + x + y * dk], jr);
+                for (int q = 0; q < JK_RPT; q++)
+#pragma unroll
+                    for (int x = 0; x < NX; x++) v[q][x] = valid[q] ? trow[q][o0 + y * sy + x * sx] : 0.0;   // never read unwritten entries
+#pragma unroll
+                for (int q = 0; q < JK_RPT; q++) {
+                    const double dA = w[q] * Dy[a[q]], dB = w[q] * Dy[b[q]];
+#pragma unroll
+                    for (int x = 0; x < NX; x++) {
+                        kA[q][x] = fma(v[q][x], dB, kA[q][x]);
+                        kB[q][x] = fma(v[q][x], dA, kB[q][x]);
+                        if (xk) jr[q] = fma(v[q][x] * w[q], A.Dcd[en.colbase + x + y * dk], jr[q]);
+                    }
                 }
             }
         }
-        if (active && A.want_k) {
+        if (A.want_k) {
 #pragma unroll
-            for (int x = 0; x < NX; x++) {
-                A.PA[(size_t)(un.ao0 + x) * A.ldP + row] = kA[x];
-                A.PB[(size_t)(un.ao0 + x) * A.ldP + row] = kB[x];
-            }
+            for (int q = 0; q < JK_RPT; q++)
+                if (active[q]) {
+#pragma unroll
+                    for (int x = 0; x < NX; x++) {
+                        A.PA[(size_t)(un.ao0 + x) * A.ldP + row0 + 128 * q] = kA[q][x];
+                        A.PB[(size_t)(un.ao0 + x) * A.ldP + row0 + 128 * q] = kB[q][x];
+                    }
+                }
         }
     }
-    if (active && jr != 0.0) atomicAdd(A.jrow + A.row0 + row, jr);
+#pragma unroll
+    for (int q = 0; q < JK_RPT; q++)
+        if (active[q] && jr[q] != 0.0) atomicAdd(A.jrow + A.row0 + row0 + 128 * q, jr[q]);
 }
 
 // K'[a, x] += sum over the chunk's rows with first AO a of PA[x][row];  K'[b, x] += ... PB[x][row].  One block per x.
@@ -337,8 +364,8 @@ static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
         cudaMalloc((void **)&d->d_Dcd, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
         cudaMalloc((void **)&d->d_jrow, sizeof(double) * std::max<long long>(1, d->nrows)) != cudaSuccess ||
         cudaMalloc((void **)&d->d_jcol, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_PA, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_PB, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)) != cudaSuccess)
+        b200_big_alloc((void **)&d->d_PA, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)) ||
+        b200_big_alloc((void **)&d->d_PB, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)))
         return b200_fail(CINTB200_ENOMEM, "J/K digestion: cannot allocate the work arrays (%zu bytes of row partials)", 2 * sizeof(double) * (size_t)nao * d->ldmax);
     d->jk_ready = 1;
     return 0;
@@ -406,7 +433,7 @@ int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, cons
         JKArgs A;
         A.tile = tile; A.ld = ld; A.row0 = row0; A.nao = d->nao; A.rowinfo = d->d_rowinfo; A.units = d->d_units; A.entries = d->d_entries;
         A.dm = d->d_dm; A.Dcd = d->d_Dcd; A.PA = d->d_PA; A.PB = d->d_PB; A.jrow = d->d_jrow; A.ldP = d->ldmax; A.want_k = job.want_k;
-        const unsigned gx = (unsigned)((ld + 127) / 128);
+        const unsigned gx = (unsigned)((ld + 128 * JK_RPT - 1) / (128 * JK_RPT));
         for (int nx = 1; nx <= JK_NXMAX; nx++) {
             A.ubeg = d->unit_beg[nx]; A.uend = d->unit_beg[nx + 1];
             if (A.uend <= A.ubeg) continue;

@@ -45,8 +45,8 @@ void jobplan_free(JobPlan *p)
         cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
         cudaFree(c.d_tq); cudaFree(c.dB_tq); cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
     }
-    if (p->own_out) cudaFree(p->d_out[0]);
-    cudaFree(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
+    if (p->own_out) b200_big_free(p->d_out[0]);
+    b200_big_free(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (int k = 0; k < JobPlan::NS; k++) { if (p->streams[k]) cudaStreamDestroy(p->streams[k]); if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -348,7 +348,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     }
     if (plan->host_only) return 0;
     // one tile buffer; the second one (overlap of D2H with the next chunk's kernels) is allocated on first use of a host sink
-    if (cudaMalloc((void **)&plan->d_out[0], sizeof(double) * need) != cudaSuccess)
+    if (b200_big_alloc((void **)&plan->d_out[0], sizeof(double) * need))
         return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
     CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
@@ -507,7 +507,9 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
         if (sink.nsinks < 1) return b200_fail(CINTB200_EINVAL, "host sinks given but nsinks = %d", sink.nsinks);
         for (int k = 0; k < sink.nsinks; k++) if (!sink.sinks[k]) return b200_fail(CINTB200_EINVAL, "host sink %d is NULL", k);
     } else if (sink.fn) return b200_fail(CINTB200_EINVAL, "a tile callback needs at least one host sink");
+    double tph = b200_now();
     if (ncenter == 4 && c->schwarz_thr > 0 && c->omega == 0 && !c->force_generic && ctx_compute_schwarz(c)) return CINTB200_ENODEV;
+    b200_phase("job: schwarz bounds", tph);
     std::lock_guard<std::mutex> lock(c->mtx);
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
@@ -521,17 +523,24 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
         plan = new JobPlan();
         plan->ncenter = ncenter; plan->aux0 = (ncenter == 3) ? aux0 : 0;
         plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic; plan->schwarz_thr = c->schwarz_thr;
+        tph = b200_now();
         int rc = build_plan(c, plan);
+        b200_phase("job: build_plan", tph);
+        tph = b200_now();
         if (!rc) rc = build_launches(c, plan);
+        b200_phase("job: build_launches", tph);
         if (rc) { jobplan_free(plan); return rc; }
         c->plan = plan;
     }
-    if (sink.sinks && !plan->d_out[1] && cudaMalloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles) != cudaSuccess)
+    if (sink.sinks && !plan->d_out[1] && b200_big_alloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles))
         return b200_fail(CINTB200_ENOMEM, "cannot allocate the second %zu-byte tile buffer", sizeof(double) * plan->out_doubles);
     if (sink.sinks && plan->out_doubles * sizeof(double) > chunk_bytes)
         return b200_fail(CINTB200_EINVAL, "host sinks: the largest tile (one bra shell x all of this rank's kets) needs %zu bytes, "
                          "chunk_bytes = %zu is too small", plan->out_doubles * sizeof(double), chunk_bytes);
-    return execute_plan(c, plan, ncenter, sink, stats);
+    tph = b200_now();
+    const int rc_exec = execute_plan(c, plan, ncenter, sink, stats);
+    b200_phase("job: execute", tph);
+    return rc_exec;
 }
 
 // Launch every kernel of a plan (all chunks); finished tiles go to the device-side consumers and / or to the host sinks.
@@ -1176,7 +1185,7 @@ static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntr
             return CINTB200_ENOMEM;
     }
     if (dev_out) { plan->d_out[0] = dev_out; plan->own_out = 0; }
-    else if (cudaMalloc((void **)&plan->d_out[0], sizeof(double) * std::max<size_t>(1, plan->out_doubles)) != cudaSuccess)
+    else if (b200_big_alloc((void **)&plan->d_out[0], sizeof(double) * std::max<size_t>(1, plan->out_doubles)))
         return b200_fail(CINTB200_ENOMEM, "cannot allocate the %zu-byte block buffer", sizeof(double) * plan->out_doubles);
     CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdarg>
+#include <ctime>
 #include <vector>
 #include <map>
 #include <mutex>
@@ -48,6 +49,15 @@ int b200_fail(int code, const char *fmt, ...)
     return b200_fail(CINTB200_ENODEV, "%s failed: %s", #call, cudaGetErrorString(e_)); } while (0)
 
 extern "C" const char *cintb200_last_error(void) { return g_err; }
+
+double b200_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+bool b200_timing() { static const bool on = getenv("CINTB200_TIMING") && atoi(getenv("CINTB200_TIMING")); return on; }
+void b200_phase(const char *what, double t0) { if (b200_timing()) fprintf(stderr, "[cintb200 timing] %-28s %8.2f ms\n", what, 1e3 * (b200_now() - t0)); }
 
 // ------------------------------------------------------------------ shell helpers (src/cint_bas.c)
 extern "C" {
@@ -127,8 +137,11 @@ static uint64_t basis_hash(const int *atm, int natm, const int *bas, int nbas, c
 
 static int g_constants_ready_dev[64];
 
+static std::mutex g_constants_mtx;
+
 static int setup_device_constants(int dev)
 {
+    std::lock_guard<std::mutex> lock(g_constants_mtx);       // contexts may be created from several threads at once
     if (dev < 64 && g_constants_ready_dev[dev]) return 0;
     RysMeta meta;
     memset(&meta, 0, sizeof meta);
@@ -305,15 +318,22 @@ extern "C" int cintb200_create(cintb200_ctx **out, const int *atm, int natm, con
     if (e != cudaSuccess || ndev == 0)
         return b200_fail(CINTB200_ENODEV, "no CUDA device available (%s); this library has no CPU path",
                          e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    if (device < 0) CUDA_OK(cudaGetDevice(&device));
+    int caller_dev = -1;
+    CUDA_OK(cudaGetDevice(&caller_dev));
+    if (device < 0) device = caller_dev;
     if (device >= ndev) return b200_fail(CINTB200_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    struct RestoreDevice { int d; ~RestoreDevice() { if (d >= 0) cudaSetDevice(d); } } restore{device != caller_dev ? caller_dev : -1};
     CUDA_OK(cudaSetDevice(device));
     if (setup_device_constants(device)) return CINTB200_ENODEV;
     CINTOpt *c = NULL;
+    double t0 = b200_now();
     int rc = ctx_new_host(&c, atm, natm, bas, nbas, env);
     if (rc) return rc;
+    b200_phase("context: pair tables (host)", t0);
     c->device = device;
+    t0 = b200_now();
     rc = ctx_upload(c);
+    b200_phase("context: upload", t0);
     if (rc) { cintb200_destroy(c); return rc; }
     *out = c;
     return 0;
@@ -833,23 +853,56 @@ extern "C" int cintb200_schwarz_bounds(cintb200_ctx *c, double *q)
 static std::mutex g_cache_mtx;
 static std::vector<CINTOpt *> g_cache;
 
-static CINTOpt *context_for(CINTOpt *opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
+// RAII holder of a context used by one drop-in call: cached contexts are reference-counted, so that the eviction of the
+// least-recently-used entry can never destroy a context another thread is still inside (concurrent callers with
+// opt == NULL on different molecules, examples/time_c60.c:196-219 style OpenMP loops).
+struct CtxRef {
+    CINTOpt *c = nullptr;
+    bool counted = false;
+    ~CtxRef() { if (c && counted) c->users.fetch_sub(1); }
+};
+
+static void context_for(CtxRef &ref, CINTOpt *opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env)
 {
     const uint64_t h = basis_hash(atm, natm, bas, nbas, env);
-    if (opt && opt->magic == B200_CTX_MAGIC && opt->hash == h) return opt;
+    if (opt && opt->magic == B200_CTX_MAGIC && opt->hash == h) { ref.c = opt; return; }      // the caller's own optimizer: caller keeps it alive
     std::lock_guard<std::mutex> lock(g_cache_mtx);
     for (size_t i = 0; i < g_cache.size(); i++)
         if (g_cache[i]->hash == h) {
             CINTOpt *c = g_cache[i];
             g_cache.erase(g_cache.begin() + i);
             g_cache.push_back(c);
-            return c;
+            c->users.fetch_add(1);
+            ref.c = c; ref.counted = true;
+            return;
         }
     CINTOpt *c = NULL;
-    if (cintb200_create(&c, atm, natm, bas, nbas, env, -1)) return NULL;
-    if (g_cache.size() >= 8) { cintb200_destroy(g_cache.front()); g_cache.erase(g_cache.begin()); }
+    if (cintb200_create(&c, atm, natm, bas, nbas, env, -1)) return;
+    // evict the least-recently-used IDLE context once more than 8 are cached (busy ones stay: the cache may grow for a while)
+    for (size_t i = 0; g_cache.size() >= 8 && i < g_cache.size();) {
+        if (g_cache[i]->users.load() == 0) { cintb200_destroy(g_cache[i]); g_cache.erase(g_cache.begin() + i); }
+        else i++;
+    }
+    c->users.fetch_add(1);
     g_cache.push_back(c);
-    return c;
+    ref.c = c; ref.counted = true;
+}
+
+// failed drop-in call: the reference cannot fail; hand back a zero block (what it does for screened-out blocks) and 0,
+// the reason stays in cintb200_last_error() / on stderr
+static CACHE_SIZE_T drop_in_failed(double *out, const FINT *dims, const FINT *shls, const FINT *bas, int ncenter, int cart, int ncomp)
+{
+    if (!out) return 0;
+    size_t d[4] = {1, 1, 1, 1};
+    for (int m = 0; m < ncenter; m++) d[m] = cart ? CINTcgto_cart(shls[m], bas) : CINTcgto_spheric(shls[m], bas);
+    if (!dims) { memset(out, 0, sizeof(double) * ncomp * d[0] * d[1] * d[2] * d[3]); return 0; }
+    const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1, nl = (ncenter > 3) ? dims[3] : 1;
+    for (int comp = 0; comp < ncomp; comp++)
+        for (size_t l = 0; l < d[3]; l++)
+            for (size_t k = 0; k < d[2]; k++)
+                for (size_t j = 0; j < d[1]; j++)
+                    memset(out + comp * ni * nj * nk * nl + ni * (j + nj * (k + nk * l)), 0, sizeof(double) * d[0]);
+    return 0;
 }
 
 static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm,
@@ -862,23 +915,24 @@ static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT
         for (int m = 0; m < ncenter; m++) n *= CINTcgto_cart(shls[m], bas);
         return (CACHE_SIZE_T)n;
     }
-    CINTOpt *c = context_for(opt, atm, natm, bas, nbas, env);
-    if (!c) return 0;
     const int cart = (kind == CINTB200_CART);
-    size_t d[4] = {1, 1, 1, 1};
-    for (int m = 0; m < ncenter; m++) {
+    for (int m = 0; m < ncenter; m++)
         if (shls[m] < 0 || shls[m] >= nbas) { b200_fail(CINTB200_EINVAL, "shell id %d out of range", shls[m]); return 0; }
-        d[m] = shell_dim(c->shells[shls[m]], cart);
-    }
+    CtxRef ref;
+    context_for(ref, opt, atm, natm, bas, nbas, env);
+    CINTOpt *c = ref.c;
+    if (!c) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 1);
+    size_t d[4] = {1, 1, 1, 1};
+    for (int m = 0; m < ncenter; m++) d[m] = shell_dim(c->shells[shls[m]], cart);
     const size_t len = d[0] * d[1] * d[2] * d[3];
     int nz = 0;
     if (!dims) {
         long rc = run_batch(c, ncenter, kind, shls, 1, NULL, out, 0, &nz);
-        return rc < 0 ? 0 : nz;
+        return rc < 0 ? drop_in_failed(out, dims, shls, bas, ncenter, cart, 1) : nz;
     }
     std::vector<double> tmp(len);
     long rc = run_batch(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz);
-    if (rc < 0) return 0;
+    if (rc < 0) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 1);
     // embed into the caller's larger tensor: leading dimensions dims[] (src/cint2e.c:853-856)
     const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1;
     for (size_t l = 0; l < d[3]; l++)
@@ -897,23 +951,24 @@ static CACHE_SIZE_T drop_in_ip1(int ncenter, int kind, double *out, FINT *dims, 
         for (int m = 0; m < ncenter; m++) n *= CINTcgto_cart(shls[m], bas);
         return (CACHE_SIZE_T)n;
     }
-    CINTOpt *c = context_for(opt, atm, natm, bas, nbas, env);
-    if (!c) return 0;
     const int cart = (kind == CINTB200_CART);
-    size_t d[4] = {1, 1, 1, 1};
-    for (int m = 0; m < ncenter; m++) {
+    for (int m = 0; m < ncenter; m++)
         if (shls[m] < 0 || shls[m] >= nbas) { b200_fail(CINTB200_EINVAL, "shell id %d out of range", shls[m]); return 0; }
-        d[m] = shell_dim(c->shells[shls[m]], cart);
-    }
+    CtxRef ref;
+    context_for(ref, opt, atm, natm, bas, nbas, env);
+    CINTOpt *c = ref.c;
+    if (!c) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 3);
+    size_t d[4] = {1, 1, 1, 1};
+    for (int m = 0; m < ncenter; m++) d[m] = shell_dim(c->shells[shls[m]], cart);
     const size_t len = d[0] * d[1] * d[2] * d[3];
     int nz = 0;
     if (!dims) {
         long rc = run_batch_ip(c, ncenter, dpos, kind, shls, 1, NULL, out, 0, &nz);
-        return rc < 0 ? 0 : nz;
+        return rc < 0 ? drop_in_failed(out, dims, shls, bas, ncenter, cart, 3) : nz;
     }
     std::vector<double> tmp(3 * len);
     long rc = run_batch_ip(c, ncenter, dpos, kind, shls, 1, NULL, tmp.data(), 0, &nz);
-    if (rc < 0) return 0;
+    if (rc < 0) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 3);
     const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1, nl = (ncenter > 3) ? dims[3] : 1;
     for (size_t comp = 0; comp < 3; comp++)
         for (size_t l = 0; l < d[3]; l++)
@@ -1023,6 +1078,79 @@ int rys_tab_off(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_T
 int rys_fast_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_NINT[nroots] : 0; }
 int rys_fast_off(int nroots) { return (nroots >= 1 && nroots <= RYS_FNMAX) ? RYS_FAST_OFF[nroots] : 0; }
 
+// ------------------------------------------------------------------ large device buffers
+// Tile buffers and digestion partials come from the device's stream-ordered memory pool with the release threshold raised:
+// a destroyed context's buffers are then reused by the next context instead of being unmapped and mapped again (measured:
+// cudaFree of the 80 GB tile buffer 0.94 s, cudaMalloc ~0.1 s -- per context, which is per geometry step for a caller).
+// cintb200_release_cached_memory() hands the cached memory back to the driver.
+static std::mutex g_big_mtx;
+static std::map<void *, int> g_big_pooled;            // pointer -> device, for buffers that came from the pool
+static std::map<int, cudaStream_t> g_big_stream;
+
+static cudaStream_t big_stream(int dev)
+{
+    auto it = g_big_stream.find(dev);
+    if (it != g_big_stream.end()) return it->second;
+    cudaStream_t s = nullptr;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) s = nullptr;
+    }
+    cudaGetLastError();
+    g_big_stream[dev] = s;
+    return s;
+}
+
+int b200_big_alloc(void **p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_big_mtx);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaStream_t s = big_stream(dev);
+    *p = nullptr;
+    for (int attempt = 0; s && attempt < 2; attempt++) {
+        if (cudaMallocAsync(p, bytes ? bytes : 1, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess) {
+            g_big_pooled[*p] = dev;
+            return 0;
+        }
+        cudaGetLastError();
+        *p = nullptr;
+        cudaMemPool_t pool;                         // out of memory with cached blocks of the wrong sizes: trim and retry once
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) break;
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+    *p = nullptr;
+    return cudaMalloc(p, bytes ? bytes : 1) == cudaSuccess ? 0 : -1;
+}
+
+void b200_big_free(void *p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lock(g_big_mtx);
+    auto it = g_big_pooled.find(p);
+    if (it == g_big_pooled.end()) { cudaFree(p); return; }
+    cudaStream_t s = big_stream(it->second);
+    g_big_pooled.erase(it);
+    cudaDeviceSynchronize();                        // every consumer of the buffer has finished (callers free at teardown only)
+    cudaFreeAsync(p, s);
+    cudaStreamSynchronize(s);
+}
+
+extern "C" int cintb200_release_cached_memory(int device)
+{
+    std::lock_guard<std::mutex> lock(g_big_mtx);
+    int dev = device;
+    if (dev < 0) cudaGetDevice(&dev);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return b200_fail(CINTB200_ENODEV, "no memory pool on device %d", dev);
+    cudaDeviceSynchronize();
+    return cudaMemPoolTrimTo(pool, 0) == cudaSuccess ? 0 : b200_fail(CINTB200_ENODEV, "cudaMemPoolTrimTo failed");
+}
+
 // ------------------------------------------------------------------ launch geometry of the persistent tile kernels
 int tile_smem_limit()
 {
@@ -1048,7 +1176,7 @@ int tile_grid_blocks(const void *fn, int threads, size_t smem, long long total)
     cudaGetDevice(&dev);
     if (per_sm < 0) {
         const char *e = getenv("CINTB200_PBLOCKS");
-        per_sm = (e && !strcmp(e, "occ")) ? 0 : (e && atoi(e) > 0) ? atoi(e) : 16;
+        per_sm = (e && atoi(e) > 0) ? atoi(e) : 0;       // measured on C60: occupancy-sized 1137 ms, 4/SM 1143, 8/SM 1150, 16/SM 1156, 32/SM 1171
     }
     int &sms = sm_count[dev];
     if (!sms && (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)) sms = 148;

@@ -2,6 +2,7 @@
 #pragma once
 #include <vector>
 #include <mutex>
+#include <atomic>
 #include <cuda_runtime.h>
 #include "types.h"
 
@@ -50,6 +51,7 @@ struct CINTOpt {
     int force_generic = 0;              // tests: route every class through the generic kernel
     int checksums = 0;                  // whole-job driver: reduce every tile to per-row sums (cintb200_set_checksums)
     std::mutex mtx;
+    std::atomic<int> users{0};          // drop-in calls currently inside this context (cached contexts only; eviction waits for 0)
 };
 
 struct JobPlan;
@@ -60,4 +62,11 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
 int ctx_compute_schwarz(CINTOpt *c);
 int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);
+// CINTB200_TIMING=1: host-phase timings on stderr (context build, plan build, job execution)
+double b200_now();
+bool b200_timing();
+void b200_phase(const char *what, double t0);
 int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_host);
+// large device buffers from the stream-ordered pool (kept across contexts; engine.cu)
+int b200_big_alloc(void **p, size_t bytes);
+void b200_big_free(void *p);

@@ -28,8 +28,8 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
 
 // Grid of a persistent tile-kernel launch (engine.cu): raises the function's dynamic shared-memory limit when needed (fails with
 // -1 if `smem` exceeds what the device offers -- callers route such classes to the generic kernel) and returns
-// min(total work items, blocks per SM x number of SMs).  Blocks per SM: CINTB200_PBLOCKS (default 16: every block stages its
-// Rys table and then pulls work items from the launch's counter; "occ" = exactly the resident capacity of the function).
+// min(total work items, blocks per SM x number of SMs).  Blocks per SM: exactly the resident capacity of the function (every
+// block stages its Rys table once and then pulls work items from the launch's counter); CINTB200_PBLOCKS=n forces n per SM.
 int tile_grid_blocks(const void *fn, int threads, size_t smem, long long total);
 int tile_smem_limit();                        // largest dynamic shared memory per block the device allows (opt-in), bytes
 

@@ -7,6 +7,8 @@
  *   - only every `stride`-th ij pair (offset `phase`) is evaluated so the run is a bounded sample;
  *   - one buffer per thread instead of malloc/free per quartet (the library call is what is timed).
  * usage: time_ref <lib.so> <basis.bin> <stride> <phase> [aux_shell0]
+ *        time_ref <lib.so> <basis.bin> sweep <list.txt>     class sweep (BASELINE config 4): every line "i j k l reps" of the list
+ *                 is timed as `reps` calls of int2e_sph on that shell quartet spread over the OpenMP threads (optimizer on)
  * With aux_shell0 > 0 the density-fitting loop is timed instead: int3c2e_sph for every `stride`-th orbital shell pair
  * i >= j < aux_shell0 and ALL auxiliary shells k >= aux_shell0 (the loop shape of cintb200_int3c2e_sph_all).
  */
@@ -38,6 +40,40 @@ int main(int argc, char **argv)
         if (fread(bas, sizeof(int), nbas * 8, f) != (size_t)nbas * 8) return 1;
         if (fread(env, sizeof(double), nenv, f) != (size_t)nenv) return 1;
         fclose(f);
+        if (argv[3][0] == 's') {          /* class sweep */
+                FILE *lf = fopen(argv[4], "r");
+                if (!lf) { fprintf(stderr, "cannot read %s\n", argv[4]); return 1; }
+                int md = 0;
+                for (int i = 0; i < nbas; i++) { int d = (2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3]; if (d > md) md = d; }
+                void *opts = NULL;
+                optim(&opts, atm, natm, bas, nbas, env);
+                int q[4];
+                long reps;
+                printf("{\"threads\": %d, \"rows\": [", omp_get_max_threads());
+                int first = 1;
+                while (fscanf(lf, "%d %d %d %d %ld", &q[0], &q[1], &q[2], &q[3], &reps) == 5) {
+                        double chk = 0;
+                        double t0 = omp_get_wtime();
+#pragma omp parallel reduction(+ : chk)
+                        {
+                                double *buf = malloc(sizeof(double) * (size_t)md * md * md * md);
+#pragma omp for schedule(static)
+                                for (long r = 0; r < reps; r++) {
+                                        int shls[4] = {q[0], q[1], q[2], q[3]};
+                                        intor(buf, NULL, shls, atm, natm, bas, nbas, env, opts, NULL);
+                                        chk += buf[0];
+                                }
+                                free(buf);
+                        }
+                        double t1 = omp_get_wtime();
+                        long n = 1;
+                        for (int m = 0; m < 4; m++) n *= (2 * bas[q[m] * 8 + 1] + 1) * bas[q[m] * 8 + 3];
+                        printf("%s[%d,%d,%d,%d,%ld,%.6e,%ld,%.6e]", first ? "" : ",", q[0], q[1], q[2], q[3], reps, t1 - t0, n, chk);
+                        first = 0;
+                }
+                printf("]}\n");
+                return 0;
+        }
         long stride = atol(argv[3]), phase = atol(argv[4]);
         int aux0 = (argc > 5) ? atoi(argv[5]) : 0;
         if (aux0 > 0) {

@@ -199,7 +199,7 @@ def test_c60_full_job_through_host_tiles():
     name = "c60_ccpvdz"
     atm, bas, env = cb.load_fixture(name)
     gold = golden(name)
-    chunk = 8 << 30
+    chunk = 12 << 30                         # one bra shell x all kets of C60 is an 11.9 GB tile
     sinks = pinned_sinks(2, chunk)
     ctx = cb.Context(atm, bas, env)
     S, F, st, nt = host_fingerprints(ctx, bas, sinks, chunk_bytes=chunk)

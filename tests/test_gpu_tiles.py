@@ -127,9 +127,9 @@ def test_range_separated_density_fitting_and_blocks():
 
 def test_tiles_multi_chunk():
     # tiny chunk budget -> many chunks through the ring of sinks; every chunk is verified by value (1, 2 and 3 sinks)
-    check_job("c2h6_ccpvdz", chunk_bytes=200_000)
-    check_job("c2h6_631g", chunk_bytes=60_000, nsinks=1)
-    check_job("c2h6_631g", chunk_bytes=60_000, nsinks=3, nranks=2)
+    check_job("c2h6_ccpvdz", chunk_bytes=3_000_000)          # the largest tile (one bra shell x all kets) is 2.45 MB
+    check_job("c2h6_631g", chunk_bytes=400_000, nsinks=1)
+    check_job("c2h6_631g", chunk_bytes=400_000, nsinks=3, nranks=2)
 
 
 def test_c60_job_statistics_and_sample():

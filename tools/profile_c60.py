@@ -13,5 +13,5 @@ tot = rows[:, 7].sum()
 print("total %.1f ms (events sum %.1f) model %.3e flop" % (st[7], tot, st[6]))
 print("class nct ncu kind      ms    %%   quartets   primq   GFLOP/s(model)  ns/primq  launches")
 for r in sorted(rows, key=lambda r: -r[7]):
-    print("(%d%d|%d%d) %d %d %s %9.2f %5.1f %9.3g %9.3g %9.1f %9.3f %5d" % (r[0], r[1], r[2], r[3], r[4], r[5], "reg" if r[6] else "GEN",
+    print("(%d%d|%d%d) %d %d %s %9.2f %5.1f %9.3g %9.3g %9.1f %9.3f %5d" % (r[0], r[1], r[2], r[3], r[4], r[5], {0: "GEN", 1: "reg", 2: "coop"}[int(r[6])],
           r[7], 100 * r[7] / tot, r[8], r[9], r[10] / r[7] / 1e6, r[7] * 1e6 / max(r[9], 1), r[11]))

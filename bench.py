@@ -493,6 +493,7 @@ def main():
 
     # ---------------- end to end: host arrays in, host results out (J/K digestion on the device) ----------------
     e2e = None
+    ctx.close()                                 # the end-to-end steps build their own contexts (and their own 80 GB tiles)
     if not args.no_e2e:
         nao = int(sum((2 * int(b[1]) + 1) * int(b[3]) for b in bas))
         _, _, Dm, Uprobe = cb.job_weights(nao)
@@ -579,7 +580,6 @@ def main():
     extra = None
     if not args.no_df:
         from libcint_b200.basis import c60_df_basis
-        ctx.close()
         a3, b3, e3, norb = c60_df_basis()
         c3 = cb.Context(a3, b3, e3, device=local)
         for _ in range(3):

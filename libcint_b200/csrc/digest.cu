@@ -472,6 +472,8 @@ int digest_end(CINTOpt *c, JobPlan *plan, const DigestJob &job, double *vj_dev, 
     return 0;
 }
 
+void digest_mark_rowsums(JobPlan *plan) { if (plan->digest) plan->digest->have_rowsums = 1; }
+
 // Per-bra-pair fingerprints of the last run with checksums on (this rank's partial sums over its kets):
 //   S[p] = sum v, A[p] = sum |v|, F[p] = sum v h(row position) g(c,d)      -- definitions in oracle/ref_golden.c
 int digest_fetch_checksums(CINTOpt *c, JobPlan *plan, double *S, double *A, double *F, double *total)

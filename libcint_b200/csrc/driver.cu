@@ -39,12 +39,7 @@ extern const int *engine_c2s_off();
 void jobplan_free(JobPlan *p)
 {
     if (!p) return;
-    for (PairClass &c : p->uclasses) { cudaFree(c.d_tpair); cudaFree(c.d_tI); cudaFree(c.d_ucol); cudaFree(c.d_ustride); }
-    for (PairClass &c : p->classes) {
-        cudaFree(c.d_tprim); cudaFree(c.d_tgeom); cudaFree(c.d_trow); cudaFree(c.d_ucol);
-        cudaFree(c.d_tstride); cudaFree(c.d_tI); cudaFree(c.d_tpair); cudaFree(c.d_ustride); cudaFree(c.d_tnpp);
-        cudaFree(c.d_tq); cudaFree(c.dB_tq); cudaFree(c.dB_tprim); cudaFree(c.dB_tgeom); cudaFree(c.dB_trow); cudaFree(c.dB_tstride); cudaFree(c.dB_tI); cudaFree(c.dB_tpair); cudaFree(c.dB_tnpp);
-    }
+    p->arena.release();                     // every table uploaded while the plan was built
     if (p->own_out) b200_big_free(p->d_out[0]);
     b200_big_free(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
@@ -57,14 +52,41 @@ void jobplan_free(JobPlan *p)
     if (p->ev_t0) cudaEventDestroy(p->ev_t0);
     if (p->ev_t1) cudaEventDestroy(p->ev_t1);
     digest_free(p->digest);
+    for (int k = 0; k < 2; k++) if (p->graph[k].exec) cudaGraphExecDestroy(p->graph[k].exec);
     delete p;
 }
+
+void *DeviceArena::alloc(size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > left) {
+        const size_t blk = std::max(bytes, (size_t)32 << 20);
+        void *p = nullptr;
+        if (b200_big_alloc(&p, blk)) return nullptr;
+        blocks.push_back(p);
+        cur = (char *)p; left = blk;
+    }
+    void *r = cur;
+    cur += bytes; left -= bytes;
+    return r;
+}
+void DeviceArena::release()
+{
+    for (void *p : blocks) b200_big_free(p);
+    blocks.clear(); cur = nullptr; left = 0;
+}
+
+static thread_local DeviceArena *g_arena = nullptr;         // set while a plan is being built: upload() allocates from it
 
 template <class T>
 static int upload(T **dst, const std::vector<T> &src)
 {
-    if (cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(1, src.size())) != cudaSuccess)
-        return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", sizeof(T) * src.size());
+    const size_t bytes = sizeof(T) * std::max<size_t>(1, src.size());
+    if (g_arena) {
+        *dst = (T *)g_arena->alloc(bytes);
+        if (!*dst) return b200_fail(CINTB200_ENOMEM, "device arena: %zu bytes failed", bytes);
+    } else if (cudaMalloc((void **)dst, bytes) != cudaSuccess)
+        return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", bytes);
     if (!src.empty() && cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess)
         return b200_fail(CINTB200_ENODEV, "upload failed");
     return 0;
@@ -88,8 +110,32 @@ static void model_flops(int li, int lj, int lk, int ll, int nc, double *per_prim
     *per_quartet = 4.0 * nf * nc;
 }
 
+// Structure-of-arrays primitive table of a list of T pairs: rows [6 + nct][Q][NT] = aij, 1/aij, px, py, pz, kij, cc[nct]
+// (consecutive THREADS read consecutive addresses); pairs are padded to Q primitives with zero-weight entries.
+static void fill_tprim(const CINTOpt *c, const PairHdr &h, size_t n, size_t NT, int Q, int nct, std::vector<double> &tprim, std::vector<double> &tgeom)
+{
+    const size_t F = (size_t)Q * NT;
+    for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
+    for (int q = 0; q < Q; q++) {
+        const size_t o = (size_t)q * NT + n;
+        if (q < h.npp) {
+            const PrimPair &pp = c->prims[h.pp_off + q];
+            tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
+            tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
+            tprim[5 * F + o] = pp.kij;
+            for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
+        } else {            // zero-weight padding primitive
+            tprim[o] = 1.0; tprim[F + o] = 1.0;
+            tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
+            tprim[5 * F + o] = 0.0;
+            for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
+        }
+    }
+}
+
 static int build_plan(CINTOpt *c, JobPlan *plan)
 {
+    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } } arena_scope(plan->host_only ? nullptr : &plan->arena);
     const int nranks = plan->nranks, rank = plan->rank;
     const bool three = plan->ncenter == 3;
     const int nbas = three ? plan->aux0 : c->nbas;          // shells that form the bra pairs (rows)
@@ -302,22 +348,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
             for (size_t n = 0; n < NT; n++) {
                 const int p = ids[n];
                 const PairHdr &h = c->pairs[p];
-                for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
-                for (int q = 0; q < Q; q++) {
-                    const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
-                    if (q < h.npp) {
-                        const PrimPair &pp = c->prims[h.pp_off + q];
-                        tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
-                        tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
-                        tprim[5 * F + o] = pp.kij;
-                        for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
-                    } else {            // zero-weight padding primitive
-                        tprim[o] = 1.0; tprim[F + o] = 1.0;
-                        tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
-                        tprim[5 * F + o] = 0.0;
-                        for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
-                    }
-                }
+                fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
                 // strides of the canonical indices inside the (i,j) block: i fastest
                 const int i = I[n];
                 const ShellInfo &si = c->shells[i];
@@ -558,9 +589,6 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileS
     const bool prof = c->profile != 0;
     const bool host = sink.sinks != nullptr;
     cudaStream_t st = c->stream;
-    CU_OK(cudaEventRecord(plan->ev_t0, st));
-    CU_OK(cudaMemsetAsync(plan->d_counters, 0, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size()), st));
-    if (digest_begin(c, plan, sink.job, sink.dm_dev, st)) return CINTB200_ENODEV;
     const int NS = prof ? 1 : JobPlan::NS;
     auto fork = [&]() -> int {                 // side streams start after everything queued on the main stream
         if (NS == 1) return 0;
@@ -613,7 +641,12 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileS
         for (auto &e : pev) CU_OK(cudaEventCreate(&e));
     }
     size_t li = 0;
-    int group = -1, cur_chunk = -1, buf = 0, pend_ch = -1, pend_buf = 0, pend_slot = 0;
+    int pend_ch = -1, pend_buf = 0, pend_slot = 0;
+    // everything that goes to the streams between the two timing events (capturable into a CUDA graph, see below)
+    auto enqueue = [&]() -> int {
+    int group = -1, cur_chunk = -1, buf = 0;
+    CU_OK(cudaMemsetAsync(plan->d_counters, 0, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size()), st));
+    if (digest_begin(c, plan, sink.job, sink.dm_dev, st)) return CINTB200_ENODEV;
     const size_t nl = plan->launches.size();
     for (size_t k = 0; k <= nl; k++) {
         const bool last = (k == nl);
@@ -659,6 +692,41 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileS
     }
     if (prof) CU_OK(cudaEventRecord(pev[li], st));
     if (digest_end(c, plan, sink.job, sink.vj_dev, sink.vk_dev, st)) return CINTB200_ENODEV;
+    return 0;
+    };      // enqueue
+    // Device-resident runs replay a CUDA graph: the launch list of a plan is static (1573 launches for C60, 120-1200 for the
+    // C2H6 bases), so the second run with the same consumers is captured -- fork / join over the side streams included -- and
+    // every later run is ONE graph launch instead of hundreds of kernel launches (what bounds the small-molecule jobs and the
+    // per-rank work at 8 GPUs).  Host-sink runs (callbacks between chunks), profiled runs and J/K runs (caller-owned
+    // pointers in the kernel arguments) are enqueued directly.
+    static const bool graphs_on = !(getenv("CINTB200_NO_GRAPH") && atoi(getenv("CINTB200_NO_GRAPH")));
+    JobPlan::GraphSlot &gs = plan->graph[sink.job.checksums ? 1 : 0];
+    const bool graphable = graphs_on && !host && !prof && !sink.job.jk;
+    CU_OK(cudaEventRecord(plan->ev_t0, st));
+    if (graphable && gs.exec) {
+        CU_OK(cudaGraphLaunch(gs.exec, st));
+        nlaunch = gs.nlaunch; reg_launches = gs.reg_launches;
+        if (sink.job.checksums) digest_mark_rowsums(plan);
+    } else if (graphable && gs.warm) {
+        CU_OK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc_enq = enqueue();
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc_enq || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            return rc_enq ? rc_enq : b200_fail(CINTB200_ENODEV, "CUDA graph capture of the job failed: %s", cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&gs.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) { gs.exec = nullptr; return b200_fail(CINTB200_ENODEV, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+        gs.nlaunch = nlaunch; gs.reg_launches = reg_launches;
+        CU_OK(cudaGraphLaunch(gs.exec, st));
+    } else {
+        const int rc_enq = enqueue();
+        if (rc_enq) return rc_enq;
+        if (graphable) gs.warm = 1;
+    }
     CU_OK(cudaEventRecord(plan->ev_t1, st));
     if (pend_ch >= 0 && deliver(pend_ch, pend_buf, pend_slot)) return CINTB200_EINVAL;
     CU_OK(cudaStreamSynchronize(st));
@@ -923,22 +991,7 @@ static int listclass_upload(CINTOpt *c, ListClass &lc)
         std::vector<int> nppc(NT);
         for (size_t n = 0; n < NT; n++) {
             const PairHdr &h = c->pairs[lc.ids[n]];
-            for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
-            for (int q = 0; q < Q; q++) {
-                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
-                if (q < h.npp) {
-                    const PrimPair &pp = c->prims[h.pp_off + q];
-                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
-                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
-                    tprim[5 * F + o] = pp.kij;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
-                } else {
-                    tprim[o] = 1.0; tprim[F + o] = 1.0;
-                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
-                    tprim[5 * F + o] = 0.0;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
-                }
-            }
+            fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
             nppc[n] = std::max(h.npp, 1);
         }
         if (upload(&lc.d_tprim, tprim) || upload(&lc.d_tgeom, tgeom) || upload(&lc.d_tnpp, nppc)) return CINTB200_ENOMEM;
@@ -1100,6 +1153,7 @@ struct RectEntry { int pair; long long off; int s_a, s_b; };      // pair id, bl
 static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntry> &T, const std::vector<RectEntry> &U,
                            long long ld, long long ncols, double *dev_out)
 {
+    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } } arena_scope(&plan->arena);
     auto group = [&](const std::vector<RectEntry> &E, std::vector<PairClass> &out, std::vector<std::vector<int>> &members) {
         std::map<std::vector<int>, int> key2class;
         for (size_t n = 0; n < E.size(); n++) {
@@ -1140,22 +1194,7 @@ static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntr
             const RectEntry &e = T[mem[n]];
             const PairHdr &h = c->pairs[e.pair];
             pc.ids.push_back(e.pair); pc.I.push_back(0); pc.npp.push_back(h.npp);
-            for (int dd = 0; dd < 3; dd++) { tgeom[dd * NT + n] = h.ra[dd]; tgeom[(3 + dd) * NT + n] = h.ab[dd]; }
-            for (int q = 0; q < Q; q++) {
-                const size_t F = (size_t)Q * NT, o = (size_t)q * NT + n;
-                if (q < h.npp) {
-                    const PrimPair &pp = c->prims[h.pp_off + q];
-                    tprim[o] = pp.aij; tprim[F + o] = pp.inv_aij;
-                    tprim[2 * F + o] = pp.px; tprim[3 * F + o] = pp.py; tprim[4 * F + o] = pp.pz;
-                    tprim[5 * F + o] = pp.kij;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = c->pcoef[h.cc_off + (size_t)q * nct + k];
-                } else {
-                    tprim[o] = 1.0; tprim[F + o] = 1.0;
-                    tprim[2 * F + o] = h.ra[0]; tprim[3 * F + o] = h.ra[1]; tprim[4 * F + o] = h.ra[2];
-                    tprim[5 * F + o] = 0.0;
-                    for (int k = 0; k < nct; k++) tprim[(6 + k) * F + o] = 0.0;
-                }
-            }
+            fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
             tstride[n] = e.s_a; tstride[NT + n] = e.s_b;
             trow[n] = e.off;
             nppc[n] = std::max(h.npp, 1);

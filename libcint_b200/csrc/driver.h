@@ -5,6 +5,16 @@
 #include "types.h"
 #include "kernels.h"
 
+// Bump allocator for the many small device tables of a plan: a few pooled blocks instead of ~200 cudaMalloc / cudaFree calls
+// per plan (each a driver round trip with an implicit synchronisation -- per context, i.e. per end-to-end step).
+struct DeviceArena {
+    std::vector<void *> blocks;
+    char *cur = nullptr;
+    size_t left = 0;
+    void *alloc(size_t bytes);
+    void release();
+};
+
 struct PairClass {
     int la, lb, nca, ncb, Q;
     std::vector<int> ids, I, npp;
@@ -73,7 +83,11 @@ struct JobPlan {
     // ---- job geometry for consumers of the tiles (digest.cu: checksums, J/K; host callbacks) ----
     std::vector<int> row_pair, row_pos;     // [all rows] bra pair id i(i+1)/2+j of the row and its position mi + di*mj inside the block
     std::vector<int> col_pair, col_pos;     // [this rank's columns] ket pair id (3-centre: auxiliary shell id) and position mk + dk*ml
+    DeviceArena arena;                      // owns every table uploaded while the plan was built
     struct DigestState *digest = nullptr;   // device-side state of the tile consumers, built on first use (digest.cu)
+    // CUDA graphs of the device-resident job (driver.cu:execute_plan), one per consumer set: [0] plain, [1] with checksums
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; int warm = 0; long long nlaunch = 0, reg_launches = 0; };
+    GraphSlot graph[2];
 };
 
 // ---- tile consumers (digest.cu) ----
@@ -87,6 +101,7 @@ void digest_free(struct DigestState *d);
 int digest_begin(CINTOpt *c, JobPlan *plan, const DigestJob &job, const double *dm_dev, cudaStream_t st);
 int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, const double *tile, cudaStream_t st);
 int digest_end(CINTOpt *c, JobPlan *plan, const DigestJob &job, double *vj_dev, double *vk_dev, cudaStream_t st);
+void digest_mark_rowsums(JobPlan *plan);     // a replayed graph refreshed the row sums
 int digest_fetch_checksums(CINTOpt *c, JobPlan *plan, double *S, double *A, double *F, double *total);
 
 

@@ -12,8 +12,12 @@
 // out[row(ab) + ld * col(cd)] -- consecutive threads write consecutive rows.
 //
 // Reference stages replaced (same math, different order of operations):
-//   CINT2e_loop (src/cint2e.c:660-758)   -> the two primitive loops below (pair-level screening only:
-//                                           the quartet-level test would drop 3% more primitives, all < e^-60)
+//   CINT2e_loop (src/cint2e.c:660-758)   -> the two primitive loops below.  Pair-level screening only: the quartet-level
+//                                           test cce_ij + cce_kl > expcutoff (:720) would drop 3.6% more primitives, all
+//                                           < e^-60.  A warp-uniform form of it (primitives sorted by cce, surviving U
+//                                           primitives = a prefix bounded by the warp's smallest cce_ij) was built and
+//                                           measured in round 2: C60 1137 -> 1190 ms, the bound costs more than it saves
+//                                           (uncontracted and cooperative classes +4-18%, the contracted ones -1%)
 //   CINTrys_roots (src/rys_roots.c:57)   -> rys_roots_t2w<N> from the smem-staged table
 //   CINTg0_2e (src/g2e.c:4518-4540)      -> b00/b10/b01/c00/c0p written in t^2, no division
 //   CINTg0_2e_2d (src/g2e.c:272-421)     -> register VRR, unrolled

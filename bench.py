@@ -367,6 +367,11 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library chatter of any
+    # rank) is sent to stderr for the whole run, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import libcint_b200 as cb
     rank = int(os.environ.get("RANK", "0"))
@@ -649,7 +654,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum, "e2e": e2e, "gpu_launches": launches,
             "clocks": sampler.summary(), "extra": extra,
         }
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -186,6 +186,16 @@ int cintb200_int3c2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double 
 /* 2-centre metric (i|k): shls_slice = {i0,i1, k0,k1}, out[i + NI k] (src/cint2c2e.c:351). */
 int cintb200_int2c2e_sph_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
 
+/* Cartesian output (int2e_cart src/cint2e.c:1202, int3c2e_cart src/cint3c2e.c:710, int2c2e_cart src/cint2c2e.c:368) from the same
+ * specialised kernels, the cart->sph stages compiled out: block dimensions and AO offsets are the Cartesian ones
+ * ((l+1)(l+2)/2 functions per shell and contraction), everything else as for the spherical calls above. */
+int cintb200_int2e_cart_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+int cintb200_int3c2e_cart_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+int cintb200_int2c2e_cart_block(cintb200_ctx *ctx, const int *shls_slice, double *out, int on_device, double *stats);
+int cintb200_int2e_cart_all_unique(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes, double *host_sink, double *stats);
+int cintb200_int2e_cart_all_unique_tiles(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
+                                         cintb200_tile_fn fn, void *user, double *stats);
+
 /* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
  * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity
  * tolerance by construction); 0 switches it off.  The bounds are evaluated on the device on first use.

@@ -146,7 +146,8 @@ class Context:
         l, nc = self.bas[:, 1].astype(np.int64), self.bas[:, 3].astype(np.int64)
         dim = ((l + 1) * (l + 2) // 2 if cart else 2 * l + 1) * nc                 # per shell
         sizes = (ncomp * np.prod(dim[shls], axis=1)).astype(np.uint64) if n else np.zeros(0, np.uint64)
-        if out_off is None:
+        packed = out_off is None
+        if packed:              # blocks back to back in input order: the library computes the same offsets itself (out_off = NULL)
             offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if n else np.zeros(0, np.uint64)
             total = int(sizes.sum())
         else:
@@ -154,12 +155,12 @@ class Context:
             total = int((offs + sizes).max()) if n else 0
         nz = np.zeros(n, dtype=np.int32)
         if device_ptr is not None:
-            rc = fn(self.handle, kind, _p(shls), n, _p(offs), ctypes.c_void_p(device_ptr), 1, _p(nz))
+            rc = fn(self.handle, kind, _p(shls), n, None if packed else _p(offs), ctypes.c_void_p(device_ptr), 1, _p(nz))
             res = None
         else:
             if out is None:
                 out = np.zeros(total)
-            rc = fn(self.handle, kind, _p(shls), n, _p(offs), _p(out), 0, _p(nz))
+            rc = fn(self.handle, kind, _p(shls), n, None if packed else _p(offs), _p(out), 0, _p(nz))
             res = out
         if rc < 0:
             raise B200Error("batch failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
@@ -193,11 +194,13 @@ class Context:
     def int2c2e_ip2_batch(self, shls, kind=SPH, **kw):
         return self._batch(self.lib.cintb200_int2c2e_ip2_batch, 2, shls, kind, ncomp=3, **kw)
 
-    def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None):
-        """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array."""
+    def all_unique(self, rank=0, nranks=1, chunk_bytes=0, host_sink=None, cart=False):
+        """Whole-job driver of examples/time_c60.c:200-219 on this rank's shard; returns the stats array (cart: int2e_cart)."""
         stats = np.zeros(16)
-        rc = self.lib.cintb200_int2e_sph_all_unique(self.handle, rank, nranks, chunk_bytes,
-                                                    ctypes.c_void_p(host_sink) if host_sink else None, _p(stats))
+        f = self.lib.cintb200_int2e_cart_all_unique if cart else self.lib.cintb200_int2e_sph_all_unique
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+        f.restype = ctypes.c_int
+        rc = f(self.handle, rank, nranks, chunk_bytes, ctypes.c_void_p(host_sink) if host_sink else None, _p(stats))
         if rc < 0:
             raise B200Error("all_unique failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return stats
@@ -239,7 +242,7 @@ class Context:
                 raise B200Error(self.lib.cintb200_last_error().decode())
         return rows, cols
 
-    def all_unique_tiles(self, sinks, callback=None, rank=0, nranks=1, chunk_bytes=0, aux_shell0=None):
+    def all_unique_tiles(self, sinks, callback=None, rank=0, nranks=1, chunk_bytes=0, aux_shell0=None, cart=False):
         """Whole job with every tile delivered to the host: `sinks` = list of pinned-buffer addresses (ints), `callback(tile
         dict, values ndarray[nrows, ncols] F-order view into the sink)` is called once per tile in chunk order."""
         err = []
@@ -260,7 +263,7 @@ class Context:
         arr = (ctypes.c_void_p * len(sinks))(*sinks)
         stats = np.zeros(16)
         if aux_shell0 is None:
-            f = self.lib.cintb200_int2e_sph_all_unique_tiles
+            f = self.lib.cintb200_int2e_cart_all_unique_tiles if cart else self.lib.cintb200_int2e_sph_all_unique_tiles
             f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int, TILE_FN, ctypes.c_void_p, ctypes.c_void_p]
             f.restype = ctypes.c_int
             rc = f(self.handle, rank, nranks, chunk_bytes, arr, len(sinks), cb, None, _p(stats))
@@ -306,10 +309,10 @@ class Context:
             raise B200Error("int3c2e_all failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return stats
 
-    def _block(self, fn, ncenter, shls_slice, device_ptr=None):
+    def _block(self, fn, ncenter, shls_slice, device_ptr=None, cart=False):
         sl = np.ascontiguousarray(shls_slice, dtype=np.int32).reshape(-1)
         assert sl.size == 2 * ncenter
-        ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in self.bas])])
+        ao = np.concatenate([[0], np.cumsum([((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in self.bas])])
         shape = tuple(int(ao[sl[2 * m + 1]] - ao[sl[2 * m]]) for m in range(ncenter))
         stats = np.zeros(16)
         fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
@@ -324,17 +327,17 @@ class Context:
             raise B200Error("block failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
         return out, stats
 
-    def int2e_block(self, shls_slice, device_ptr=None):
-        """Dense (NI,NJ,NK,NL) tensor of int2e_sph over shell slices (i0,i1,j0,j1,k0,k1,l0,l1); returns (array, stats)."""
-        return self._block(self.lib.cintb200_int2e_sph_block, 4, shls_slice, device_ptr)
+    def int2e_block(self, shls_slice, device_ptr=None, cart=False):
+        """Dense (NI,NJ,NK,NL) tensor of int2e_sph (cart: int2e_cart) over shell slices (i0,i1,j0,j1,k0,k1,l0,l1); returns (array, stats)."""
+        return self._block(self.lib.cintb200_int2e_cart_block if cart else self.lib.cintb200_int2e_sph_block, 4, shls_slice, device_ptr, cart)
 
-    def int3c2e_block(self, shls_slice, device_ptr=None):
-        """Dense (NI,NJ,NK) tensor of int3c2e_sph over shell slices (i0,i1,j0,j1,k0,k1)."""
-        return self._block(self.lib.cintb200_int3c2e_sph_block, 3, shls_slice, device_ptr)
+    def int3c2e_block(self, shls_slice, device_ptr=None, cart=False):
+        """Dense (NI,NJ,NK) tensor of int3c2e_sph / int3c2e_cart over shell slices (i0,i1,j0,j1,k0,k1)."""
+        return self._block(self.lib.cintb200_int3c2e_cart_block if cart else self.lib.cintb200_int3c2e_sph_block, 3, shls_slice, device_ptr, cart)
 
-    def int2c2e_block(self, shls_slice, device_ptr=None):
-        """Dense (NI,NK) matrix of int2c2e_sph over shell slices (i0,i1,k0,k1): the density-fitting metric."""
-        return self._block(self.lib.cintb200_int2c2e_sph_block, 2, shls_slice, device_ptr)
+    def int2c2e_block(self, shls_slice, device_ptr=None, cart=False):
+        """Dense (NI,NK) matrix of int2c2e_sph / int2c2e_cart over shell slices (i0,i1,k0,k1): the density-fitting metric."""
+        return self._block(self.lib.cintb200_int2c2e_cart_block if cart else self.lib.cintb200_int2c2e_sph_block, 2, shls_slice, device_ptr, cart)
 
     def aux_offset(self, k):
         """This rank's column offset of auxiliary shell k in the tiles of int3c2e_all (-1: owned by another rank)."""

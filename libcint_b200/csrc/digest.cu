@@ -66,7 +66,8 @@ static int up(T **dst, const std::vector<T> &src)
     return 0;
 }
 
-static inline int shell_dim_sph(const ShellInfo &s) { return (2 * s.l + 1) * s.nctr; }
+static inline int shell_dim_of(const ShellInfo &s, int cart) { return (cart ? B200_NCART(s.l) : 2 * s.l + 1) * s.nctr; }
+static inline int shell_ao_of(const ShellInfo &s, int cart) { return cart ? s.ao_cart : s.ao_sph; }
 static inline void pair_shells(int p, int *i, int *j)
 {
     int ii = (int)((sqrt(8.0 * p + 1.0) - 1.0) / 2.0);
@@ -111,18 +112,19 @@ static int checksums_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
     std::vector<int> rowI(d->nrows), colK(d->ncols);
     std::vector<double> colg(d->ncols);
     for (long long r = 0; r < d->nrows; r++) { int i, j; pair_shells(plan->row_pair[r], &i, &j); rowI[r] = i; }
-    const int ao_aux0 = plan->ncenter == 3 ? c->shells[plan->aux0].ao_sph : 0;
+    const int cart = plan->cart;
+    const int ao_aux0 = plan->ncenter == 3 ? shell_ao_of(c->shells[plan->aux0], cart) : 0;
     for (long long q = 0; q < d->ncols; q++) {
         if (plan->ncenter == 3) {           // columns = auxiliary functions: always valid; weight g(c - first auxiliary AO, 0)
             const ShellInfo &sk = c->shells[plan->col_pair[q]];
             colK[q] = -1;
-            colg[q] = g_weight(sk.ao_sph + plan->col_pos[q] - ao_aux0, 0);
+            colg[q] = g_weight(shell_ao_of(sk, cart) + plan->col_pos[q] - ao_aux0, 0);
         } else {
             int k, l;
             pair_shells(plan->col_pair[q], &k, &l);
-            const int dk = shell_dim_sph(c->shells[k]);
+            const int dk = shell_dim_of(c->shells[k], cart);
             colK[q] = k;
-            colg[q] = g_weight(c->shells[k].ao_sph + plan->col_pos[q] % dk, c->shells[l].ao_sph + plan->col_pos[q] / dk);
+            colg[q] = g_weight(shell_ao_of(c->shells[k], cart) + plan->col_pos[q] % dk, shell_ao_of(c->shells[l], cart) + plan->col_pos[q] / dk);
         }
     }
     if (up(&d->d_rowI, rowI) || up(&d->d_colK, colK) || up(&d->d_colg, colg)) return CINTB200_ENOMEM;
@@ -148,7 +150,7 @@ struct JKArgs {
 // The Coulomb row part J'[a,b] += 2 s (ab|cd) D[c,d] rides along in the visit from the ket's first shell.
 #define JK_RPT 2                 // tile rows per thread: twice the loads in flight, the per-entry decoding shared by both
 template <int NX>
-__global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
+__global__ void __launch_bounds__(128, 4) jk_rows_kernel(const JKArgs A)
 {
     const long long row0 = (long long)blockIdx.x * (128 * JK_RPT) + threadIdx.x;
     bool active[JK_RPT];
@@ -296,16 +298,19 @@ __global__ void jk_symm_kernel(const double *__restrict__ P, int nao, double *ou
     out[n] = P[n] + P[(size_t)b * nao + a];
 }
 
+static inline int shell_dim_sphx(const ShellInfo &s) { return (2 * s.l + 1) * s.nctr; }
+
 static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
 {
     if (d->jk_ready) return 0;
+    if (plan->cart) return b200_fail(CINTB200_ENOSUP, "J/K digestion works on the spherical job");
     const int nbas = c->nbas, nao = c->nao_sph;
     d->nao = nao;
     std::vector<int4> rowinfo(d->nrows);
     for (long long r = 0; r < d->nrows; r++) {
         int i, j;
         pair_shells(plan->row_pair[r], &i, &j);
-        const int di = shell_dim_sph(c->shells[i]);
+        const int di = shell_dim_sphx(c->shells[i]);
         rowinfo[r] = make_int4(c->shells[i].ao_sph + plan->row_pos[r] % di, c->shells[j].ao_sph + plan->row_pos[r] / di, plan->row_pair[r], i == j);
     }
     std::vector<int2> colinfo(d->ncols);
@@ -313,7 +318,7 @@ static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
     for (long long q = 0; q < d->ncols; q++) {
         int k, l;
         pair_shells(plan->col_pair[q], &k, &l);
-        const int dk = shell_dim_sph(c->shells[k]);
+        const int dk = shell_dim_sphx(c->shells[k]);
         colinfo[q] = make_int2(plan->col_pair[q], k == l);
         colc[q] = c->shells[k].ao_sph + plan->col_pos[q] % dk;
         cold[q] = c->shells[l].ao_sph + plan->col_pos[q] / dk;
@@ -322,7 +327,7 @@ static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
     struct HU { int ao0, nx; std::vector<JKEntry> e; };
     std::vector<std::vector<HU>> byshell(nbas);
     for (int X = 0; X < nbas; X++) {
-        const int dx = shell_dim_sph(c->shells[X]);
+        const int dx = shell_dim_sphx(c->shells[X]);
         if (dx > 255) return b200_fail(CINTB200_ENOSUP, "J/K digestion: shell %d has %d > 255 functions", X, dx);
         for (int x0 = 0; x0 < dx; x0 += JK_NXMAX) byshell[X].push_back(HU{c->shells[X].ao_sph + x0, std::min(JK_NXMAX, dx - x0), {}});
     }
@@ -331,7 +336,7 @@ static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
             const int q = k * (k + 1) / 2 + l;
             if (plan->colof[q] < 0) continue;
             if (plan->colof[q] > 0x7fffffffLL) return b200_fail(CINTB200_ENOSUP, "J/K digestion: more than 2^31 tile columns");
-            const int dk = shell_dim_sph(c->shells[k]), dl = shell_dim_sph(c->shells[l]);
+            const int dk = shell_dim_sphx(c->shells[k]), dl = shell_dim_sphx(c->shells[l]);
             for (size_t s = 0; s < byshell[k].size(); s++) {        // visit from the first shell: x = c (unit stride), y = d
                 const int x0 = byshell[k][s].ao0 - c->shells[k].ao_sph;
                 byshell[k][s].e.push_back(JKEntry{(int)plan->colof[q] + x0, q, c->shells[l].ao_sph, dl | dk << 8 | 1 << 16});

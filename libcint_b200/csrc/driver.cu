@@ -141,11 +141,10 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     const int nbas = three ? plan->aux0 : c->nbas;          // shells that form the bra pairs (rows)
     const size_t npair = (size_t)nbas * (nbas + 1) / 2;
     long long aux_cols = 0;                                 // 3-centre: spherical AOs of all auxiliary shells
-    if (three) for (int k = plan->aux0; k < c->nbas; k++) aux_cols += (2 * c->shells[k].l + 1) * c->shells[k].nctr;
-    auto pair_dim = [&](int i, int j) {
-        const ShellInfo &si = c->shells[i], &sj = c->shells[j];
-        return (long long)(2 * si.l + 1) * si.nctr * (2 * sj.l + 1) * sj.nctr;
-    };
+    const int cart = plan->cart;
+    auto sdim = [&](int i) { const ShellInfo &si = c->shells[i]; return (long long)(cart ? B200_NCART(si.l) : 2 * si.l + 1) * si.nctr; };
+    if (three) for (int k = plan->aux0; k < c->nbas; k++) aux_cols += sdim(k);
+    auto pair_dim = [&](int i, int j) { return sdim(i) * sdim(j); };
     // 1. pair classes (la, lb, nca, ncb), lists in enumeration order = sorted by the larger shell index
     std::map<std::vector<int>, int> key2class;
     plan->rowoff.resize(npair);
@@ -275,7 +274,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
                 if ((int)(n % nranks) != rank) continue;
                 ucol[n] = cols;
                 plan->colof_aux[pc.I[n] - plan->aux0] = cols;
-                cols += (2 * pc.la + 1) * pc.nca;
+                cols += (cart ? B200_NCART(pc.la) : 2 * pc.la + 1) * pc.nca;
             }
             pc.npp_prefix.assign(NU + 1, 0);
             for (size_t n = 0; n < NU; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
@@ -320,7 +319,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
         for (int k = plan->aux0; k < c->nbas; k++) {
             const long long c0 = plan->colof_aux[k - plan->aux0];
             if (c0 < 0) continue;
-            const int dk = (2 * c->shells[k].l + 1) * c->shells[k].nctr;
+            const int dk = (int)sdim(k);
             for (int r = 0; r < dk; r++) { plan->col_pair[c0 + r] = k; plan->col_pos[c0 + r] = r; }
         }
     } else {
@@ -351,8 +350,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
                 fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
                 // strides of the canonical indices inside the (i,j) block: i fastest
                 const int i = I[n];
-                const ShellInfo &si = c->shells[i];
-                const int di = (2 * si.l + 1) * si.nctr;
+                const int di = (int)sdim(i);
                 const bool a_is_i = (h.sh_a == i);
                 tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
                 trow[n] = plan->rowoff[p];
@@ -456,7 +454,8 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     prim_here += (double)U.npp[u] * npp_ge[kk];
                 }
                 if (q_here == 0) continue;
-                const double blk = (double)(2 * T.la + 1) * (2 * T.lb + 1) * T.nca * T.ncb * (2 * U.la + 1) * (2 * U.lb + 1) * U.nca * U.ncb;
+                auto ld_ = [&](int l) { return plan->cart ? B200_NCART(l) : 2 * l + 1; };
+                const double blk = (double)ld_(T.la) * ld_(T.lb) * T.nca * T.ncb * ld_(U.la) * ld_(U.lb) * U.nca * U.ncb;
                 double fp, fq;
                 model_flops(T.la, T.lb, U.la, U.lb, T.nca * T.ncb * U.nca * U.ncb, &fp, &fq);
                 plan->st_quartets += q_here; plan->st_integrals += q_here * blk; plan->st_prim += prim_here;
@@ -468,9 +467,9 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 const bool generic_only = c->force_generic;
                 const int rs = c->omega != 0;
                 P.rs_w2 = c->omega * c->omega; P.rs_sign = c->omega;      /* sign * |omega| */ P.rs_pass0 = c->omega > 0 ? 1 : 0;
-                L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, rs);
+                L.fn = generic_only ? nullptr : reg_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, rs, plan->cart);
                 if (!L.fn && !generic_only) {
-                    L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci, rs);
+                    L.fn = coop_kernel_lookup(T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, &L.ci, rs, plan->cart);
                     L.coop = L.fn != nullptr;
                 }
                 // deeply contracted kets (all-electron heavy-element bases) can push the staged ket primitives past the
@@ -491,7 +490,7 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                     }
                     plan->launches.push_back(L);
                 } else {
-                    if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, 0, L.ntasks, engine_c2s_off(), c->omega < 0))
+                    if (generic_plan(&L.GC, &L.GL, T.la, T.lb, U.la, U.lb, T.nca * T.ncb, U.nca * U.ncb, plan->cart, L.ntasks, engine_c2s_off(), c->omega < 0))
                         return b200_fail(CINTB200_ENOSUP, "class (%d%d|%d%d) exceeds this build's limits", T.la, T.lb, U.la, U.lb);
                     scratch_need = std::max(scratch_need, L.GC.scratch_per_block * (size_t)L.GL.grid);
                     plan->launches.push_back(L);
@@ -520,6 +519,7 @@ struct TileSink {
     cintb200_tile_fn fn = nullptr;          // called on the calling thread when a tile has arrived in its sink
     void *user = nullptr;
     DigestJob job;                          // device-side consumers (digest.cu)
+    int cart = 0;                           // Cartesian output
     const double *dm_dev = nullptr;         // J/K: density matrix (device), results (device)
     double *vj_dev = nullptr, *vk_dev = nullptr;
 };
@@ -549,10 +549,10 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
     if (chunk_bytes == 0) chunk_bytes = (size_t)16 << 30;
     JobPlan *plan = c->plan;
     if (!plan || plan->rect || plan->rank != rank || plan->nranks != nranks || plan->chunk_bytes != chunk_bytes || plan->force_generic != c->force_generic
-        || plan->schwarz_thr != c->schwarz_thr || plan->ncenter != ncenter || plan->aux0 != (ncenter == 3 ? aux0 : 0)) {
+        || plan->schwarz_thr != c->schwarz_thr || plan->ncenter != ncenter || plan->aux0 != (ncenter == 3 ? aux0 : 0) || plan->cart != sink.cart) {
         if (plan) { cudaDeviceSynchronize(); jobplan_free(plan); c->plan = nullptr; }
         plan = new JobPlan();
-        plan->ncenter = ncenter; plan->aux0 = (ncenter == 3) ? aux0 : 0;
+        plan->ncenter = ncenter; plan->aux0 = (ncenter == 3) ? aux0 : 0; plan->cart = sink.cart;
         plan->rank = rank; plan->nranks = nranks; plan->chunk_bytes = chunk_bytes; plan->force_generic = c->force_generic; plan->schwarz_thr = c->schwarz_thr;
         tph = b200_now();
         int rc = build_plan(c, plan);
@@ -582,7 +582,7 @@ static int execute_plan(cintb200_ctx *c, JobPlan *plan, int ncenter, const TileS
 {
     EngineParams EP;
     EP.pairs = c->d_pairs; EP.prims = c->d_prims; EP.pcoef = c->d_pcoef; EP.rys_coef = c->d_rys; EP.c2s = c->d_c2s;
-    EP.expcutoff = (ncenter == 3) ? c->expcutoff3 : c->expcutoff4; EP.omega = c->omega; EP.cart = 0;
+    EP.expcutoff = (ncenter == 3) ? c->expcutoff3 : c->expcutoff4; EP.omega = c->omega; EP.cart = plan->cart;
 
     double d2h = 0;
     long long nlaunch = 0, reg_launches = 0;
@@ -787,6 +787,26 @@ extern "C" int cintb200_int3c2e_sph_all(cintb200_ctx *c, int aux_shell0, int ran
     return run_job(c, 3, aux_shell0, rank, nranks, chunk_bytes, s, stats);
 }
 
+// int2e_cart over the same loop (north star: int2e_cart is part of the hot path): Cartesian block dimensions everywhere
+extern "C" int cintb200_int2e_cart_all_unique(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes, double *host_sink, double *stats)
+{
+    TileSink s;
+    double *one[1] = {host_sink};
+    if (host_sink) { s.sinks = one; s.nsinks = 1; }
+    s.cart = 1;
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
+}
+extern "C" int cintb200_int2e_cart_all_unique_tiles(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
+                                                    cintb200_tile_fn fn, void *user, double *stats)
+{
+    if (!sinks || nsinks < 1) return b200_fail(CINTB200_EINVAL, "cintb200_int2e_cart_all_unique_tiles needs at least one host sink");
+    TileSink s;
+    s.sinks = sinks; s.nsinks = nsinks; s.fn = fn; s.user = user; s.cart = 1;
+    s.job.checksums = (c && c->magic == B200_CTX_MAGIC) ? c->checksums : 0;
+    return run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
+}
+
 // Same jobs with every tile handed to the caller: ring of pinned sinks + callback (include/cint_b200.h)
 extern "C" int cintb200_int2e_sph_all_unique_tiles(cintb200_ctx *c, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
                                                    cintb200_tile_fn fn, void *user, double *stats)
@@ -916,29 +936,15 @@ extern "C" int cintb200_job_col_map(cintb200_ctx *c, int chunk, int *sh_k, int *
 // ket class that has a specialised kernel is turned into explicit work items for it: the tuples are sorted by ket, each ket
 // owns a run of T OCCURRENCES (output offset + strides of that tuple, and the row of the bra pair in a per-class pair table
 // shared by all calls), and an item is {ket, first occurrence, count <= 32}.  Groups without a kernel stay with the caller.
-struct ListClass {
-    int la, lb, nca, ncb, Q;
-    std::vector<int> ids;
-    double *d_tprim = nullptr, *d_tgeom = nullptr;
-    int *d_tnpp = nullptr;
-};
-struct ListChoice { RegKernelFn fn; int coop; CoopInfo ci; };
-struct ListTables {
-    std::vector<ListClass> cls;
-    std::vector<int> cls_of, row_of;        // per pair id (shell pairs, then the single-shell pseudo pairs)
-    std::vector<ListChoice> choice;         // [bra class * ncls + ket class]: the specialised kernel, if any
-    void *d_buf = nullptr; size_t cap = 0;  // per-call arrays (grow-only)
-};
-
 void listtables_free(ListTables *lt)
 {
     if (!lt) return;
     for (ListClass &lc : lt->cls) { cudaFree(lc.d_tprim); cudaFree(lc.d_tgeom); cudaFree(lc.d_tnpp); }
-    cudaFree(lt->d_buf);
+    cudaFree(lt->d_buf); cudaFree(lt->d_cls_of); cudaFree(lt->d_row_of); cudaFree(lt->d_sdim); cudaFree(lt->d_per); cudaFree(lt->d_work);
     delete lt;
 }
 
-static int listtables_build(CINTOpt *c)
+int listtables_build(CINTOpt *c)
 {
     ListTables *lt = new ListTables();
     const size_t np = c->pairs.size();
@@ -963,14 +969,16 @@ static int listtables_build(CINTOpt *c)
     }
     const int ncls = (int)lt->cls.size();
     lt->choice.resize((size_t)ncls * ncls);
+    lt->choice_cart.resize((size_t)ncls * ncls);
+    for (int cart = 0; cart < 2; cart++)
     for (int cb = 0; cb < ncls; cb++)
         for (int ck = 0; ck < ncls; ck++) {
             const ListClass &B = lt->cls[cb], &K = lt->cls[ck];
-            ListChoice &ch = lt->choice[(size_t)cb * ncls + ck];
+            ListChoice &ch = (cart ? lt->choice_cart : lt->choice)[(size_t)cb * ncls + ck];
             memset(&ch, 0, sizeof ch);
             const int rs = c->omega != 0;
-            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, rs);
-            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci, rs); ch.coop = ch.fn != nullptr; }
+            ch.fn = reg_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, rs, cart);
+            if (!ch.fn) { ch.fn = coop_kernel_lookup(B.la, B.lb, K.la, K.lb, B.nca * B.ncb, K.nca * K.ncb, &ch.ci, rs, cart); ch.coop = ch.fn != nullptr; }
             const int nroots_ = (B.la + B.lb + K.la + K.lb) / 2 + 1, ncu_ = K.nca * K.ncb, umax_ = std::max(1, K.Q);
             if (ch.fn && (ch.coop ? coop_kernel_smem(ch.ci, ncu_, umax_) : reg_kernel_smem(ch.fn, nroots_, ncu_, umax_)) > (size_t)tile_smem_limit()) {
                 ch.fn = nullptr; ch.coop = 0;       // ket too deeply contracted for the staged primitives: generic kernel
@@ -981,7 +989,7 @@ static int listtables_build(CINTOpt *c)
 }
 
 // structure-of-arrays primitive table of one bra class, uploaded the first time a list uses the class
-static int listclass_upload(CINTOpt *c, ListClass &lc)
+int listclass_upload(CINTOpt *c, ListClass &lc)
 {
     if (lc.d_tprim) return 0;
     {
@@ -1002,7 +1010,7 @@ static int listclass_upload(CINTOpt *c, ListClass &lc)
 // Evaluate the tuples whose (bra class, ket class) has a specialised kernel; handled[t] = 1 for those.  tasks are in the
 // caller's order (Task::off = element offset of the tuple's block in d_out, strides for the packed block).  Spherical,
 // plain Coulomb only.  Caller holds c->mtx; launches go to c->stream (not synchronised here).
-int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled)
+int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled, int cart)
 {
     if (!c->ltab && listtables_build(c)) return CINTB200_ENOMEM;
     ListTables *lt = c->ltab;
@@ -1019,7 +1027,7 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
         gkey[t] = g;
         all[t].t = (unsigned int)t;
         all[t].key = ~0ull;
-        if (lt->choice[g].fn) {
+        if ((cart ? lt->choice_cart : lt->choice)[g].fn) {
             handled[t] = 1;
             const unsigned long long np_ = (unsigned long long)(127 - std::min(c->pairs[tasks[t].bra].npp, 127));
             all[t].key = ((unsigned long long)g << 42) | ((unsigned long long)(unsigned int)tasks[t].ket << 8)
@@ -1037,7 +1045,7 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
     const size_t m = recs.size();
     std::vector<size_t> idx(m);
     for (size_t q = 0; q < m; q++) idx[q] = recs[q].t;
-    auto choice = [&](int g) -> const Choice & { return lt->choice[g]; };
+    auto choice = [&](int g) -> const Choice & { return (cart ? lt->choice_cart : lt->choice)[g]; };
     std::vector<int> tsel(m), tstride(2 * m), upair, ustride;
     std::vector<long long> trow(m);
     std::vector<int4> items;
@@ -1242,7 +1250,7 @@ static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntr
 }
 
 // ncenter 4: shls_slice = {i0,i1, j0,j1, k0,k1, l0,l1};  ncenter 3: {i0,i1, j0,j1, k0,k1}
-static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_device, double *stats)
+static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_device, double *stats, int cart = 0)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (!sl || !out) return b200_fail(CINTB200_EINVAL, "NULL shls_slice/out");
@@ -1251,8 +1259,8 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
             return b200_fail(CINTB200_EINVAL, "shell slice %d = [%d, %d) is empty or outside 0..%d", m, sl[2 * m], sl[2 * m + 1], c->nbas);
     std::lock_guard<std::mutex> lock(c->mtx);
     CU_OK(cudaSetDevice(c->device));
-    auto ao0 = [&](int sh) { return (long long)c->shells[sh].ao_sph; };
-    auto aoend = [&](int sh) { return (long long)c->shells[sh].ao_sph + (2 * c->shells[sh].l + 1) * c->shells[sh].nctr; };
+    auto ao0 = [&](int sh) { return (long long)(cart ? c->shells[sh].ao_cart : c->shells[sh].ao_sph); };
+    auto aoend = [&](int sh) { return ao0(sh) + (cart ? B200_NCART(c->shells[sh].l) : 2 * c->shells[sh].l + 1) * c->shells[sh].nctr; };
     const size_t npair2 = (size_t)c->nbas * (c->nbas + 1) / 2;
     std::vector<RectEntry> T, U;
     if (ncenter == 2) {
@@ -1262,7 +1270,7 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
         for (int k = sl[2]; k < sl[3]; k++) U.push_back(RectEntry{(int)(npair2 + k), ao0(k) - ao0(sl[2]), 1, 0});
         if (c->plan) { cudaDeviceSynchronize(); jobplan_free(c->plan); c->plan = nullptr; }
         JobPlan *plan2 = new JobPlan();
-        plan2->ncenter = 3; plan2->rect = 2; plan2->force_generic = c->force_generic; plan2->schwarz_thr = 0;
+        plan2->ncenter = 3; plan2->rect = 2; plan2->force_generic = c->force_generic; plan2->schwarz_thr = 0; plan2->cart = cart;
         int rc2 = build_rect_plan(c, plan2, T, U, NI2, NK2, on_device ? out : nullptr);
         if (!rc2) rc2 = build_launches(c, plan2);
         if (rc2) { jobplan_free(plan2); return rc2; }
@@ -1305,7 +1313,7 @@ static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, i
     JobPlan *plan = new JobPlan();
     plan->ncenter = 3;                  // rectangular job: separate ket classes, every ket meets every bra (see build_launches)
     plan->rect = ncenter; plan->aux0 = 0; plan->rank = 0; plan->nranks = 1; plan->chunk_bytes = 0;
-    plan->force_generic = c->force_generic; plan->schwarz_thr = 0;
+    plan->force_generic = c->force_generic; plan->schwarz_thr = 0; plan->cart = cart;
     int rc = build_rect_plan(c, plan, T, U, NI * NJ, NK * NL, on_device ? out : nullptr);
     if (!rc) rc = build_launches(c, plan);
     if (rc) { jobplan_free(plan); return rc; }
@@ -1321,6 +1329,13 @@ extern "C" int cintb200_int3c2e_sph_block(cintb200_ctx *c, const int *shls_slice
 { return run_block(c, 3, shls_slice, out, on_device, stats); }
 extern "C" int cintb200_int2c2e_sph_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
 { return run_block(c, 2, shls_slice, out, on_device, stats); }
+// Cartesian output (int2e_cart / int3c2e_cart / int2c2e_cart): the same kernels with the cart->sph stages compiled out
+extern "C" int cintb200_int2e_cart_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 4, shls_slice, out, on_device, stats, 1); }
+extern "C" int cintb200_int3c2e_cart_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 3, shls_slice, out, on_device, stats, 1); }
+extern "C" int cintb200_int2c2e_cart_block(cintb200_ctx *c, const int *shls_slice, double *out, int on_device, double *stats)
+{ return run_block(c, 2, shls_slice, out, on_device, stats, 1); }
 
 // Copy a rectangle of the most recent tile of chunk `chunk` ... (verification helper for tests):
 // evaluates ONE chunk and returns it on the host together with its geometry.

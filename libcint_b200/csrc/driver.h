@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include "types.h"
 #include "kernels.h"
+struct CINTOpt;
 
 // Bump allocator for the many small device tables of a plan: a few pooled blocks instead of ~200 cudaMalloc / cudaFree calls
 // per plan (each a driver round trip with an implicit synchronisation -- per context, i.e. per end-to-end step).
@@ -52,6 +53,7 @@ struct JobPlan {
     int ncenter = 4, aux0 = 0;              // 3: rows = orbital pairs of shells [0, aux0), columns = auxiliary shells [aux0, nbas)
     int rect = 0;                           // dense shell-slice block (build_rect_plan): explicit bra / ket lists, one tile; value =
                                             // number of centres of the integral (3 or 4)
+    int cart = 0;                           // Cartesian output (int2e_cart / int3c2e_cart): block dimensions are ncart(l) * nctr
     int own_out = 1;                        // d_out[0] belongs to the plan (rect jobs may write into the caller's device buffer)
     std::vector<PairClass> classes;
     std::vector<PairClass> uclasses;        // 3-centre jobs: classes of the single-shell pseudo pairs (kets); 4-centre: unused
@@ -90,8 +92,29 @@ struct JobPlan {
     GraphSlot graph[2];
 };
 
+// ---- list mode on the tile kernels (driver.cu:list_mode_run on the host, listdev.cu on the device) ----
+struct ListClass {
+    int la, lb, nca, ncb, Q;
+    std::vector<int> ids;
+    double *d_tprim = nullptr, *d_tgeom = nullptr;
+    int *d_tnpp = nullptr;
+};
+struct ListChoice { RegKernelFn fn; int coop; CoopInfo ci; };
+struct ListTables {
+    std::vector<ListClass> cls;
+    std::vector<int> cls_of, row_of;        // per pair id (shell pairs, then the single-shell pseudo pairs)
+    std::vector<ListChoice> choice, choice_cart;   // [bra class * ncls + ket class]: the specialised kernel, if any (spherical / Cartesian output)
+    void *d_buf = nullptr; size_t cap = 0;  // per-call arrays (grow-only)
+    // device-side list handling (listdev.cu): per pair id class / table row, per shell dimensions {sph, cart}, per group
+    // bras per work item (0: no specialised kernel) for spherical and Cartesian output, grow-only work area
+    int *d_cls_of = nullptr, *d_row_of = nullptr, *d_sdim = nullptr, *d_per = nullptr;
+    void *d_work = nullptr; size_t cap_work = 0;
+};
+
+int listtables_build(CINTOpt *c);
+int listclass_upload(CINTOpt *c, ListClass &lc);
+
 // ---- tile consumers (digest.cu) ----
-struct CINTOpt;
 struct DigestJob {                          // what to do with every finished tile, besides (optionally) copying it to the host
     int checksums = 0;                      // per-row sums of the valid entries (cintb200_set_checksums)
     int jk = 0;                             // digest into Coulomb / exchange matrices (cintb200_int2e_sph_jk)

@@ -411,6 +411,33 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
     CUDA_OK(cudaSetDevice(c->device));
     const size_t npair2 = (size_t)c->nbas * (c->nbas + 1) / 2;
 
+    // Large lists: the whole bookkeeping runs on the device (listdev.cu) when every class of the list has a specialised kernel
+    static const bool list_fast = getenv("CINTB200_LIST_GENERIC") == nullptr;
+    static const bool list_dev = getenv("CINTB200_LIST_HOST") == nullptr;
+    if (list_fast && list_dev && n >= 4096 && cart_pos < 0 && !c->force_generic) {
+        size_t tot_dev = 0;
+        double *d_used = nullptr;
+        const int r = list_mode_device(c, ncenter, cart, shls, n, out_off, on_device ? out : nullptr, &d_used, &tot_dev, nonzero);
+        if (r < 0) return r;
+        if (r == 1) {
+            if (!on_device) {
+                if (ctx_reserve(c, (void **)&c->h_stage, &c->cap_stage, sizeof(double) * std::max<size_t>(1, tot_dev), true)) return CINTB200_ENOMEM;
+                CUDA_OK(cudaMemcpyAsync(c->h_stage, d_used, sizeof(double) * tot_dev, cudaMemcpyDeviceToHost, c->stream));
+            }
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) return b200_fail(CINTB200_ENODEV, "kernel execution failed: %s", cudaGetErrorString(le));
+            if (!on_device) {
+                if (out_off) {
+                    for (size_t t = 0; t < n; t++) {
+                        const size_t len = cintb200_block_size(c, kind, shls + t * ncenter, ncenter);
+                        memcpy(out + out_off[t], (double *)c->h_stage + out_off[t], sizeof(double) * len);
+                    }
+                } else memcpy(out, c->h_stage, sizeof(double) * tot_dev);
+            }
+            return (long)n;
+        }
+    }
     std::vector<Task> tasks(n);
     std::vector<ClassKey> keys(n);
     std::vector<size_t> offs(n);
@@ -488,12 +515,11 @@ static long run_batch(CINTOpt *c, int ncenter, int kind, const int *shls, size_t
         if (ctx_reserve(c, (void **)&c->d_out, &c->cap_out, sizeof(double) * total, false)) return CINTB200_ENOMEM;
         d_out = c->d_out;
     }
-    // fast path: tuples whose classes have a specialised tile kernel run there (driver.cu:list_mode_run); spherical,
-    // plain Coulomb, packed output below 2^31 elements (the kernels keep row offsets in 32 bits)
+    // fast path: tuples whose classes have a specialised tile kernel run there (driver.cu:list_mode_run);
+    // packed output below 2^31 elements (the kernels keep row offsets in 32 bits)
     std::vector<unsigned char> handled(n, 0);
-    static const bool list_fast = getenv("CINTB200_LIST_GENERIC") == nullptr;
-    if (list_fast && n >= 32 && !cart && cart_pos < 0 && !c->force_generic && total < ((size_t)1 << 31)) {   // single calls: generic kernel (lower latency)
-        if (list_mode_run(c, tasks.data(), n, d_out, handled.data())) return CINTB200_ENODEV;
+    if (list_fast && n >= 32 && cart_pos < 0 && !c->force_generic && total < ((size_t)1 << 31)) {   // single calls: generic kernel (lower latency)
+        if (list_mode_run(c, tasks.data(), n, d_out, handled.data(), cart)) return CINTB200_ENODEV;
     }
     // the rest: class-sorted order for the generic kernel
     const size_t n_all = n;

@@ -58,7 +58,9 @@ struct JobPlan;
 void jobplan_free(JobPlan *p);
 struct ListTables;
 void listtables_free(ListTables *lt);
-int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled);
+int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsigned char *handled, int cart = 0);
+int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t n, const size_t *out_off, double *d_out_or_null,
+                     double **d_out_used, size_t *total, int *nonzero);      // listdev.cu
 int ctx_compute_schwarz(CINTOpt *c);
 int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);

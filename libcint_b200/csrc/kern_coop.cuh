@@ -42,14 +42,15 @@ __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, in
     return (a > b ? a : b) | 1;
 }
 
-template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T, bool RS = false>
+template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T, bool RS = false, bool CART = false>
 __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
     constexpr int NE = cx_nrange(LA, LA + LB), NF = cx_nrange(LC, LC + LD);
     constexpr int NFA = cx_ncart(LA), NFB = cx_ncart(LB), NFC = cx_ncart(LC), NFD = cx_ncart(LD);
-    constexpr int DA = SphDim<LA>::value, DB = SphDim<LB>::value, DC = SphDim<LC>::value, DD = SphDim<LD>::value;
+    constexpr int DA = CART ? NFA : SphDim<LA>::value, DB = CART ? NFB : SphDim<LB>::value;          // CART: see kern_reg.cuh
+    constexpr int DC = CART ? NFC : SphDim<LC>::value, DD = CART ? NFD : SphDim<LD>::value;
     constexpr int NAB = DA * DB;
     constexpr int QPB = COOP_THREADS / FS;                       // quartets per block
     constexpr int NCT = REG_IS_T ? NCR : NCL, NCU = REG_IS_T ? NCL : NCR;
@@ -348,11 +349,11 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
         double abc[NFA * NFB];
         hrr_pair_reg<LA, LB, 1, 1>(ef, abc, abR);
         double s1[DA * NFB];
-        if constexpr (LA >= 2) c2s_reg<LA, 1, NFB>(abc, s1);
-        double *p1 = (LA >= 2) ? s1 : abc;
+        if constexpr (LA >= 2 && !CART) c2s_reg<LA, 1, NFB>(abc, s1);
+        double *p1 = (LA >= 2 && !CART) ? s1 : abc;
         double s2[DA * DB];
-        if constexpr (LB >= 2) c2s_reg<LB, DA, 1>(p1, s2);
-        double *p2 = (LB >= 2) ? s2 : p1;
+        if constexpr (LB >= 2 && !CART) c2s_reg<LB, DA, 1>(p1, s2);
+        double *p2 = (LB >= 2 && !CART) ? s2 : p1;
         // exchange: X[mab][f]
         if (lane < NF) {
 #pragma unroll
@@ -368,11 +369,11 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
             double cdc[NFC * NFD];
             hrr_pair_reg<LC, LD, 1, 1>(fr, cdc, abL);
             double s3[DC * NFD];
-            if constexpr (LC >= 2) c2s_reg<LC, 1, NFD>(cdc, s3);
-            double *p3 = (LC >= 2) ? s3 : cdc;
+            if constexpr (LC >= 2 && !CART) c2s_reg<LC, 1, NFD>(cdc, s3);
+            double *p3 = (LC >= 2 && !CART) ? s3 : cdc;
             double s4[DC * DD];
-            if constexpr (LD >= 2) c2s_reg<LD, DC, 1>(p3, s4);
-            double *p4 = (LD >= 2) ? s4 : p3;
+            if constexpr (LD >= 2 && !CART) c2s_reg<LD, DC, 1>(p3, s4);
+            double *p4 = (LD >= 2 && !CART) ? s4 : p3;
             const int ma = mab / DB, mb = mab - ma * DB;
             if (active) {
                 double *d2 = dst + ma * s_a + mb * s_b;

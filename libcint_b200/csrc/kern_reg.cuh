@@ -306,7 +306,7 @@ template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart
 // and lets three blocks share an SM instead of two.
 __host__ __device__ constexpr bool reg_acc_in_smem(int nct, int nacc) { return nct > 1 && nacc <= REG_ACC_SMEM_MAX; }
 
-template <int LA, int LB, int LC, int LD, int NCT, int NCU, bool RS = false>
+template <int LA, int LB, int LC, int LD, int NCT, int NCU, bool RS = false, bool CART = false>
 __global__ void __launch_bounds__(REG_THREADS, reg_acc_in_smem(NCT, NCT * NCU * cx_nrange(LA, LA + LB) * cx_nrange(LC, LC + LD)) ? 3 : REG_MIN_BLOCKS)
 eri_reg_kernel(const TileParams P)
 {
@@ -314,7 +314,9 @@ eri_reg_kernel(const TileParams P)
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;
     constexpr int NE = cx_nrange(LA, LA + LB), NF = cx_nrange(LC, LC + LD), NEF = NE * NF;
     constexpr int NFA = cx_ncart(LA), NFB = cx_ncart(LB), NFC = cx_ncart(LC), NFD = cx_ncart(LD);
-    constexpr int DA = SphDim<LA>::value, DB = SphDim<LB>::value, DC = SphDim<LC>::value, DD = SphDim<LD>::value;
+    // CART: Cartesian output (int2e_cart, c2s_cart_2e1 src/cart2sph.c:5845): the cart->sph stages of the epilogue are skipped
+    constexpr int DA = CART ? NFA : SphDim<LA>::value, DB = CART ? NFB : SphDim<LB>::value;
+    constexpr int DC = CART ? NFC : SphDim<LC>::value, DD = CART ? NFD : SphDim<LD>::value;
     constexpr int USTR = 9 + NCU;      // doubles per staged U primitive
 
     extern __shared__ double smem[];
@@ -626,17 +628,17 @@ eri_reg_kernel(const TileParams P)
         hrr_pair_reg<LC, LD, NFA * NFB, 1>(abf, abcd, abU);          // [a][b][c][d]
         // c2s on each index with l >= 2 (s, p are identities)
         double s1[DA * NFB * NFC * NFD];
-        if constexpr (LA >= 2) c2s_reg<LA, 1, NFB * NFC * NFD>(abcd, s1);
-        double *p1 = (LA >= 2) ? s1 : abcd;
+        if constexpr (LA >= 2 && !CART) c2s_reg<LA, 1, NFB * NFC * NFD>(abcd, s1);
+        double *p1 = (LA >= 2 && !CART) ? s1 : abcd;
         double s2[DA * DB * NFC * NFD];
-        if constexpr (LB >= 2) c2s_reg<LB, DA, NFC * NFD>(p1, s2);
-        double *p2 = (LB >= 2) ? s2 : p1;
+        if constexpr (LB >= 2 && !CART) c2s_reg<LB, DA, NFC * NFD>(p1, s2);
+        double *p2 = (LB >= 2 && !CART) ? s2 : p1;
         double s3[DA * DB * DC * NFD];
-        if constexpr (LC >= 2) c2s_reg<LC, DA * DB, NFD>(p2, s3);
-        double *p3 = (LC >= 2) ? s3 : p2;
+        if constexpr (LC >= 2 && !CART) c2s_reg<LC, DA * DB, NFD>(p2, s3);
+        double *p3 = (LC >= 2 && !CART) ? s3 : p2;
         double s4[DA * DB * DC * DD];
-        if constexpr (LD >= 2) c2s_reg<LD, DA * DB * DC, 1>(p3, s4);
-        double *p4 = (LD >= 2) ? s4 : p3;
+        if constexpr (LD >= 2 && !CART) c2s_reg<LD, DA * DB * DC, 1>(p3, s4);
+        double *p4 = (LD >= 2 && !CART) ? s4 : p3;
 
         const int cc = cu % nca_u, cd = cu / nca_u;
         double *dst = obase + cc * DC * sc + cd * DD * sd;

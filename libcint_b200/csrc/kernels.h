@@ -35,7 +35,7 @@ int tile_smem_limit();                        // largest dynamic shared memory p
 
 // register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
 typedef void (*RegKernelFn)(const TileParams);
-RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu, int rs = 0);     // rs: range-separated variant
+RegKernelFn reg_kernel_lookup(int la, int lb, int lc, int ld, int nct, int ncu, int rs = 0, int cart = 0);     // rs: range-separated variant, cart: Cartesian output
 int rys_tab_nint(int nroots);
 int rys_fast_nint(int nroots);
 int rys_fast_off(int nroots);
@@ -44,6 +44,6 @@ size_t reg_kernel_smem(RegKernelFn fn, int nroots, int ncu, int umax);       // 
 
 // cooperative kernels (kern_coop_inst*.cu): FS lanes per quartet
 struct CoopInfo { int fs, xsz, nroots; };
-RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info, int rs = 0);
+RegKernelFn coop_kernel_lookup(int tla, int tlb, int ula, int ulb, int nct, int ncu, CoopInfo *info, int rs = 0, int cart = 0);
 int coop_kernel_launch(RegKernelFn fn, const CoopInfo &info, int ncu, const TileParams &P, int grid_x, int grid_y, cudaStream_t stream);
 size_t coop_kernel_smem(const CoopInfo &info, int ncu, int umax);

@@ -15,7 +15,7 @@ def pinned_sinks(n, nbytes):
     return [torch.empty(max(1, nbytes // 8), dtype=torch.float64, pin_memory=True) for _ in range(n)]
 
 
-def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 28, max_quartets=None, tol=1e-12, omega=None, nsinks=2):
+def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 28, max_quartets=None, tol=1e-12, omega=None, nsinks=2, cart=False):
     """Whole job through the host-tile path (ring of pinned sinks + callback): EVERY chunk is delivered to the host and its
     blocks are compared element-wise with the oracle; entries outside the loop (k > i) must arrive as zeros."""
     which, _ = ou.best()
@@ -26,7 +26,8 @@ def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 28, max_quar
         if omega < 0:
             which = "port"                  # the port evaluates erfc as full - erf in extended precision roots
     nbas = len(bas)
-    dims = [(2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    dims = [((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in bas]
+    intor = "int2e_cart" if cart else "int2e_sph"
     total_q = 0
     worst = [0.0]
     rng = np.random.default_rng(1)
@@ -60,13 +61,13 @@ def check_job(name, nranks=1, force_generic=False, chunk_bytes=1 << 28, max_quar
                     if k_ > i:              # outside the loop of examples/time_c60.c:206: never evaluated, delivered as zeros
                         assert not got.any(), (name, rank, (i, j, k_, l))
                         continue
-                    want, _ = ou.eval_tuple(which, "int2e_sph", (i, j, k_, l), atm, bas, env)
+                    want, _ = ou.eval_tuple(which, intor, (i, j, k_, l), atm, bas, env)
                     err = np.abs(got - want.reshape((nb, nk), order="F")).max()
                     scale = max(1.0, np.abs(want).max())
                     assert err <= tol * scale, (name, rank, (i, j, k_, l), err)
                     worst[0] = max(worst[0], err / scale)
 
-        st = ctx.all_unique_tiles([t.data_ptr() for t in sinks], on_tile, rank=rank, nranks=nranks, chunk_bytes=chunk_bytes)
+        st = ctx.all_unique_tiles([t.data_ptr() for t in sinks], on_tile, rank=rank, nranks=nranks, chunk_bytes=chunk_bytes, cart=cart)
         total_q += st[0]
         assert seen == sorted(set(seen)) and len(seen) <= int(st[9]), seen      # chunks arrive once each, in order
         if nranks == 1:
@@ -123,6 +124,28 @@ def test_range_separated_density_fitting_and_blocks():
     env[8] = 0.4
     ctx = cb.Context(atm, bas, env)
     _check_block(ctx, atm, bas, env, (norb, len(bas), norb, len(bas)), "int2c2e_sph", 1500, rng, tol=1e-11)
+
+
+def test_tiles_cartesian_output_specialised_kernels():
+    # int2e_cart (north star: part of the hot path) from the register / cooperative kernels with the c2s stages compiled out:
+    # every block of every chunk against the oracle's int2e_cart, d shells (cc-pVDZ) and f shells (cc-pVTZ), 1 and 2 ranks
+    check_job("c2h6_ccpvdz", cart=True, max_quartets=40000)
+    check_job("c2h6_ccpvdz", cart=True, nranks=2, chunk_bytes=4_000_000, max_quartets=30000)
+    check_job("c2h6_ccpvtz", cart=True, max_quartets=6000)
+    # the launches really are specialised kernels
+    atm, bas, env = cb.load_fixture("c2h6_ccpvdz")
+    ctx = cb.Context(atm, bas, env)
+    ctx.all_unique(cart=True)
+    assert set(ctx.launch_rows()[:, 7].astype(int)) <= {1, 2}
+    # dense Cartesian blocks and list-mode batches (kind = CART) agree with the oracle too
+    rng = np.random.default_rng(5)
+    _check_block(ctx, atm, bas, env, (0, 14, 3, 20, 5, 28, 0, 9), "int2e_cart", 1500, rng)
+    q = rng.integers(0, len(bas), size=(4000, 4)).astype(np.int32)
+    v, o, s, nz = ctx.int2e_batch(q, kind=cb.CART)
+    which, _ = ou.best()
+    for n in rng.choice(len(q), 300, replace=False):
+        want, _ = ou.eval_tuple(which, "int2e_cart", q[n], atm, bas, env)
+        assert np.abs(v[o[n]:o[n] + s[n]] - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), q[n]
 
 
 def test_tiles_multi_chunk():
@@ -350,8 +373,9 @@ def _check_block(ctx, atm, bas, env, sl, name, nsample, rng, tol=1e-12):
     """dense shell-slice tensor against the oracle, quartet by quartet (all of them, or a random sample)"""
     which, _ = ou.best()
     nc = len(sl) // 2
-    arr, st = (ctx.int2e_block(sl) if nc == 4 else ctx.int3c2e_block(sl) if nc == 3 else ctx.int2c2e_block(sl))
-    ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+    cart = name.endswith("cart")
+    arr, st = (ctx.int2e_block(sl, cart=cart) if nc == 4 else ctx.int3c2e_block(sl, cart=cart) if nc == 3 else ctx.int2c2e_block(sl, cart=cart))
+    ao = np.concatenate([[0], np.cumsum([((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
     ranges = [range(sl[2 * m], sl[2 * m + 1]) for m in range(nc)]
     import itertools
     tuples = list(itertools.product(*ranges))

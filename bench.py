@@ -248,57 +248,106 @@ def extra_workloads(cb, torch, local, steps, cpu_threads, affinity, with_cpu):
     for label, q in lists.items():
         nint = int(np.prod(dims[q], axis=1).sum())
         dbuf = torch.empty(nint, dtype=torch.float64, device="cuda")
+        import ctypes
+        f = c.lib.cintb200_int2e_batch          # the C entry point itself: host shell list in, packed device-resident output
         ts = []
         for k in range(1 + steps):
             t0 = time.perf_counter()
-            c.int2e_batch(q, device_ptr=dbuf.data_ptr())
+            rc = f(c.handle, 0, q.ctypes.data_as(ctypes.c_void_p), len(q), None, ctypes.c_void_p(dbuf.data_ptr()), 1, None)
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
+            assert rc == len(q), rc
         t = sum(ts[1:]) / steps
         lm[label] = {"value": nint / t, "quartets_per_s": len(q) / t, "s_per_call": t, "quartets": len(q), "integrals": nint}
         del dbuf
     c.close()
     out["list_mode"] = {"unit": "integrals/s", "workload": "cintb200_int2e_batch on 1e6 C60 cc-pVDZ shell quartets (random / 1000 bra pairs x 1000 kets), host shell list in, "
-                        "packed device-resident output, wall clock incl. the host-side sorting of the list", "cases": lm}
-    # ---- configs[3]: class sweep s..h, one contracted quartet (3 primitives x 2 contractions per shell) per class, many copies ----
+                        "packed device-resident output; wall clock of the C call incl. the upload of the list and the device-side keying / sorting / item building", "cases": lm}
+    # ---- first derivatives on the tile kernels: the gradient loop of examples/time_c2h6.c:798-835 on C2H6 cc-pVQZ ----
+    atm, bas, env = cb.load_fixture("c2h6_ccpvqz")
+    c = cb.Context(atm, bas, env, device=local)
+    nb = len(bas)
+    dims = np.array([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])
+    nao = int(dims.sum())
+    dbuf = torch.empty(3 * nao * nao * int(dims.max()) * nao, dtype=torch.float64, device="cuda")
+
+    def ip1_pass():
+        ms, nint = 0.0, 0
+        t0 = time.perf_counter()
+        for k in range(nb):                     # all ordered (i,j), k >= l: one dense block per ket shell k
+            _, st = c.ip1_block((0, nb, 0, nb, k, k + 1, 0, k + 1), device_ptr=dbuf.data_ptr())
+            ms += float(st[7])
+            nint += int(st[1])
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0, ms, nint
+    ip1_pass()
+    ts = [ip1_pass() for _ in range(steps)]
+    wall = sum(t[0] for t in ts) / steps
+    tot1 = float(nao) ** 4 / 2 * 3              # the reference driver's count (examples/time_c2h6.c:799)
+    out["int2e_ip1"] = {"unit": "integrals/s", "value": tot1 / wall, "s_per_pass": wall, "eri_kernel_ms": sum(t[1] for t in ts) / steps,
+                        "integrals_written": ts[0][2], "integrals_counted": tot1,
+                        "workload": "C2H6 cc-pVQZ, ( nabla i j | k l ) for all ordered (i,j) and k >= l (the gradient loop of examples/time_c2h6.c:798-835) "
+                                    "through cintb200_int2e_ip1_block, one dense block per ket shell k, device-resident output, wall clock"}
+    del dbuf
+    if with_cpu:
+        exe = os.path.join(ROOT, "oracle", "_ref", "time_ref")
+        lib = os.path.join(ROOT, "oracle", "_ref", "libcint_ref.so")
+        if os.path.exists(exe):
+            with tempfile.TemporaryDirectory() as tmp:
+                bb = os.path.join(tmp, "basis.bin")
+                dump_basis_bin(bb, atm, bas, env)
+                e = dict(os.environ)
+                e["OMP_NUM_THREADS"] = str(cpu_threads)
+                stride = 8
+                r = subprocess.run([exe, lib, bb, "ip1", str(stride)], capture_output=True, text=True, env=e, timeout=1800,
+                                   preexec_fn=(lambda: os.sched_setaffinity(0, affinity)) if affinity else None)
+                if r.returncode == 0:
+                    j = json.loads(r.stdout.strip().splitlines()[-1])
+                    out["int2e_ip1"]["cpu_baseline"] = {"value": j["integrals"] * (tot1 / (3.0 * nao ** 2 * sum(int(dims[k]) * int(dims[:k + 1].sum()) for k in range(nb)))) / j["seconds"],
+                                                        "cores": j["threads"], "kind": "reference",
+                                                        "sample": "every %d-th ordered (i,j) pair, all k >= l, %.1f s" % (stride, j["seconds"])}
+    c.close()
+    # ---- configs[3]: class sweep s..h, one shell quartet per symmetry-unique angular class, many copies ----
     from libcint_b200.basis import class_sweep_basis
     lmax = 5
-    atm, bas, env = class_sweep_basis(lmax=lmax)
-    c = cb.Context(atm, bas, env, device=local)
     classes = sweep_classes(lmax)
-    sw = []
-    ref_rows = []
-    for cls in classes:
-        sh = [cen * (lmax + 1) + l for cen, l in enumerate(cls)]
-        reps = sweep_reps(cls, 2, 4e8)
-        q = np.tile(np.array(sh, np.int32), (reps, 1))
-        n1 = int(np.prod([(2 * l + 1) * 2 for l in cls]))
-        dbuf = torch.empty(n1 * reps, dtype=torch.float64, device="cuda")
-        ts = []
-        for k in range(3):
-            t0 = time.perf_counter()
-            c.int2e_batch(q, device_ptr=dbuf.data_ptr())
-            torch.cuda.synchronize()
-            ts.append(time.perf_counter() - t0)
-        del dbuf
-        t = min(ts[1:])
-        sw.append({"class": "(%s%s|%s%s)" % tuple("spdfgh"[l] for l in cls), "reps": reps, "value": n1 * reps / t, "us_per_quartet": 1e6 * t / reps})
-        ref_rows.append(tuple(sh) + (max(8, reps // 50),))
-    if with_cpu:
-        rr = run_reference_sweep(atm, bas, env, ref_rows, cpu_threads, affinity)
-        if rr is not None:
-            for row, (sec, n1), rrow in zip(sw, rr[0], ref_rows):
-                row["cpu_value"] = n1 * rrow[4] / sec
-                row["speedup"] = row["value"] / row["cpu_value"]
-            out_threads = rr[1]
-    c.close()
-    slow = sorted(sw, key=lambda r: r.get("speedup", 1e30))[:5]
-    out["class_sweep"] = {"unit": "integrals/s", "workload": "one contracted shell quartet per symmetry-unique angular class (li>=lj, lk>=ll, ij>=kl), l = s..h, 4 centres of "
-                          "testsuite/test_cint.py:51-58, 3 primitives x 2 contractions per shell; `reps` copies per class through cintb200_int2e_batch "
-                          "(device-resident output, wall clock incl. host list handling); cpu_value = the reference on the host cores, reps/50 copies",
-                          "classes": len(sw), "cpu_cores": out_threads if with_cpu and rr is not None else None,
-                          "geomean_speedup": float(np.exp(np.mean([np.log(r["speedup"]) for r in sw]))) if sw and "speedup" in sw[0] else None,
-                          "slowest_vs_cpu": slow, "rows": sw}
+    flavours = {}
+    for label, nctr in (("general_contraction_3x2", 2), ("segmented_3x1", 1)):
+        atm, bas, env = class_sweep_basis(lmax=lmax, nctr=nctr)
+        c = cb.Context(atm, bas, env, device=local)
+        sw, ref_rows = [], []
+        for cls in classes:
+            sh = [cen * (lmax + 1) + l for cen, l in enumerate(cls)]
+            reps = sweep_reps(cls, nctr, 4e8)
+            q = np.tile(np.array(sh, np.int32), (reps, 1))
+            n1 = int(np.prod([(2 * l + 1) * nctr for l in cls]))
+            dbuf = torch.empty(n1 * reps, dtype=torch.float64, device="cuda")
+            ts = []
+            for k in range(3):
+                t0 = time.perf_counter()
+                c.int2e_batch(q, device_ptr=dbuf.data_ptr())
+                torch.cuda.synchronize()
+                ts.append(time.perf_counter() - t0)
+            del dbuf
+            t = min(ts[1:])
+            sw.append({"class": "(%s%s|%s%s)" % tuple("spdfgh"[l] for l in cls), "reps": reps, "value": n1 * reps / t, "us_per_quartet": 1e6 * t / reps})
+            ref_rows.append(tuple(sh) + (max(8, reps // 50),))
+        threads = None
+        if with_cpu:
+            rr = run_reference_sweep(atm, bas, env, ref_rows, cpu_threads, affinity)
+            if rr is not None:
+                threads = rr[1]
+                for row, (sec, n1), rrow in zip(sw, rr[0], ref_rows):
+                    row["cpu_value"] = n1 * rrow[4] / sec
+                    row["speedup"] = row["value"] / row["cpu_value"]
+        c.close()
+        flavours[label] = {"classes": len(sw), "cpu_cores": threads,
+                           "geomean_speedup": float(np.exp(np.mean([np.log(r["speedup"]) for r in sw]))) if sw and "speedup" in sw[0] else None,
+                           "slowest_vs_cpu": sorted(sw, key=lambda r: r.get("speedup", 1e30))[:5], "rows": sw}
+    out["class_sweep"] = {"unit": "integrals/s", "workload": "one shell quartet per symmetry-unique angular class (li>=lj, lk>=ll, ij>=kl), l = s..h, 4 centres of "
+                          "testsuite/test_cint.py:51-58, 3 primitives per shell with 2 general contractions (SURVEY config 4) and with 1 (segmented, what real "
+                          "basis sets have above p); `reps` copies per class through cintb200_int2e_batch (device-resident output, wall clock incl. list handling); "
+                          "cpu_value = the reference on the host cores, reps/50 copies", "flavours": flavours}
     return out
 
 

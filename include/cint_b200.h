@@ -196,6 +196,13 @@ int cintb200_int2e_cart_all_unique(cintb200_ctx *ctx, int rank, int nranks, size
 int cintb200_int2e_cart_all_unique_tiles(cintb200_ctx *ctx, int rank, int nranks, size_t chunk_bytes, double *const *sinks, int nsinks,
                                          cintb200_tile_fn fn, void *user, double *stats);
 
+/* First derivatives on dense shell-slice blocks, evaluated by the specialised kernels (raised / lowered shell blocks in Cartesians,
+ * derivative and cart->sph on the dense tensor):  ( nabla i j | k l ), int2e_ip1_sph / _cart (src/autocode/grad2.c:19-68) and
+ * ( nabla i j | k ), int3c2e_ip1 (src/autocode/int3c2e.c).  out[i + NI (j + NJ (k + NK (l + NL comp)))], comp = x, y, z: 3x the plain
+ * block; kind = CINTB200_SPH or CINTB200_CART; shls_slice as for the plain block calls. */
+int cintb200_int2e_ip1_block(cintb200_ctx *ctx, int kind, const int *shls_slice, double *out, int on_device, double *stats);
+int cintb200_int3c2e_ip1_block(cintb200_ctx *ctx, int kind, const int *shls_slice, double *out, int on_device, double *stats);
+
 /* Schwarz screening of the whole-job driver: work items (32 quartets) whose bounds sqrt(max|(ij|ij)|) * sqrt(max|(kl|kl)|)
  * are all below `thr` are not evaluated and their blocks are zero-filled.  Default 1e-15 (errors below the 1e-12 parity
  * tolerance by construction); 0 switches it off.  The bounds are evaluated on the device on first use.

@@ -339,6 +339,27 @@ class Context:
         """Dense (NI,NK) matrix of int2c2e_sph / int2c2e_cart over shell slices (i0,i1,k0,k1): the density-fitting metric."""
         return self._block(self.lib.cintb200_int2c2e_cart_block if cart else self.lib.cintb200_int2c2e_sph_block, 2, shls_slice, device_ptr, cart)
 
+    def ip1_block(self, shls_slice, kind=SPH, device_ptr=None):
+        """( nabla i j | k l ) (8 slice bounds) or ( nabla i j | k ) (6 bounds) over shell slices: array of shape (NI, NJ, NK[, NL], 3)."""
+        sl = np.ascontiguousarray(shls_slice, dtype=np.int32).reshape(-1)
+        nc = sl.size // 2
+        fn = self.lib.cintb200_int2e_ip1_block if nc == 4 else self.lib.cintb200_int3c2e_ip1_block
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+        cart = kind == CART
+        ao = np.concatenate([[0], np.cumsum([((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in self.bas])])
+        shape = tuple(int(ao[sl[2 * m + 1]] - ao[sl[2 * m]]) for m in range(nc)) + (3,)
+        stats = np.zeros(16)
+        if device_ptr is not None:
+            rc = fn(self.handle, kind, _p(sl), ctypes.c_void_p(device_ptr), 1, _p(stats))
+            out = None
+        else:
+            out = np.zeros(shape, order="F")
+            rc = fn(self.handle, kind, _p(sl), _p(out), 0, _p(stats))
+        if rc < 0:
+            raise B200Error("ip1 block failed (%d): %s" % (rc, self.lib.cintb200_last_error().decode()))
+        return out, stats
+
     def aux_offset(self, k):
         """This rank's column offset of auxiliary shell k in the tiles of int3c2e_all (-1: owned by another rank)."""
         f = self.lib.cintb200_debug_aux_offset

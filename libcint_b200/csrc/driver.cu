@@ -338,41 +338,36 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
         for (size_t n = 0; n < NT; n++) pc.npp_prefix[n + 1] = pc.npp_prefix[n] + pc.npp[n];
         if (plan->host_only) continue;
         const int nct = pc.nca * pc.ncb, Q = pc.Q;
-        auto build = [&](const std::vector<int> &ids, const std::vector<int> &I, const std::vector<int> &npp,
-                         double **d_tprim, double **d_tgeom, long long **d_trow, int **d_tstride, int **d_tI,
-                         int **d_tpair, int **d_tnpp, long long **d_ucol, int **d_ustride) -> int {
-            std::vector<double> tprim((size_t)(6 + nct) * Q * NT), tgeom(6 * NT);
-            std::vector<long long> trow(NT), ucol(NT);
-            std::vector<int> tstride(2 * NT);
-            for (size_t n = 0; n < NT; n++) {
-                const int p = ids[n];
+        // ONE table set per class holding both orderings back to back: rows [0, NT) = ordering A (per chunk by descending primitive
+        // count), rows [NT, 2 NT) = ordering B (by the larger shell index), so that a single launch can serve the kets below the
+        // chunk's bra shells (all bras valid, A) and the chunk's own kets (valid bras = a suffix of B): see build_launches
+        {
+            const size_t N2 = 2 * NT;
+            std::vector<double> tprim((size_t)(6 + nct) * Q * N2), tgeom(6 * N2);
+            std::vector<long long> trow(N2), ucol(NT);
+            std::vector<int> tstride(2 * N2), ustride(2 * NT), tI(N2), tids(N2), nppc(N2);
+            for (size_t n = 0; n < N2; n++) {
+                const bool B = n >= NT;
+                const int p = B ? pc.idsB[n - NT] : pc.ids[n], i = B ? pc.IB[n - NT] : pc.I[n];
                 const PairHdr &h = c->pairs[p];
-                fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
+                fill_tprim(c, h, n, N2, Q, nct, tprim, tgeom);
                 // strides of the canonical indices inside the (i,j) block: i fastest
-                const int i = I[n];
                 const int di = (int)sdim(i);
                 const bool a_is_i = (h.sh_a == i);
-                tstride[n] = a_is_i ? 1 : di;  tstride[NT + n] = a_is_i ? di : 1;
+                tstride[n] = a_is_i ? 1 : di;  tstride[N2 + n] = a_is_i ? di : 1;
                 trow[n] = plan->rowoff[p];
-                ucol[n] = colof[p];
+                tI[n] = i; tids[n] = p;
+                nppc[n] = std::max(B ? pc.nppB[n - NT] : pc.npp[n], 1);       // dead pairs still run one zero-weight primitive
+                if (!B) { ucol[n] = colof[p]; ustride[n] = tstride[n]; ustride[NT + n] = tstride[N2 + n]; }
             }
-            std::vector<int> nppc(npp);
-            for (int &v : nppc) v = std::max(v, 1);       // dead pairs still run one zero-weight primitive
-            if (upload(d_tprim, tprim) || upload(d_tgeom, tgeom) || upload(d_trow, trow) || upload(d_tstride, tstride) ||
-                upload(d_tI, I) || upload(d_tpair, ids) || upload(d_tnpp, nppc))
+            if (upload(&pc.d_tprim, tprim) || upload(&pc.d_tgeom, tgeom) || upload(&pc.d_trow, trow) || upload(&pc.d_tstride, tstride) ||
+                upload(&pc.d_tI, tI) || upload(&pc.d_tpair, tids) || upload(&pc.d_tnpp, nppc) || upload(&pc.d_ucol, ucol) || upload(&pc.d_ustride, ustride))
                 return CINTB200_ENOMEM;
-            if (d_ucol && (upload(d_ucol, ucol) || upload(d_ustride, tstride))) return CINTB200_ENOMEM;
-            return 0;
-        };
-        if (build(pc.ids, pc.I, pc.npp, &pc.d_tprim, &pc.d_tgeom, &pc.d_trow, &pc.d_tstride, &pc.d_tI, &pc.d_tpair, &pc.d_tnpp,
-                  &pc.d_ucol, &pc.d_ustride) ||
-            build(pc.idsB, pc.IB, pc.nppB, &pc.dB_tprim, &pc.dB_tgeom, &pc.dB_trow, &pc.dB_tstride, &pc.dB_tI, &pc.dB_tpair, &pc.dB_tnpp,
-                  nullptr, nullptr))
-            return CINTB200_ENOMEM;
-        if (!c->schwarz.empty()) {
-            std::vector<double> qa(NT), qb(NT);
-            for (size_t n = 0; n < NT; n++) { qa[n] = c->schwarz[pc.ids[n]]; qb[n] = c->schwarz[pc.idsB[n]]; }
-            if (upload(&pc.d_tq, qa) || upload(&pc.dB_tq, qb)) return CINTB200_ENOMEM;
+            if (!c->schwarz.empty()) {
+                std::vector<double> q2(N2);
+                for (size_t n = 0; n < N2; n++) q2[n] = c->schwarz[n >= NT ? pc.idsB[n - NT] : pc.ids[n]];
+                if (upload(&pc.d_tq, q2)) return CINTB200_ENOMEM;
+            }
         }
     }
     if (plan->host_only) return 0;
@@ -416,11 +411,14 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
             std::vector<PairClass> &UC = (plan->ncenter == 3) ? plan->uclasses : plan->classes;
             for (size_t cu = 0; cu < UC.size(); cu++) {
               PairClass &U = UC[cu];
-              // part 0: kets below the chunk's shell range (every bra of the chunk is valid; bras sorted by primitive count)
+              // part 0: kets below the chunk's shell range (every bra of the chunk is valid; bras sorted by primitive count: ordering A)
               // part 1: kets inside it (valid bras = those with I >= K: a suffix of the shell-sorted ordering B)
+              // part 2: both in ONE launch (the kernel picks the ordering per ket): half the launches; CINTB200_MERGE=0 keeps them apart
               // 3-centre jobs: every auxiliary ket meets every bra pair of the chunk -> part 0 only, all kets
-              for (int part = 0; part < (plan->ncenter == 3 ? 1 : 2); part++) {
-                const int u_lo = part == 0 ? 0 : U.chunk_lo[ch], u_hi = part == 0 ? U.chunk_lo[ch] : U.chunk_lo[ch + 1];
+              static const bool merge = !(getenv("CINTB200_MERGE") && !atoi(getenv("CINTB200_MERGE")));
+              const int part_first = (plan->ncenter == 3) ? 0 : merge ? 2 : 0, part_last = (plan->ncenter == 3) ? 0 : merge ? 2 : 1;
+              for (int part = part_first; part <= part_last; part++) {
+                const int u_lo = part == 1 ? U.chunk_lo[ch] : 0, u_hi = part == 0 ? U.chunk_lo[ch] : U.chunk_lo[ch + 1];
                 // this rank's kets in [u_lo, u_hi): indices congruent to rank modulo nranks
                 int u_first = u_lo + ((rank - u_lo) % nranks + nranks) % nranks;
                 if (u_first >= u_hi) continue;
@@ -428,14 +426,12 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
                 LaunchRec L;
                 memset(&L, 0, sizeof L);
                 TileParams &P = L.P;
-                if (part == 0) {
-                    P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
-                    P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp; P.tq = T.d_tq;
-                } else {
-                    P.tprim = T.dB_tprim; P.tgeom = T.dB_tgeom; P.trow = T.dB_trow; P.tstride = T.dB_tstride;
-                    P.tI = T.dB_tI; P.tpair = T.dB_tpair; P.tnpp = T.dB_tnpp; P.tq = T.dB_tq;
-                }
-                P.NT = (int)T.ids.size(); P.NTs = P.NT; P.Q = T.Q; P.t_begin = t_begin; P.t_end = t_end; P.nca_t = T.nca;
+                P.tprim = T.d_tprim; P.tgeom = T.d_tgeom; P.trow = T.d_trow; P.tstride = T.d_tstride;
+                P.tI = T.d_tI; P.tpair = T.d_tpair; P.tnpp = T.d_tnpp; P.tq = T.d_tq;
+                const int NT1 = (int)T.ids.size(), tB = (plan->ncenter == 3) ? 0 : NT1;       // rect / 3-centre plans hold ordering A only
+                P.NT = plan->rect ? NT1 : 2 * NT1; P.NTs = P.NT; P.Q = T.Q; P.nca_t = T.nca;
+                P.t_begin = t_begin + (part == 1 ? tB : 0); P.t_end = t_end + (part == 1 ? tB : 0);
+                P.tB = part == 2 ? tB : 0; P.tri_i0 = i0;
                 P.upair = U.d_tpair; P.uK = U.d_tI; P.ucol = U.d_ucol; P.ustride = U.d_ustride;
                 P.NU = nu_mine; P.NU_all = (int)U.ids.size(); P.u_step = nranks; P.u_first = u_first; P.nca_u = U.nca; P.umax = std::max(1, U.Q);
                 P.tri = part;
@@ -1250,7 +1246,7 @@ static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntr
 }
 
 // ncenter 4: shls_slice = {i0,i1, j0,j1, k0,k1, l0,l1};  ncenter 3: {i0,i1, j0,j1, k0,k1}
-static int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_device, double *stats, int cart = 0)
+int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_device, double *stats, int cart)
 {
     if (!c || c->magic != B200_CTX_MAGIC) return b200_fail(CINTB200_EINVAL, "invalid context");
     if (!sl || !out) return b200_fail(CINTB200_EINVAL, "NULL shls_slice/out");

@@ -25,12 +25,10 @@ struct PairClass {
     int *d_tstride = nullptr, *d_tI = nullptr, *d_tpair = nullptr, *d_ustride = nullptr, *d_tnpp = nullptr;
     std::vector<int> chunk_lo;              // first list index of every chunk (+ end)
     // second ordering of the same pairs for the DIAGONAL kets of a chunk (K inside the chunk's bra shell range):
-    // sorted by the larger shell index (then by primitive count), so the valid bras of a ket are a suffix
+    // sorted by the larger shell index (then by primitive count), so the valid bras of a ket are a suffix.  The device
+    // tables above hold both orderings back to back (rows [0, NT) and [NT, 2 NT)).
     std::vector<int> idsB, IB, nppB;
-    double *dB_tprim = nullptr, *dB_tgeom = nullptr;
-    long long *dB_trow = nullptr;
-    int *dB_tstride = nullptr, *dB_tI = nullptr, *dB_tpair = nullptr, *dB_tnpp = nullptr;
-    double *d_tq = nullptr, *dB_tq = nullptr;   // Schwarz bounds in both orderings
+    double *d_tq = nullptr;                 // Schwarz bounds, same two orderings
 };
 
 struct LaunchRec {

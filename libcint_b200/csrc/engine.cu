@@ -681,7 +681,7 @@ __global__ void ip1_assemble_kernel(const IpTask *__restrict__ tasks, size_t nta
     }
 }
 
-static CINTOpt *ctx_deriv(CINTOpt *c)
+CINTOpt *ctx_deriv(CINTOpt *c)
 {
     std::lock_guard<std::mutex> lock(c->mtx);
     if (c->deriv) return c->deriv;
@@ -767,8 +767,11 @@ static long run_batch_ip(CINTOpt *c, int ncenter, int dpos, int kind, const int 
     d_o = out;
     if (!on_device && cudaMalloc(&d_o, sizeof(double) * toto) != cudaSuccess) { d_o = nullptr; cleanup(); return b200_fail(CINTB200_ENOMEM, "derivative output allocation failed"); }
     std::vector<int> nzp(n, 0), nzm(offm.size(), 0);
-    long rc = run_batch(d, ncenter, kind, shp.data(), n, offp.data(), d_p, 1, nzp.data(), dpos);
-    if (rc >= 0 && !offm.empty()) rc = run_batch(d, ncenter, kind, shm.data(), offm.size(), offm.data(), d_m, 1, nzm.data(), dpos);
+    // Cartesian kind: every index of the helper blocks is Cartesian anyway, so they are ordinary int2e_cart batches and run on
+    // the specialised tile kernels (list mode); spherical kind: the differentiated index alone stays Cartesian (generic kernel)
+    const int cpos = cart ? -1 : dpos;
+    long rc = run_batch(d, ncenter, kind, shp.data(), n, offp.data(), d_p, 1, nzp.data(), cpos);
+    if (rc >= 0 && !offm.empty()) rc = run_batch(d, ncenter, kind, shm.data(), offm.size(), offm.data(), d_m, 1, nzm.data(), cpos);
     if (rc < 0) { cleanup(); return rc; }
     {
         std::lock_guard<std::mutex> lock(c->mtx);

@@ -62,6 +62,9 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
 int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t n, const size_t *out_off, double *d_out_or_null,
                      double **d_out_used, size_t *total, int *nonzero);      // listdev.cu
 int ctx_compute_schwarz(CINTOpt *c);
+CINTOpt *ctx_deriv(CINTOpt *c);         // helper context with raised / lowered copies of every shell (engine.cu)
+// dense shell-slice block on the tile kernels (driver.cu); ncenter 2, 3 or 4, cart: Cartesian output
+int run_block(CINTOpt *c, int ncenter, const int *sl, double *out, int on_device, double *stats, int cart = 0);
 int ctx_new_host(CINTOpt **out, const int *atm, int natm, const int *bas, int nbas, const double *env);
 int b200_fail(int code, const char *fmt, ...);
 // CINTB200_TIMING=1: host-phase timings on stderr (context build, plan build, job execution)

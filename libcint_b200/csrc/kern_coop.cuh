@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
     double *s_q = s_rys + nint * rys_smem_stride(N) + (size_t)NWARP * P.umax * USTR + (size_t)q * XSZ;      // this quartet's area
     double *s_rw = s_q + GSZ;                                   // [2N] t2/w of the current primitive
     const long long total = P.items ? P.nitems : (long long)P.gx * P.NU;
-    int cur_by = -1, t_lo = P.t_begin;
+    int cur_by = -1, t_lo = P.t_begin, t_hi_k = P.t_end;
     PairHdr hu;
     __syncthreads();                    // table staged; warps are independent from here on (see kern_reg.cuh)
     for (;;) {
@@ -115,14 +115,18 @@ __global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_n
         }
         __syncwarp();
         cur_by = by;
-        t_lo = P.t_begin;               // see kern_reg.cuh for the two tile orderings; once per ket, not per work item
+        t_lo = P.t_begin; t_hi_k = P.t_end;      // see kern_reg.cuh for the two tile orderings; once per ket, not per work item
         if (P.tri) {
             const int K = P.uK[u];
-            int lo = P.t_begin, hi = P.t_end;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
-            t_lo = lo;
+            if (P.tri == 1 || K >= P.tri_i0) {
+                int lo = P.t_begin + P.tB, hi = P.t_end + P.tB;
+                t_hi_k = hi;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tI[mid] < K) lo = mid + 1; else hi = mid; }
+                t_lo = lo;
+            }
         }
     }
+    if (!P.items) t_hi = t_hi_k;
     const int t0 = P.items ? t0l : t_lo + bx * QPW;
     if (t0 >= t_hi) continue;            // warp-uniform
     const int t = t0 + (q - warp * QPW);

@@ -13,9 +13,12 @@
 //                                                                                [e0|f0] (exact identity; the reference
 //                                                                                applies it per primitive and root)
 //   cart->sph, scatter           c2s_sph_2e1            src/cart2sph.c:5324    -> dense small matrices, strided store
+#include <algorithm>
+#include <cstdlib>
 #include "types.h"
 #include "rys.cuh"
 #include "kernels.h"
+#include "tile_task.cuh"
 
 __constant__ int c_cart_off[2 * B200_LMAX + 2];                 // first component of degree l
 __constant__ unsigned char c_cart_xyz[3 * 560];                 // (lx,ly,lz) of every component, l = 0..2*LMAX
@@ -80,26 +83,6 @@ __device__ void c2s_index(const double *in, double *out, int pre, int post, int 
     }
 }
 
-// tile mode: work item w -> (u, t) of the rectangle (this rank's kets) x (T pairs of the chunk);
-// returns bra = -1 for quartets outside the reference loop bound k <= i
-__device__ __forceinline__ Task tile_task(const TileParams &T, long long w)
-{
-    const int nT = T.t_end - T.t_begin;
-    const int j = (int)(w / nT);
-    const int t = T.t_begin + (int)(w - (long long)j * nT);
-    const int u = T.u_first + T.u_step * j;
-    Task k;
-    k.bra = (T.tri && T.tI[t] < T.uK[u]) ? -1 : T.tpair[t];      // tri = 1 lists are shell-sorted; a predicate is enough here
-    k.ket = T.upair[u];
-    k.sa = T.tstride[t];
-    k.sb = T.tstride[T.NT + t];
-    k.sc = (long long)T.ustride[u] * T.ld;
-    k.sd = (long long)T.ustride[T.NU_all + u] * T.ld;
-    k.off = (T.trow[t] - T.row0) + T.ucol[u] * T.ld;
-    k.flags = 0; k.pad = 0;
-    return k;
-}
-
 __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
                                    double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters,
                                    TileParams TP, const long long *__restrict__ uprefix)
@@ -145,16 +128,19 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
     const double common = 34.986836655249725693 /* 2 pi^3 / sqrt(pi) */
         * (la < 2 ? fsp[la] : 1.0) * (lb < 2 ? fsp[lb] : 1.0) * (lc < 2 ? fsp[lc] : 1.0) * (ld < 2 ? fsp[ld] : 1.0);
 
-    for (long long t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    // epilogue-only mode (C.epilogue_only): the [e0|f0] accumulators of task C.task_base + blockIdx.x were produced by the wide
+    // kernel (kern_wide.cu) in this block's scratch; only HRR, cart->sph and the store remain
+    const bool epi = C.epilogue_only != 0;
+    for (long long t = epi ? C.task_base + blockIdx.x : blockIdx.x; t < ntasks; t += epi ? ntasks : gridDim.x) {
         const Task task = tasks ? tasks[t] : tile_task(TP, t);
         if (task.bra < 0) continue;          // block-uniform
         const PairHdr hb = P.pairs[task.bra];
         const PairHdr hk = P.pairs[task.ket];
         __syncthreads();
-        for (int i = tid; i < ncomb * nEF; i += blockDim.x) acc[i] = 0.0;
+        if (!epi) for (int i = tid; i < ncomb * nEF; i += blockDim.x) acc[i] = 0.0;
         int executed = 0;
 
-        for (int kq = 0; kq < hk.npp; kq++) {
+        for (int kq = 0; kq < (epi ? 0 : hk.npp); kq++) {
             const PrimPair pk = P.prims[hk.pp_off + kq];
             if (pk.cce > P.expcutoff) continue;
             for (int bq = 0; bq < hb.npp; bq++) {
@@ -231,7 +217,7 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
             }
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && !epi) {
             if (nonzero) nonzero[t] = executed > 0;
             if (counters) atomicAdd(counters, (unsigned long long)executed);
         }
@@ -352,7 +338,9 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
     const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
     size_t smem = fixed;
-    C->acc_in_smem = (smem + acc_b <= budget);
+    static const bool wide_on = !(getenv("CINTB200_NO_WIDE") && atoi(getenv("CINTB200_NO_WIDE")));
+    C->wide = wide_on && wide_eligible(la, lb, lc, ld, ncab, nccd, short_range);
+    C->acc_in_smem = !C->wide && (smem + acc_b <= budget);      // wide classes: the accumulators arrive in global scratch
     if (C->acc_in_smem) smem += acc_b;
     C->work_in_smem = (smem + work_b <= budget);
     if (C->work_in_smem) smem += work_b;
@@ -368,6 +356,12 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     if (per_sm > 16) per_sm = 16;
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)148 * per_sm;
+    if (C->wide) {
+        // wide classes: one block per task and launch pair (quadrature, epilogue); as many tasks per pair as 2 GB of scratch
+        // hold, so that a class is a handful of full-machine launches instead of a chain of single-wave ones
+        const long long cap = (long long)(((size_t)2 << 30) / (sizeof(double) * std::max<size_t>(1, C->scratch_per_block)));
+        grid = std::max<long long>(grid, std::min<long long>(cap, 1 << 20));
+    }
     if (grid > ntasks) grid = ntasks;
     L->grid = (int)grid;
     return 0;
@@ -384,6 +378,20 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
     if (L.smem > 48 * 1024) {
         if (cudaFuncSetAttribute(eri_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem) != cudaSuccess)
             return -1;
+    }
+    if (C.wide) {
+        // high-l classes: quadrature by the wide kernel into this launch's scratch blocks (L.grid tasks at a time), then the
+        // epilogue of this kernel on that scratch
+        GenericClass CE = C;
+        CE.epilogue_only = 1;
+        for (long long base = 0; base < ntasks; base += L.grid) {
+            const int here = (int)std::min<long long>(L.grid, ntasks - base);
+            if (wide_launch(P, C, tasks, base, ntasks, here, nonzero, stream, tile)) return -1;
+            CE.task_base = base;
+            eri_generic_kernel<<<here, L.threads, L.smem, stream>>>(P, CE, tasks, ntasks, out, nonzero, counters, TP, uprefix);
+            if (cudaGetLastError() != cudaSuccess) return -1;
+        }
+        return 0;
     }
     eri_generic_kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters, TP, uprefix);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

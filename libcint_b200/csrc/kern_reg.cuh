@@ -345,7 +345,7 @@ eri_reg_kernel(const TileParams P)
     int2 *s_tab = (int2 *)(s_st + 32 * RB);                     // [32*RB] {row offset in the tile or -1, index into s_st}
     int2 *s_meta = s_tab + 32 * RB;                             // [32] {row base or -1, +di if a is the first index else -di}
     const long long total = P.items ? P.nitems : (long long)P.gx * P.NU;
-    int cur_by = -1, t_lo = P.t_begin;
+    int cur_by = -1, t_lo = P.t_begin, t_hi_k = P.t_end;
     PairHdr hu;
     __syncthreads();                    // table staged; from here on the warps run independently (no block barriers)
     // dynamic scheduling per WARP: a warp grabs batches of P.batch consecutive work items (item = one ket x 32 bras)
@@ -387,17 +387,23 @@ eri_reg_kernel(const TileParams P)
         // reference loop bound k <= i (examples/time_c60.c:206).  tri = 0: this ket lies below the chunk's bra shells,
         // every T pair is valid (list sorted by primitive count).  tri = 1: the list is sorted by the bra's larger
         // shell index and the valid T pairs are the suffix starting at the first pair with I >= K.
-        t_lo = P.t_begin;
+        // tri = 2: one launch serves both kinds of ket -- below the chunk's bra shells (range as given, ordering A) and inside
+        // them (suffix of the same range in ordering B, tB rows further down the tables)
+        t_lo = P.t_begin; t_hi_k = P.t_end;
         if (P.tri) {
             const int K = P.uK[u];
-            int lo = P.t_begin, hi = P.t_end;
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+            if (P.tri == 1 || K >= P.tri_i0) {
+                int lo = P.t_begin + P.tB, hi = P.t_end + P.tB;
+                t_hi_k = hi;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (P.tI[mid] < K) lo = mid + 1; else hi = mid;
+                }
+                t_lo = lo;
             }
-            t_lo = lo;
         }
     }
+    if (!P.items) t_hi = t_hi_k;
     const int t0 = P.items ? t0l : t_lo + bx * 32;
     if (t0 >= t_hi) continue;           // warp-uniform
     const int t = t0 + lane;

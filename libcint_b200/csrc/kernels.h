@@ -15,6 +15,9 @@ struct GenericClass {           // uniform per launch of eri_generic_kernel
     int c2s_off[4];             // offsets of the four c2s matrices inside EngineParams::c2s
     double *scratch;            // global scratch, scratch_per_block doubles per block
     size_t scratch_per_block;
+    int wide;                   // the quadrature runs on the wide kernel (kern_wide.cu), this kernel does the epilogue only
+    int epilogue_only;          // set per launch: accumulators of task task_base + blockIdx.x are already in the block's scratch
+    long long task_base;
 };
 
 struct GenericLaunch { int grid, threads; size_t smem; };
@@ -32,6 +35,11 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
 // block stages its Rys table once and then pulls work items from the launch's counter); CINTB200_PBLOCKS=n forces n per SM.
 int tile_grid_blocks(const void *fn, int threads, size_t smem, long long total);
 int tile_smem_limit();                        // largest dynamic shared memory per block the device allows (opt-in), bytes
+
+// wide kernel (kern_wide.cu): high-l classes without a register / cooperative instantiation
+int wide_eligible(int la, int lb, int lc, int ld, int ncab, int nccd, int short_range);
+int wide_launch(const EngineParams &P, const GenericClass &C, const Task *tasks, long long task_base, long long ntasks, int ntask_here,
+                int *nonzero, cudaStream_t stream, const TileParams *tile);
 
 // register kernels (kern_reg_inst*.cu): thread per quartet, compile-time class
 typedef void (*RegKernelFn)(const TileParams);

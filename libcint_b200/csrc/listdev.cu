@@ -183,9 +183,11 @@ static int listdev_tables(CINTOpt *c)
 int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t n, const size_t *out_off, double *d_out_or_null,
                      double **d_out_used, size_t *total, int *nonzero)
 {
+    double tph = b200_now();
     if (!c->ltab && listtables_build(c)) return CINTB200_ENOMEM;
     ListTables *lt = c->ltab;
     if (listdev_tables(c)) return CINTB200_ENOMEM;
+    b200_phase("list: tables", tph); tph = b200_now();
     const int ncls = (int)lt->cls.size();
     if ((unsigned long long)ncls * ncls >= (1ull << 22) || n >= (1ull << 31)) return 0;
     cudaStream_t st = c->stream;
@@ -252,6 +254,7 @@ int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t 
     CU_OK(cudaMemcpyAsync(&tail.lastoff, d_offs + n - 1, 8, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaMemcpyAsync(&tail.lastsize, A.size + n - 1, 8, cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
+    b200_phase("list: keys + sort + flags", tph); tph = b200_now();
     if (tail.cnt[0]) return b200_fail(CINTB200_EINVAL, "%d tuples with a shell id out of range", tail.cnt[0]);
     if (tail.cnt[1]) return 0;                          // some class has no specialised kernel: host path (generic kernel for those)
     size_t tot = 0;
@@ -292,6 +295,7 @@ int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t 
     std::vector<int> h_itoff((size_t)nruns + 1);
     CU_OK(cudaMemcpyAsync(h_itoff.data(), itemoff, 4 * ((size_t)nruns + 1), cudaMemcpyDeviceToHost, st));
     CU_OK(cudaStreamSynchronize(st));
+    b200_phase("list: runs + items", tph); tph = b200_now();
     for (long long g = 0; g < ngroups; g++) {
         const int gkey = hg[g].x;
         const long long t0 = hg[g].y, u0 = hg[g].z;
@@ -329,5 +333,6 @@ int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t 
         c->launches++;
     }
     if (nonzero) CU_OK(cudaMemcpyAsync(nonzero, A.nz, 4 * n, cudaMemcpyDeviceToHost, st));
+    b200_phase("list: launches queued", tph);
     return 1;
 }

@@ -103,7 +103,10 @@ struct TileParams {
     int u_step, u_first;       // rank sharding: u = u_first + u_step * blockIdx.y
     int nca_u;
     int umax;                  // most primitive pairs of any ket of this launch (sizes the per-warp smem slice)
-    int tri;                   // 1: only quartets with K(u) <= I(t) (reference benchmark loop)
+    int tri;                   // 0: every T pair of [t_begin, t_end) meets every ket; 1: only quartets with K(u) <= I(t) (reference
+                               // benchmark loop; the range lies in the shell-sorted ordering B); 2: kets with K < tri_i0 take the range
+                               // as it is (ordering A), the others the suffix of [t_begin + tB, t_end + tB) with I >= K (ordering B)
+    int tB, tri_i0;
     // output tile
     double *out;
     long long row0;            // global row of the chunk's first row

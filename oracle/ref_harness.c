@@ -7,6 +7,8 @@
  *   - only every `stride`-th ij pair (offset `phase`) is evaluated so the run is a bounded sample;
  *   - one buffer per thread instead of malloc/free per quartet (the library call is what is timed).
  * usage: time_ref <lib.so> <basis.bin> <stride> <phase> [aux_shell0]
+ *        time_ref <lib.so> <basis.bin> ip1 <stride>        gradient loop of examples/time_c2h6.c:798-835: int2e_ip1_sph for every
+ *                 stride-th ordered pair (i,j) and all k >= l, optimizer on
  *        time_ref <lib.so> <basis.bin> sweep <list.txt>     class sweep (BASELINE config 4): every line "i j k l reps" of the list
  *                 is timed as `reps` calls of int2e_sph on that shell quartet spread over the OpenMP threads (optimizer on)
  * With aux_shell0 > 0 the density-fitting loop is timed instead: int3c2e_sph for every `stride`-th orbital shell pair
@@ -40,6 +42,42 @@ int main(int argc, char **argv)
         if (fread(bas, sizeof(int), nbas * 8, f) != (size_t)nbas * 8) return 1;
         if (fread(env, sizeof(double), nenv, f) != (size_t)nenv) return 1;
         fclose(f);
+        if (argv[3][0] == 'i') {          /* first-derivative loop */
+                intor_t ip1 = (intor_t)dlsym(h, "int2e_ip1_sph");
+                optim_t oip1 = (optim_t)dlsym(h, "int2e_ip1_optimizer");
+                if (!ip1 || !oip1) { fprintf(stderr, "no int2e_ip1_sph in %s\n", argv[1]); return 1; }
+                long strd = atol(argv[4]);
+                int md = 0;
+                for (int i = 0; i < nbas; i++) { int d = (2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3]; if (d > md) md = d; }
+                void *opt1 = NULL;
+                oip1(&opt1, atm, natm, bas, nbas, env);
+                double nints = 0, chk = 0;
+                long nq = 0;
+                double t0 = omp_get_wtime();
+#pragma omp parallel reduction(+ : nints, chk, nq)
+                {
+                        double *buf = malloc(sizeof(double) * 3 * (size_t)md * md * md * md);
+#pragma omp for schedule(dynamic, 2)
+                        for (long ij = 0; ij < (long)nbas * nbas; ij += strd) {
+                                int i = (int)(ij / nbas), j = (int)(ij - (long)nbas * i);
+                                long dij = (long)(2 * bas[i * 8 + 1] + 1) * bas[i * 8 + 3] * (2 * bas[j * 8 + 1] + 1) * bas[j * 8 + 3];
+                                for (int k = 0; k < nbas; k++)
+                                        for (int l = 0; l <= k; l++) {
+                                                int shls[4] = {i, j, k, l};
+                                                ip1(buf, NULL, shls, atm, natm, bas, nbas, env, opt1, NULL);
+                                                long n = 3 * dij * (2 * bas[k * 8 + 1] + 1) * bas[k * 8 + 3] * (2 * bas[l * 8 + 1] + 1) * bas[l * 8 + 3];
+                                                nints += n;
+                                                chk += buf[0] + buf[n - 1];
+                                                nq++;
+                                        }
+                        }
+                        free(buf);
+                }
+                double t1 = omp_get_wtime();
+                printf("{\"seconds\": %.6f, \"integrals\": %.0f, \"quartets\": %ld, \"threads\": %d, \"stride\": %ld, \"phase\": 0, \"checksum\": %.15e}\n",
+                       t1 - t0, nints, nq, omp_get_max_threads(), strd, chk);
+                return 0;
+        }
         if (argv[3][0] == 's') {          /* class sweep */
                 FILE *lf = fopen(argv[4], "r");
                 if (!lf) { fprintf(stderr, "cannot read %s\n", argv[4]); return 1; }

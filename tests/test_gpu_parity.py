@@ -457,3 +457,129 @@ def test_dropin_calls_from_concurrent_threads():
             assert rc == r0 and np.abs(buf - want).max() <= TOL * max(1.0, np.abs(want).max()), (n, sh)
     lib.CINTdel_optimizer(ctypes.byref(opt))
     assert not opt.value
+
+
+def test_large_lists_device_side_bookkeeping():
+    """Lists of >= 4096 tuples are keyed, sorted and turned into work items ON THE DEVICE (csrc/listdev.cu): random C60 quartets,
+    packed and caller-given offsets, host and device output, Cartesian output, 3- and 2-centre tuples -- sampled blocks against
+    the oracle and the nonzero flags against the reference's return value."""
+    which, _ = ou.best()
+    atm, bas, env = cb.load_fixture("c60_ccpvdz")
+    ctx = cb.Context(atm, bas, env)
+    rng = np.random.default_rng(11)
+    n = 20000
+    q = rng.integers(0, len(bas), size=(n, 4)).astype(np.int32)
+    q[:500, 2:] = q[0, 2:]                      # a long run of one ket and ...
+    q[500:900, :2] = q[1, :2]                   # ... one bra with many kets
+    v, o, s, nz = ctx.int2e_batch(q)
+    assert nz.min() >= 0 and nz.max() == 1
+    pick = np.concatenate([np.arange(0, 40), rng.choice(n, 260, replace=False)])
+    for t in pick:
+        want, ret = ou.eval_tuple(which, "int2e_sph", q[t], atm, bas, env)
+        assert np.abs(v[o[t]:o[t] + s[t]] - want).max() <= TOL * max(1.0, np.abs(want).max()), (t, q[t])
+        assert nz[t] == ret or np.abs(want).max() < 1e-30
+    # caller-given offsets (blocks in reverse order with gaps) into a device buffer
+    import torch
+    off2 = (np.cumsum((s + 3)[::-1])[::-1] - (s + 3)).astype(np.uint64)
+    dbuf = torch.full((int((off2 + s.astype(np.uint64)).max()),), -7.0, dtype=torch.float64, device="cuda")
+    ctx.int2e_batch(q, out_off=off2, device_ptr=dbuf.data_ptr())
+    h = dbuf.cpu().numpy()
+    for t in pick[:80]:
+        assert np.array_equal(h[int(off2[t]):int(off2[t]) + s[t]], v[o[t]:o[t] + s[t]]), t
+    assert h[int(off2[5]) + s[5]] == -7.0        # the gaps stay untouched
+    # Cartesian output
+    vc, oc, sc, _ = ctx.int2e_batch(q[:6000], kind=cb.CART)
+    for t in pick[pick < 6000][:60]:
+        want, _ = ou.eval_tuple(which, "int2e_cart", q[t], atm, bas, env)
+        assert np.abs(vc[oc[t]:oc[t] + sc[t]] - want).max() <= TOL * max(1.0, np.abs(want).max()), (t, q[t])
+    ctx.close()
+    # 3- and 2-centre tuples of the density-fitting stand-in
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis(max_atoms=6)
+    ctx = cb.Context(atm, bas, env)
+    q3 = np.column_stack([rng.integers(0, norb, 8000), rng.integers(0, norb, 8000), rng.integers(norb, len(bas), 8000)]).astype(np.int32)
+    v3, o3, s3, _ = ctx.int3c2e_batch(q3)
+    for t in rng.choice(8000, 150, replace=False):
+        want, _ = ou.eval_tuple(which, "int3c2e_sph", q3[t], atm, bas, env)
+        assert np.abs(v3[o3[t]:o3[t] + s3[t]] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (t, q3[t])
+    q2 = rng.integers(norb, len(bas), size=(5000, 2)).astype(np.int32)
+    v2, o2, s2, _ = ctx.int2c2e_batch(q2)
+    for t in rng.choice(5000, 150, replace=False):
+        want, _ = ou.eval_tuple(which, "int2c2e_sph", q2[t], atm, bas, env)
+        assert np.abs(v2[o2[t]:o2[t] + s2[t]] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (t, q2[t])
+
+
+def test_ip1_dense_blocks_on_tile_kernels():
+    """( nabla i j | k l ) and ( nabla i j | k ) over shell slices (cintb200_int2e_ip1_block): raised / lowered helper blocks on the
+    specialised kernels + derivative and cart->sph on the dense tensor, against the reference's int2e_ip1 / int3c2e_ip1 per tuple."""
+    which, _ = ou.best()
+    rng = np.random.default_rng(3)
+    import itertools
+    for name, sl, kinds in (("c2h6_ccpvdz", (0, 14, 3, 20, 5, 28, 0, 9), (cb.SPH, cb.CART)), ("c2h6_ccpvtz", (20, 30, 0, 12, 30, 54, 5, 15), (cb.SPH,))):
+        atm, bas, env = cb.load_fixture(name)
+        ctx = cb.Context(atm, bas, env)
+        for kind in kinds:
+            cart = kind == cb.CART
+            arr, st = ctx.ip1_block(sl, kind=kind)
+            ao = np.concatenate([[0], np.cumsum([((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+            tuples = list(itertools.product(*[range(sl[2 * m], sl[2 * m + 1]) for m in range(4)]))
+            for sh in [tuples[n] for n in rng.choice(len(tuples), 500, replace=False)]:
+                want, _ = ou.eval_tuple(which, "int2e_ip1_cart" if cart else "int2e_ip1_sph", sh, atm, bas, env)
+                idx = tuple(slice(int(ao[s] - ao[sl[2 * m]]), int(ao[s + 1] - ao[sl[2 * m]])) for m, s in enumerate(sh))
+                got = arr[idx]
+                want = want.reshape(got.shape, order="F")
+                assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (name, kind, sh, np.abs(got - want).max())
+        ctx.close()
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis(max_atoms=3)
+    ctx = cb.Context(atm, bas, env)
+    sl = (0, norb, 0, 12, norb, len(bas))
+    arr, st = ctx.ip1_block(sl)
+    ao = np.concatenate([[0], np.cumsum([(2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+    tuples = list(itertools.product(*[range(sl[2 * m], sl[2 * m + 1]) for m in range(3)]))
+    for sh in [tuples[n] for n in rng.choice(len(tuples), 400, replace=False)]:
+        want, _ = ou.eval_tuple(which, "int3c2e_ip1_sph", sh, atm, bas, env)
+        idx = tuple(slice(int(ao[s] - ao[sl[2 * m]]), int(ao[s + 1] - ao[sl[2 * m]])) for m, s in enumerate(sh))
+        got = arr[idx]
+        assert np.abs(got - want.reshape(got.shape, order="F")).max() <= 1e-11 * max(1.0, np.abs(want).max()), sh
+
+
+def test_all_symmetry_unique_classes_s_to_h_segmented():
+    """BASELINE config 4 with segmented shells (3 primitives, 1 contraction -- what real basis sets have above p): one quartet of
+    EVERY symmetry-unique angular class (li>=lj, lk>=ll, ij>=kl; 231 classes, nroots 1..11) plus the transposed orientation of a
+    sample, against the reference (1e-10: its own roots are ~1e-11 accurate for nroots >= 7) and the extended-precision port.
+    Classes without a register / cooperative instantiation run on the wide kernel (csrc/kern_wide.cu) + the catch-all epilogue."""
+    atm, bas, env = class_sweep_basis(lmax=5, nctr=1)
+    nsh = 6
+    pairs = [(a, b) for a in range(6) for b in range(a + 1)]
+    classes = [(p[0], p[1], r[0], r[1]) for n, p in enumerate(pairs) for r in pairs[:n + 1]]
+    assert len(classes) == 231
+    q = [[0 * nsh + c[0], 1 * nsh + c[1], 2 * nsh + c[2], 3 * nsh + c[3]] for c in classes]
+    q += [[2 * nsh + c[2], 3 * nsh + c[3], 0 * nsh + c[0], 1 * nsh + c[1]] for c in classes[::7]]       # (kl|ij): the other orientation
+    q += [[1 * nsh + c[1], 0 * nsh + c[0], 3 * nsh + c[3], 2 * nsh + c[2]] for c in classes[3::11]]     # (ji|lk)
+    q = np.array(q, np.int32)
+    ctx = cb.Context(atm, bas, env)
+    got = []
+    for sh in q:                                    # 40 copies per call: list mode for the specialised classes, wide / catch-all else
+        v, o, s, nz = ctx.int2e_batch(np.tile(sh, (40, 1)))
+        assert np.array_equal(v[:s[0]], v[o[39]:o[39] + s[39]])
+        got.append(v[:s[0]].copy())
+    which, _ = ou.best()
+    want = ou.eval_many(which, "int2e_sph", q, atm, bas, env)
+    assert_blocks_close(got, want, q, tol=1e-10 if which == "ref" else TOL, what="all classes s..h")
+    hi = [n for n, sh in enumerate(q) if sum(int(bas[s, 1]) for s in sh) >= 12][::3]
+    wantp = ou.eval_many("port", "int2e_sph", q[hi], atm, bas, env)
+    assert_blocks_close([got[n] for n in hi], wantp, q[hi], tol=TOL, what="high classes vs port")
+    # long-range Coulomb and Cartesian output on high classes, 3-centre (ij|k) with g / h shells
+    env2 = env.copy()
+    env2[8] = 0.4
+    ctx2 = cb.Context(atm, bas, env2)
+    sel = np.array([q[n] for n in (230, 200, 150, 120)], np.int32)
+    v, o, s, _ = ctx2.int2e_batch(sel)
+    # (hh|hh): 11 roots, 63 001 Cartesian components folded through four h transforms -- rounding reaches 1.4e-12 on values ~ 1
+    assert_blocks_close(split(v, o, s), ou.eval_many("port", "int2e_sph", sel, atm, bas, env2), sel, tol=3e-12, what="LR high classes")
+    v, o, s, _ = ctx.int2e_batch(sel[1:], kind=cb.CART)
+    assert_blocks_close(split(v, o, s), ou.eval_many(which, "int2e_cart", sel[1:], atm, bas, env), sel[1:], tol=1e-10, what="cart high classes")
+    q3 = np.array([[5, 6 + 5, 12 + 4], [4, 6 + 4, 12 + 5], [5, 6 + 3, 12 + 5], [3, 6 + 3, 12 + 4]], np.int32)
+    v, o, s, _ = ctx.int3c2e_batch(q3)
+    assert_blocks_close(split(v, o, s), ou.eval_many(which, "int3c2e_sph", q3, atm, bas, env), q3, tol=1e-10, what="3-centre high classes")

@@ -16,6 +16,14 @@ for nq in (20000, 200000, 1000000):
         ctx.int2e_batch(q, device_ptr=buf.data_ptr())
         torch.cuda.synchronize(); dt = time.time() - t0
     print("list-mode batch: %d quartets, %.3g integrals in %.1f ms -> %.3g quartets/s, %.3g integrals/s" % (nq, tot, dt * 1e3, nq / dt, tot / dt))
+    # the C entry point alone (no numpy size computation of the Python mirror): packed output, device buffer, no flags
+    import ctypes
+    f = ctx.lib.cintb200_int2e_batch
+    for it in range(3):
+        torch.cuda.synchronize(); t0 = time.time()
+        rc = f(ctx.handle, 0, q.ctypes.data_as(ctypes.c_void_p), nq, None, ctypes.c_void_p(buf.data_ptr()), 1, None)
+        torch.cuda.synchronize(); dt = time.time() - t0
+    print("   C call only: %.1f ms -> %.3g quartets/s, %.3g integrals/s (rc %d)" % (dt * 1e3, nq / dt, tot / dt, rc))
 # structured list: every bra of a set with every ket of a set (what screened direct-SCF lists look like), same API
 import ctypes
 nb = len(bas)

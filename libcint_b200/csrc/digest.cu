@@ -148,9 +148,10 @@ struct JKArgs {
 // is needed and nothing is scattered.  Tile loads are coalesced (consecutive threads = consecutive rows of one column).
 // The partial sums go to private slots PA / PB[x][row] and are folded over the rows sharing a (or b) by jk_fold_kernel.
 // The Coulomb row part J'[a,b] += 2 s (ab|cd) D[c,d] rides along in the visit from the ket's first shell.
-#define JK_RPT 2                 // tile rows per thread: twice the loads in flight, the per-entry decoding shared by both
-template <int NX>
-__global__ void __launch_bounds__(128, 4) jk_rows_kernel(const JKArgs A)
+// JK_RPT tile rows per thread: more loads in flight per thread (ncu: the kernel waits on HBM latency with 16 resident warps per SM),
+// the per-entry decoding shared by all of them
+template <int NX, int JK_RPT>
+__global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
 {
     const long long row0 = (long long)blockIdx.x * (128 * JK_RPT) + threadIdx.x;
     bool active[JK_RPT];
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(256) jk_cols_kernel(const double *__restrict__
         const double *t = tile + ld * col;
         double p0 = 0.0, p1 = 0.0;
         long long r = lane;
-        for (; r + 32 < ld; r += 64) {
+        for (; r + 32 < ld; r += 64) {              // two independent chains (four were measured slower: 144 vs 107 ms per pass)
             const int ij0 = rowinfo[row0 + r].z, ij1 = rowinfo[row0 + r + 32].z;
             const double v0 = ci.x <= ij0 ? t[r] : 0.0, v1 = ci.x <= ij1 ? t[r + 32] : 0.0;
             p0 = fma(ci.x == ij0 ? 0.5 * v0 : v0, Dab[row0 + r], p0);
@@ -412,8 +413,9 @@ int digest_begin(CINTOpt *c, JobPlan *plan, const DigestJob &job, const double *
     return 0;
 }
 
+constexpr int jk_rpt(int nx) { return 2; }          // measured: 4 rows per thread for nx <= 3 is not faster (129 vs 124 ms for nx = 3)
 template <int NX>
-static void launch_rows(const JKArgs &A, dim3 grid, cudaStream_t st) { jk_rows_kernel<NX><<<grid, 128, 0, st>>>(A); }
+static void launch_rows(const JKArgs &A, dim3 grid, cudaStream_t st) { jk_rows_kernel<NX, jk_rpt(NX)><<<grid, 128, 0, st>>>(A); }
 
 int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, const double *tile, cudaStream_t st)
 {
@@ -438,10 +440,10 @@ int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, cons
         JKArgs A;
         A.tile = tile; A.ld = ld; A.row0 = row0; A.nao = d->nao; A.rowinfo = d->d_rowinfo; A.units = d->d_units; A.entries = d->d_entries;
         A.dm = d->d_dm; A.Dcd = d->d_Dcd; A.PA = d->d_PA; A.PB = d->d_PB; A.jrow = d->d_jrow; A.ldP = d->ldmax; A.want_k = job.want_k;
-        const unsigned gx = (unsigned)((ld + 128 * JK_RPT - 1) / (128 * JK_RPT));
         for (int nx = 1; nx <= JK_NXMAX; nx++) {
             A.ubeg = d->unit_beg[nx]; A.uend = d->unit_beg[nx + 1];
             if (A.uend <= A.ubeg) continue;
+            const unsigned gx = (unsigned)((ld + 128 * jk_rpt(nx) - 1) / (128 * jk_rpt(nx)));
             const unsigned gy = (unsigned)std::max(1, std::min(A.uend - A.ubeg, (sms * 12 + (int)gx - 1) / (int)gx));
             const dim3 grid(gx, gy);
             switch (nx) {

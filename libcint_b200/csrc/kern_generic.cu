@@ -22,6 +22,9 @@
 
 __constant__ int c_cart_off[2 * B200_LMAX + 2];                 // first component of degree l
 __constant__ unsigned char c_cart_xyz[3 * 560];                 // (lx,ly,lz) of every component, l = 0..2*LMAX
+// the same table in global memory for the lookups whose index differs from thread to thread (a divergent constant-memory
+// read is serialised lane by lane; through L1 it is one transaction per distinct line)
+__device__ unsigned char d_cart_xyz[3 * 560];
 
 __device__ __forceinline__ int cart_index(int lx, int lz, int l)
 {
@@ -51,8 +54,8 @@ __device__ void hrr_level(const double *in, double *out, int pre, int post, int 
             le++;
         }
         int ie = part / nb_out, ib = part - ie * nb_out;
-        const unsigned char *bc = c_cart_xyz + 3 * (c_cart_off[jb] + ib);
-        const unsigned char *ac = c_cart_xyz + 3 * (c_cart_off[le] + ie);
+        const unsigned char *bc = d_cart_xyz + 3 * (jb * (jb + 1) * (jb + 2) / 6 + ib);        // first component of degree l: l(l+1)(l+2)/6
+        const unsigned char *ac = d_cart_xyz + 3 * (le * (le + 1) * (le + 2) / 6 + ie);
         int bx = bc[0], by = bc[1], bz = bc[2];
         int ax = ac[0], az = ac[2];
         int d = bx ? 0 : (by ? 1 : 2);
@@ -312,6 +315,7 @@ int generic_setup_constants()
     if (n > 560) return -1;
     if (cudaMemcpyToSymbol(c_cart_off, off, sizeof off) != cudaSuccess) return -1;
     if (cudaMemcpyToSymbol(c_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
     return 0;
 }
 

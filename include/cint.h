@@ -75,6 +75,8 @@ CINTOptimizerFunction int2e_optimizer;      /* src/cint2e.c:1195 */
 CINTIntegralFunction  int3c2e_sph;          /* src/cint3c2e.c:693 */
 CINTIntegralFunction  int3c2e_cart;         /* src/cint3c2e.c:710 */
 CINTOptimizerFunction int3c2e_optimizer;    /* src/cint3c2e.c:702 */
+CINTIntegralFunction  int3c2e_sph_ssc;      /* src/cint3c2e.c:729: spherical i, j, Cartesian auxiliary index (c2s_sph_3c2e1_ssc, src/cart2sph.c:5956) */
+CINTOptimizerFunction int3c2e_ssc_optimizer; /* src/cint3c2e.c:759 */
 
 /* ---- 2-centre ERIs (density-fitting metric): src/cint2c2e.c:351-375 ---- */
 CINTIntegralFunction  int2c2e_sph;          /* src/cint2c2e.c:351 */

@@ -476,6 +476,19 @@ def int3c2e_cart(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int3c2e_cart", 3, shls, atm, bas, env, opt, dims, out, cart=True)
 
 
+def int3c2e_sph_ssc(shls, atm, bas, env, opt=None):
+    """Spherical i, j with a Cartesian auxiliary index (src/cint3c2e.c:729)."""
+    lib = load_library()
+    atm, bas, env = _as_basis(atm, bas, env)
+    d = shell_dims(bas, shls[:2]) + shell_dims(bas, shls[2:], cart=True)
+    out = np.zeros(tuple(d), order="F")
+    cshls = (ctypes.c_int * 3)(*[int(s) for s in shls])
+    lib.int3c2e_sph_ssc.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 3
+    lib.int3c2e_sph_ssc.restype = ctypes.c_int
+    rc = lib.int3c2e_sph_ssc(_p(out), None, cshls, _p(atm), len(atm), _p(bas), len(bas), _p(env), opt.handle if isinstance(opt, Context) else opt, None)
+    return out, rc
+
+
 def int2c2e_sph(shls, atm, bas, env, opt=None, dims=None, out=None):
     return _call_single("int2c2e_sph", 2, shls, atm, bas, env, opt, dims, out)
 

@@ -934,8 +934,9 @@ static CACHE_SIZE_T drop_in_failed(double *out, const FINT *dims, const FINT *sh
     return 0;
 }
 
+// cart_pos >= 0: that index of a spherical call stays Cartesian (int3c2e_sph_ssc: the auxiliary index, src/cint3c2e.c:729)
 static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm,
-                            FINT *bas, FINT nbas, double *env, CINTOpt *opt)
+                            FINT *bas, FINT nbas, double *env, CINTOpt *opt, int cart_pos = -1)
 {
     if (out == NULL) {
         // reference: required scratch length in doubles (src/cint2e.c:801-816).  The GPU path needs no
@@ -952,15 +953,15 @@ static CACHE_SIZE_T drop_in(int ncenter, int kind, double *out, FINT *dims, FINT
     CINTOpt *c = ref.c;
     if (!c) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 1);
     size_t d[4] = {1, 1, 1, 1};
-    for (int m = 0; m < ncenter; m++) d[m] = shell_dim(c->shells[shls[m]], cart);
+    for (int m = 0; m < ncenter; m++) d[m] = shell_dim(c->shells[shls[m]], cart || m == cart_pos);
     const size_t len = d[0] * d[1] * d[2] * d[3];
     int nz = 0;
     if (!dims) {
-        long rc = run_batch(c, ncenter, kind, shls, 1, NULL, out, 0, &nz);
+        long rc = run_batch(c, ncenter, kind, shls, 1, NULL, out, 0, &nz, cart_pos);
         return rc < 0 ? drop_in_failed(out, dims, shls, bas, ncenter, cart, 1) : nz;
     }
     std::vector<double> tmp(len);
-    long rc = run_batch(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz);
+    long rc = run_batch(c, ncenter, kind, shls, 1, NULL, tmp.data(), 0, &nz, cart_pos);
     if (rc < 0) return drop_in_failed(out, dims, shls, bas, ncenter, cart, 1);
     // embed into the caller's larger tensor: leading dimensions dims[] (src/cint2e.c:853-856)
     const size_t ni = dims[0], nj = dims[1], nk = (ncenter > 2) ? dims[2] : 1;
@@ -1056,6 +1057,10 @@ CACHE_SIZE_T int3c2e_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT na
 { (void)cache; return drop_in(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }
 CACHE_SIZE_T int3c2e_cart(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
 { (void)cache; return drop_in(3, CINTB200_CART, out, dims, shls, atm, natm, bas, nbas, env, opt); }
+// spherical i, j with a Cartesian auxiliary index k (c2s_sph_3c2e1_ssc, src/cart2sph.c:5956; entry point src/cint3c2e.c:729)
+CACHE_SIZE_T int3c2e_sph_ssc(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
+{ (void)cache; return drop_in(3, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt, 2); }
+void int3c2e_ssc_optimizer(CINTOpt **opt, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env) { int3c2e_optimizer(opt, atm, natm, bas, nbas, env); }
 
 CACHE_SIZE_T int2c2e_sph(double *out, FINT *dims, FINT *shls, FINT *atm, FINT natm, FINT *bas, FINT nbas, double *env, CINTOpt *opt, double *cache)
 { (void)cache; return drop_in(2, CINTB200_SPH, out, dims, shls, atm, natm, bas, nbas, env, opt); }

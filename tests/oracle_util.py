@@ -62,6 +62,8 @@ def eval_tuple(which, name, shls, atm, bas, env, dims=None):
     bas = np.ascontiguousarray(bas, np.int32)
     env = np.ascontiguousarray(env, np.float64)
     d = dims_of(bas, shls, name.endswith("cart"))
+    if name.endswith("_ssc"):               # spherical i, j; Cartesian last (auxiliary) index
+        d = d[:-1] + dims_of(bas, shls[-1:], True)
     n = int(np.prod(dims if dims is not None else d)) * (3 if ("_ip1_" in name or "_ip2_" in name) else 1)
     buf = np.zeros(n)
     cs = (ctypes.c_int * len(shls))(*[int(s) for s in shls])

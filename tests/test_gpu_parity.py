@@ -583,3 +583,19 @@ def test_all_symmetry_unique_classes_s_to_h_segmented():
     q3 = np.array([[5, 6 + 5, 12 + 4], [4, 6 + 4, 12 + 5], [5, 6 + 3, 12 + 5], [3, 6 + 3, 12 + 4]], np.int32)
     v, o, s, _ = ctx.int3c2e_batch(q3)
     assert_blocks_close(split(v, o, s), ou.eval_many(which, "int3c2e_sph", q3, atm, bas, env), q3, tol=1e-10, what="3-centre high classes")
+
+
+def test_int3c2e_sph_ssc_dropin():
+    """int3c2e_sph_ssc (src/cint3c2e.c:729): spherical orbital indices, Cartesian auxiliary index -- against the compiled reference."""
+    if ou.ref() is None:
+        pytest.skip("needs oracle/_ref (the port has no _ssc entry point)")
+    from libcint_b200.basis import c60_df_basis
+    atm, bas, env, norb = c60_df_basis(max_atoms=2)
+    ctx = cb.Context(atm, bas, env)
+    rng = np.random.default_rng(4)
+    for _ in range(60):
+        sh = (int(rng.integers(0, norb)), int(rng.integers(0, norb)), int(rng.integers(norb, len(bas))))
+        got, rc = cb.int3c2e_sph_ssc(sh, atm, bas, env, opt=ctx)
+        want, ret = ou.eval_tuple("ref", "int3c2e_sph_ssc", sh, atm, bas, env)
+        assert rc == ret
+        assert np.abs(got.ravel(order="F") - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), sh

@@ -502,11 +502,13 @@ def main():
             pass
         hbm = peaks.get("hbm_gbs", 6650.0)
         traffic, traffic_note = None, None
-        try:        # DRAM bytes of one captured launch of the dominant kernel (tools/ncu_summarize.py -> profiles/)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        try:        # DRAM bytes of one captured launch of the dominant kernel (tools/ncu_summarize_r2.py -> profiles/r2_traffic.json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tj["kernel"].replace(" ", "") == "eri_reg_kernel<%d,%d,%d,%d,%d,%d>" % tuple(int(v) for v in top[:6]) and int(top[6]) == 1:
                 traffic = tj["traffic_bytes"]
-                traffic_note = {k: tj.get(k) for k in ("capture", "dram_read_bytes", "dram_write_bytes", "algorithmic_store_bytes", "duration_us")}
+                blk = np.prod([(2 * int(l) + 1) for l in top[:4]]) * int(top[4]) * int(top[5])
+                traffic_note = {k: tj.get(k) for k in ("capture", "dram_read_bytes", "dram_write_bytes", "duration_us")}
+                traffic_note["algorithmic_store_bytes_of_an_average_launch"] = float(top[8]) * float(blk) * 8 / max(1, int(top[11]))
         except Exception:
             pass
         roofline = {

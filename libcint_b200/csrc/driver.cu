@@ -935,8 +935,8 @@ extern "C" int cintb200_job_col_map(cintb200_ctx *c, int chunk, int *sh_k, int *
 void listtables_free(ListTables *lt)
 {
     if (!lt) return;
-    for (ListClass &lc : lt->cls) { cudaFree(lc.d_tprim); cudaFree(lc.d_tgeom); cudaFree(lc.d_tnpp); }
-    cudaFree(lt->d_buf); cudaFree(lt->d_cls_of); cudaFree(lt->d_row_of); cudaFree(lt->d_sdim); cudaFree(lt->d_per); cudaFree(lt->d_work);
+    for (ListClass &lc : lt->cls) { b200_big_free(lc.d_tprim); b200_big_free(lc.d_tgeom); b200_big_free(lc.d_tnpp); }
+    cudaFree(lt->d_buf); cudaFree(lt->d_cls_of); cudaFree(lt->d_row_of); cudaFree(lt->d_sdim); cudaFree(lt->d_per); b200_big_free(lt->d_work);
     delete lt;
 }
 
@@ -998,7 +998,15 @@ int listclass_upload(CINTOpt *c, ListClass &lc)
             fill_tprim(c, h, n, NT, Q, nct, tprim, tgeom);
             nppc[n] = std::max(h.npp, 1);
         }
-        if (upload(&lc.d_tprim, tprim) || upload(&lc.d_tgeom, tgeom) || upload(&lc.d_tnpp, nppc)) return CINTB200_ENOMEM;
+        // pooled allocations (engine.cu:b200_big_alloc): a context per geometry step must not pay ~100 cudaMalloc / cudaFree pairs
+        void *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        if (b200_big_alloc(&p0, sizeof(double) * std::max<size_t>(1, tprim.size())) || b200_big_alloc(&p1, sizeof(double) * std::max<size_t>(1, tgeom.size())) ||
+            b200_big_alloc(&p2, sizeof(int) * std::max<size_t>(1, nppc.size()))) return b200_fail(CINTB200_ENOMEM, "list-mode class tables");
+        lc.d_tprim = (double *)p0; lc.d_tgeom = (double *)p1; lc.d_tnpp = (int *)p2;
+        if (cudaMemcpy(lc.d_tprim, tprim.data(), sizeof(double) * tprim.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(lc.d_tgeom, tgeom.data(), sizeof(double) * tgeom.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(lc.d_tnpp, nppc.data(), sizeof(int) * nppc.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+            return b200_fail(CINTB200_ENODEV, "list-mode class tables: upload failed");
     }
     return 0;
 }

@@ -230,12 +230,44 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
         const int cm = P.cart ? 15 : (task.flags & 15);          // indices that stay Cartesian (block-uniform)
         const int da = (cm & 1) ? nfa : 2 * la + 1, db = (cm & 2) ? nfb : 2 * lb + 1;
         const int dc = (cm & 4) ? nfc : 2 * lc + 1, dd = (cm & 8) ? nfd : 2 * ld + 1;
+        const bool use_table = C.epi.rowptr != nullptr && cm == C.epi_cm;
         for (int comb = 0; comb < ncomb; comb++) {
             const int cab = comb % C.ncab, ccd = comb / C.ncab;
             const int ca = cab % hb.nca, cb = cab / hb.nca;
             const int cc = ccd % hk.nca, cd = ccd / hk.nca;
             const double *cur = acc + (size_t)comb * nEF;
             double *nxt = w0;
+            if (use_table) {
+                // table-driven epilogue: the stages are sparse maps precomputed per class (kernels.h:EpiTable)
+                for (int sidx = 0; sidx < C.epi.nstages; sidx++) {
+                    const EpiStage S = C.epi.st[sidx];
+                    const double *ab = S.which == 1 ? hb.ab : hk.ab;
+                    const int *rp = C.epi.rowptr + S.row0;
+                    for (int idx = tid; idx < S.nout; idx += blockDim.x) {
+                        double v = 0;
+                        for (int e = rp[idx]; e < rp[idx + 1]; e++) {
+                            const int2 en = C.epi.ent[e];
+                            const double f = en.y ? C.epi.coef[e] * ab[en.y - 1] : C.epi.coef[e];
+                            v = fma(f, cur[en.x], v);
+                        }
+                        nxt[idx] = v;
+                    }
+                    __syncthreads();
+                    cur = nxt;
+                    nxt = (nxt == w0) ? w1 : w0;
+                }
+                const int n_out = C.epi.n_out;
+                double *dst = out + task.off + (long long)ca * da * task.sa + (long long)cb * db * task.sb
+                            + (long long)cc * dc * task.sc + (long long)cd * dd * task.sd;
+                const uchar4 *sidx4 = C.epi.store_idx + (task.sa <= task.sb ? 0 : n_out);
+                for (int idx = tid; idx < n_out; idx += blockDim.x) {
+                    const uchar4 m = sidx4[idx];
+                    dst[(long long)m.x * task.sa + (long long)m.y * task.sb + m.z * task.sc + m.w * task.sd]
+                        = cur[((m.x * db + m.y) * dc + m.z) * dd + m.w];
+                }
+                __syncthreads();
+                continue;
+            }
             for (int jb = 1; jb <= lb; jb++) {
                 hrr_level(cur, nxt, 1, nF, la, la + lb - jb + 1, jb, hb.ab);
                 __syncthreads();
@@ -297,6 +329,125 @@ static size_t epilogue_work_size(int la, int lb, int lc, int ld, int cart)
     return mx;
 }
 
+// ---------------------------------------------------------------- table-driven epilogue (host side)
+// Built once per (class, Cartesian mask 0 / 15) and device, cached for the life of the process: the exact index arithmetic of
+// hrr_level / c2s_index / the store loop above, evaluated on the host.
+#include <map>
+#include <mutex>
+#include <vector>
+#include <array>
+static void host_cart_xyz(int l, int idx, int *lx, int *ly, int *lz)
+{
+    int n = 0;
+    for (int x = l; x >= 0; x--)
+        for (int y = l - x; y >= 0; y--, n++)
+            if (n == idx) { *lx = x; *ly = y; *lz = l - x - y; return; }
+    *lx = *ly = *lz = 0;
+}
+static int host_cart_index(int lx, int lz, int l) { const int r = l - lx; return r * (r + 1) / 2 + lz; }
+
+struct EpiHost { std::vector<int> rowptr; std::vector<int2> ent; std::vector<double> coef; std::vector<EpiStage> st; };
+
+static void epi_add_hrr(EpiHost &H, int which, int pre, int post, int l0, int ltop, int jb)
+{
+    const int nb_in = B200_NCART(jb - 1), nb_out = B200_NCART(jb);
+    int in_part = 0, out_part = 0;
+    for (int le = l0; le <= ltop; le++) in_part += B200_NCART(le) * nb_in;
+    for (int le = l0; le < ltop; le++) out_part += B200_NCART(le) * nb_out;
+    const int total = pre * out_part * post;
+    H.st.push_back(EpiStage{total, which, (int)H.rowptr.size()});
+    for (int idx = 0; idx < total; idx++) {
+        const int q = idx % post;
+        int part = (idx / post) % out_part;
+        const int p = idx / (post * out_part);
+        int le = l0, in_off = 0;
+        while (part >= B200_NCART(le) * nb_out) { part -= B200_NCART(le) * nb_out; in_off += B200_NCART(le) * nb_in; le++; }
+        const int ie = part / nb_out, ib = part - ie * nb_out;
+        int bx, by, bz, ax, ay, az;
+        host_cart_xyz(jb, ib, &bx, &by, &bz);
+        host_cart_xyz(le, ie, &ax, &ay, &az);
+        const int d = bx ? 0 : (by ? 1 : 2);
+        bx -= (d == 0); bz -= (d == 2);
+        const int ibp = host_cart_index(bx, bz, jb - 1), iep = host_cart_index(ax + (d == 0), az + (d == 2), le + 1);
+        const int base = p * in_part * post;
+        H.rowptr.push_back((int)H.ent.size());
+        H.ent.push_back(make_int2(base + (in_off + B200_NCART(le) * nb_in + iep * nb_in + ibp) * post + q, 0)); H.coef.push_back(1.0);
+        H.ent.push_back(make_int2(base + (in_off + ie * nb_in + ibp) * post + q, d + 1)); H.coef.push_back(1.0);
+    }
+    H.rowptr.push_back((int)H.ent.size());
+}
+
+static void epi_add_c2s(EpiHost &H, int pre, int post, int l, const double *cmat)
+{
+    const int nin = B200_NCART(l), nout = 2 * l + 1, total = pre * nout * post;
+    H.st.push_back(EpiStage{total, 1, (int)H.rowptr.size()});
+    for (int idx = 0; idx < total; idx++) {
+        const int q = idx % post, m = (idx / post) % nout, p = idx / (post * nout);
+        H.rowptr.push_back((int)H.ent.size());
+        for (int c = 0; c < nin; c++)
+            if (cmat[m * nin + c] != 0.0) { H.ent.push_back(make_int2(p * nin * post + q + c * post, 0)); H.coef.push_back(cmat[m * nin + c]); }
+    }
+    H.rowptr.push_back((int)H.ent.size());
+}
+
+// c2s_host: the dense cart->sph matrices (host copy of what EngineParams::c2s holds), offsets c2s_off_table[l]
+int epilogue_table(EpiTable *T, int la, int lb, int lc, int ld, int cart, const double *c2s_host, const int *c2s_off_table)
+{
+    struct Dev { EpiTable t; };
+    static std::mutex mtx;
+    static std::map<std::array<int, 6>, Dev> cache;
+    std::lock_guard<std::mutex> lock(mtx);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const std::array<int, 6> key = {dev, la, lb, lc, ld, cart};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *T = it->second.t; return T->rowptr ? 0 : -1; }
+    Dev D;
+    memset(&D.t, 0, sizeof D.t);
+    EpiHost H;
+    const int nF = sum_ncart(lc, lc + ld);
+    const int nfa = B200_NCART(la), nfb = B200_NCART(lb), nfc = B200_NCART(lc), nfd = B200_NCART(ld);
+    const int da = (cart || la < 2) ? nfa : 2 * la + 1, db = (cart || lb < 2) ? nfb : 2 * lb + 1;
+    const int dc = (cart || lc < 2) ? nfc : 2 * lc + 1, dd = (cart || ld < 2) ? nfd : 2 * ld + 1;
+    for (int jb = 1; jb <= lb; jb++) epi_add_hrr(H, 1, 1, nF, la, la + lb - jb + 1, jb);
+    for (int jd = 1; jd <= ld; jd++) epi_add_hrr(H, 2, nfa * nfb, 1, lc, lc + ld - jd + 1, jd);
+    if (!cart) {
+        if (la > 1) epi_add_c2s(H, 1, nfb * nfc * nfd, la, c2s_host + c2s_off_table[la]);
+        if (lb > 1) epi_add_c2s(H, da, nfc * nfd, lb, c2s_host + c2s_off_table[lb]);
+        if (lc > 1) epi_add_c2s(H, da * db, nfd, lc, c2s_host + c2s_off_table[lc]);
+        if (ld > 1) epi_add_c2s(H, da * db * dc, 1, ld, c2s_host + c2s_off_table[ld]);
+    }
+    const int n_out = da * db * dc * dd;
+    bool ok = H.st.size() <= 12 && H.ent.size() <= ((size_t)3 << 20) && da < 256 && db < 256 && dc < 256 && dd < 256;
+    if (ok) {
+        std::vector<uchar4> sidx(2 * (size_t)n_out);
+        for (int fast = 0; fast < 2; fast++)
+            for (int idx = 0; idx < n_out; idx++) {
+                int ma, mb, r;
+                if (fast == 0) { ma = idx % da; r = idx / da; mb = r % db; r /= db; }
+                else           { mb = idx % db; r = idx / db; ma = r % da; r /= da; }
+                sidx[(size_t)fast * n_out + idx] = make_uchar4((unsigned char)ma, (unsigned char)mb, (unsigned char)(r % dc), (unsigned char)(r / dc));
+            }
+        int *d_rp = nullptr; int2 *d_en = nullptr; double *d_cf = nullptr; uchar4 *d_si = nullptr;
+        ok = cudaMalloc((void **)&d_rp, sizeof(int) * std::max<size_t>(1, H.rowptr.size())) == cudaSuccess &&
+             cudaMalloc((void **)&d_en, sizeof(int2) * std::max<size_t>(1, H.ent.size())) == cudaSuccess &&
+             cudaMalloc((void **)&d_cf, sizeof(double) * std::max<size_t>(1, H.coef.size())) == cudaSuccess &&
+             cudaMalloc((void **)&d_si, sizeof(uchar4) * sidx.size()) == cudaSuccess &&
+             cudaMemcpy(d_rp, H.rowptr.data(), sizeof(int) * H.rowptr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_en, H.ent.data(), sizeof(int2) * H.ent.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_cf, H.coef.data(), sizeof(double) * H.coef.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+             cudaMemcpy(d_si, sidx.data(), sizeof(uchar4) * sidx.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+        if (ok) {
+            D.t.nstages = (int)H.st.size(); D.t.n_out = n_out;
+            for (size_t k = 0; k < H.st.size(); k++) D.t.st[k] = H.st[k];
+            D.t.rowptr = d_rp; D.t.ent = d_en; D.t.coef = d_cf; D.t.store_idx = d_si;
+        } else { cudaFree(d_rp); cudaFree(d_en); cudaFree(d_cf); cudaFree(d_si); cudaGetLastError(); }
+    }
+    cache[key] = D;
+    *T = D.t;
+    return T->rowptr ? 0 : -1;
+}
+
 int generic_setup_constants()
 {
     int off[2 * B200_LMAX + 2];
@@ -318,6 +469,9 @@ int generic_setup_constants()
     if (cudaMemcpyToSymbol(d_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
     return 0;
 }
+
+extern const double *engine_c2s_coef();
+int epilogue_table(EpiTable *T, int la, int lb, int lc, int ld, int cart, const double *c2s_host, const int *c2s_off_table);
 
 // Plan a launch for one class; returns 0 on success.  scratch is (re)allocated by the caller.
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
@@ -342,6 +496,13 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
     const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
     size_t smem = fixed;
+    // table-driven epilogue (pure spherical / pure Cartesian output; needs a device: host-only planning skips it)
+    static const bool epi_on = !(getenv("CINTB200_NO_EPITAB") && atoi(getenv("CINTB200_NO_EPITAB")));
+    int dev_probe = 0;
+    C->epi_cm = cart ? 15 : 0;
+    if (epi_on && (la + lb + lc + ld) > 0 && cudaGetDevice(&dev_probe) == cudaSuccess)
+        epilogue_table(&C->epi, la, lb, lc, ld, cart, engine_c2s_coef(), c2s_off_table);
+    else cudaGetLastError();
     static const bool wide_on = !(getenv("CINTB200_NO_WIDE") && atoi(getenv("CINTB200_NO_WIDE")));
     C->wide = wide_on && wide_eligible(la, lb, lc, ld, ncab, nccd, short_range);
     C->acc_in_smem = !C->wide && (smem + acc_b <= budget);      // wide classes: the accumulators arrive in global scratch

@@ -214,8 +214,8 @@ int list_mode_device(CINTOpt *c, int ncenter, int cart, const int *shls, size_t 
     const size_t o_items = take(sizeof(int4) * 2 * n);
     if (lt->cap_work < off) {
         cudaStreamSynchronize(st);
-        cudaFree(lt->d_work); lt->d_work = nullptr; lt->cap_work = 0;
-        if (cudaMalloc(&lt->d_work, off + off / 4) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "list mode: %zu bytes of device work area", off);
+        b200_big_free(lt->d_work); lt->d_work = nullptr; lt->cap_work = 0;
+        if (b200_big_alloc(&lt->d_work, off + off / 4)) return b200_fail(CINTB200_ENOMEM, "list mode: %zu bytes of device work area", off);
         lt->cap_work = off + off / 4;
     }
     char *w = (char *)lt->d_work;

@@ -496,8 +496,11 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
     const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
     size_t smem = fixed;
-    // table-driven epilogue (pure spherical / pure Cartesian output; needs a device: host-only planning skips it)
-    static const bool epi_on = !(getenv("CINTB200_NO_EPITAB") && atoi(getenv("CINTB200_NO_EPITAB")));
+    // table-driven epilogue (pure spherical / pure Cartesian output; needs a device: host-only planning skips it).  OFF by default:
+    // measured slower than the run-time index decoding (C2H6 cc-pVQZ pass 143 -> 168 ms, (ff|ff) 2.2 -> 3.1 us per quartet) --
+    // every block streams the class' whole table (~20 B per entry, up to 1 MB per quartet) from L2, which costs more than the
+    // ~150 instructions per element it saves.  CINTB200_EPITAB=1 enables it (kept for the parity test of the maps).
+    static const bool epi_on = getenv("CINTB200_EPITAB") && atoi(getenv("CINTB200_EPITAB"));
     int dev_probe = 0;
     C->epi_cm = cart ? 15 : 0;
     if (epi_on && (la + lb + lc + ld) > 0 && cudaGetDevice(&dev_probe) == cudaSuccess)

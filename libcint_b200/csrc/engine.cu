@@ -1105,7 +1105,6 @@ void CINTdel_optimizer(CINTOpt **opt) { CINTdel_2e_optimizer(opt); }
 }
 
 const int *engine_c2s_off() { return C2S_OFF; }
-const double *engine_c2s_coef() { return C2S_COEF; }
 extern "C" void cintb200_debug_force_generic(cintb200_ctx *c, int on) { if (c && c->magic == B200_CTX_MAGIC) c->force_generic = on; }
 
 int rys_tab_nint(int nroots) { return (nroots >= 1 && nroots <= RYS_NMAX) ? RYS_TAB_NINT[nroots] : 0; }

@@ -32,7 +32,21 @@
 #ifndef COOP_MB32
 #define COOP_MB32 3
 #endif
-__host__ __device__ constexpr int coop_min_blocks(int nacc) { return (nacc <= 16 ? COOP_MB16 : nacc <= 32 ? COOP_MB32 : 2) * 128 / COOP_THREADS > 0 ? (nacc <= 16 ? COOP_MB16 : nacc <= 32 ? COOP_MB32 : 2) * 128 / COOP_THREADS : 1; }
+#ifndef COOP_MBX
+#define COOP_MBX 2
+#endif
+__host__ __device__ constexpr int coop_min_blocks_default(int nacc)
+{
+    const int mb = (nacc <= 16 ? COOP_MB16 : nacc <= 32 ? COOP_MB32 : COOP_MBX) * 128 / COOP_THREADS;
+    return mb > 0 ? mb : 1;
+}
+// per-class override (tune.inc), keyed by the kernel's own template arguments (register side first)
+__host__ __device__ constexpr int coop_min_blocks(int la, int lb, int lc, int ld, int ncr, int ncl)
+{
+    int nr = 0;
+    for (int l = la; l <= la + lb; l++) nr += (l + 1) * (l + 2) / 2;
+    return tune_lookup(g_coop_tune, sizeof(g_coop_tune) / sizeof(ClassTune), tune_key(la, lb, lc, ld, ncr, ncl), false, coop_min_blocks_default(ncr * ncl * nr));
+}
 
 __host__ __device__ constexpr int coop_g_task(int nmax, int mmax) { return ((nmax + 1) * (mmax + 1)) | 1; }
 __host__ __device__ constexpr int coop_g_size(int n, int nmax, int mmax) { return 3 * n * coop_g_task(nmax, mmax); }
@@ -43,7 +57,7 @@ __host__ __device__ constexpr int coop_xsz(int n, int nmax, int mmax, int nf, in
 }
 
 template <int LA, int LB, int LC, int LD, int NCR, int NCL, int FS, bool REG_IS_T, bool RS = false, bool CART = false>
-__global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(NCR * NCL * cx_nrange(LA, LA + LB))) eri_coop_kernel(const TileParams P)
+__global__ void __launch_bounds__(COOP_THREADS, coop_min_blocks(LA, LB, LC, LD, NCR, NCL)) eri_coop_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
     constexpr int N = (LA + LB + LC + LD) / 2 + 1;

@@ -32,22 +32,31 @@ __device__ __forceinline__ int cart_index(int lx, int lz, int l)
     return r * (r + 1) / 2 + lz;
 }
 
+// Division of a small non-negative int by a block-uniform run-time divisor without the ~20-instruction software divide:
+// q = (n * m) >> 32 with m = floor(2^32 / d) + 1, exact for n, d < 2^16 (every index of the epilogue is far below that...
+// the products n * d stay < 2^32, which is the condition).
+struct FastDiv {
+    unsigned long long m;
+    int d;
+    __device__ __forceinline__ explicit FastDiv(int d_) : m((0x100000000ull / (unsigned)d_) + 1), d(d_) {}
+    __device__ __forceinline__ int div(int n) const { return (int)(((unsigned long long)(unsigned)n * m) >> 32); }
+};
+
 // One HRR level on a [pre][part][post] array.  Input level holds, for every le in [l0, ltop],
 // ncart(le) x ncart(jb-1) entries; output level holds le in [l0, ltop-1] with ncart(jb).
 //   (a, b + 1_d | = (a + 1_d, b | + AB_d (a, b |
+// The map part -> (two source offsets inside the input slice, axis) is the same for every (pre, post) element: it is decoded
+// once per level into shared memory (s_map, out_part ints), so an element costs two multiply-shift divisions, one map load,
+// two loads, one FMA and one store instead of ~150 instructions of component decoding.
 __device__ void hrr_level(const double *in, double *out, int pre, int post, int l0, int ltop, int jb,
-                          const double *ab)
+                          const double *ab, int *s_map)
 {
     const int nb_in = B200_NCART(jb - 1), nb_out = B200_NCART(jb);
     int in_part = 0, out_part = 0;
     for (int le = l0; le <= ltop; le++) in_part += B200_NCART(le) * nb_in;
     for (int le = l0; le < ltop; le++) out_part += B200_NCART(le) * nb_out;
-    const int total = pre * out_part * post;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int q = idx % post;
-        int part = (idx / post) % out_part;
-        int p = idx / (post * out_part);
-        int le = l0, in_off = 0;
+    for (int part0 = threadIdx.x; part0 < out_part; part0 += blockDim.x) {
+        int part = part0, le = l0, in_off = 0;
         while (part >= B200_NCART(le) * nb_out) {
             part -= B200_NCART(le) * nb_out;
             in_off += B200_NCART(le) * nb_in;
@@ -62,26 +71,40 @@ __device__ void hrr_level(const double *in, double *out, int pre, int post, int 
         bx -= (d == 0); bz -= (d == 2);
         int ibp = cart_index(bx, bz, jb - 1);
         int iep = cart_index(ax + (d == 0), az + (d == 2), le + 1);
-        const double *base = in + (size_t)p * in_part * post;
-        double lo = base[(size_t)(in_off + ie * nb_in + ibp) * post + q];
-        double hi = base[(size_t)(in_off + B200_NCART(le) * nb_in + iep * nb_in + ibp) * post + q];
-        out[idx] = hi + ab[d] * lo;
+        const int lo = in_off + ie * nb_in + ibp, hi = in_off + B200_NCART(le) * nb_in + iep * nb_in + ibp;
+        s_map[part0] = lo | (hi << 14) | (d << 28);           // offsets < 2^14: the largest level of l = 6 pairs has 1640 entries
+    }
+    __syncthreads();
+    const double abx = ab[0], aby = ab[1], abz = ab[2];
+    const int total = pre * out_part * post;
+    const FastDiv dpost(post), dpart(out_part);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int r = dpost.div(idx), q = idx - r * post;
+        const int p = dpart.div(r), part = r - p * out_part;
+        const int m = s_map[part];
+        const int d = m >> 28;
+        const double *base = in + (size_t)p * in_part * post + q;
+        const double lo = base[(size_t)(m & 0x3fff) * post], hi = base[(size_t)((m >> 14) & 0x3fff) * post];
+        out[idx] = fma(d == 0 ? abx : d == 1 ? aby : abz, lo, hi);
     }
 }
 
-// out[p][m][q] = sum_c C[m][c] in[p][c][q]
+// out[p][m][q] = sum_c C[m][c] in[p][c][q]; zero coefficients (more than half of every cart->sph matrix) are skipped
 __device__ void c2s_index(const double *in, double *out, int pre, int post, int l, const double *__restrict__ cmat)
 {
     const int nin = B200_NCART(l), nout = 2 * l + 1;
     const int total = pre * nout * post;
+    const FastDiv dpost(post), dout(nout);
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int q = idx % post;
-        int m = (idx / post) % nout;
-        int p = idx / (post * nout);
+        const int r = dpost.div(idx), q = idx - r * post;
+        const int p = dout.div(r), m = r - p * nout;
         const double *src = in + (size_t)p * nin * post + q;
         const double *cm = cmat + m * nin;
         double s = 0;
-        for (int c = 0; c < nin; c++) s = fma(__ldg(cm + c), src[(size_t)c * post], s);
+        for (int c = 0; c < nin; c++) {
+            const double cf = __ldg(cm + c);
+            if (cf != 0.0) s = fma(cf, src[(size_t)c * post], s);
+        }
         out[idx] = s;
     }
 }
@@ -106,7 +129,8 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
     double *s_g = s_rw + 2 * nreff;                      // [3][nreff][nmax+1][mmax+1]
     int *s_ecomp = (int *)(s_g + 3 * nreff * gstride_r);   // [nE], [nF] packed exponents
     int *s_fcomp = s_ecomp + nE;
-    double *s_dyn = (double *)(s_fcomp + nF + ((nE + nF) & 1));
+    int *s_map = s_fcomp + nF;                            // [C.map_ints] HRR map of the current level
+    double *s_dyn = (double *)(s_map + C.map_ints + ((nE + nF + C.map_ints) & 1));
     double *gscratch = C.scratch + (size_t)blockIdx.x * C.scratch_per_block;
     double *acc, *w0, *w1;
     if (C.acc_in_smem) { acc = s_dyn; s_dyn += (size_t)ncomb * nEF; }
@@ -199,8 +223,9 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
                 __syncthreads();
                 const double *ccb = P.pcoef + hb.cc_off + (size_t)bq * C.ncab;
                 const double *cck = P.pcoef + hk.cc_off + (size_t)kq * C.nccd;
+                const FastDiv dF(nF);
                 for (int idx = tid; idx < nEF; idx += blockDim.x) {
-                    const int e = idx / nF, f = idx - e * nF;
+                    const int e = dF.div(idx), f = idx - e * nF;
                     const int ec = s_ecomp[e], fc = s_fcomp[f];
                     const int ms = mmax + 1;
                     const int ox = (ec & 255) * ms + (fc & 255);
@@ -230,52 +255,20 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
         const int cm = P.cart ? 15 : (task.flags & 15);          // indices that stay Cartesian (block-uniform)
         const int da = (cm & 1) ? nfa : 2 * la + 1, db = (cm & 2) ? nfb : 2 * lb + 1;
         const int dc = (cm & 4) ? nfc : 2 * lc + 1, dd = (cm & 8) ? nfd : 2 * ld + 1;
-        const bool use_table = C.epi.rowptr != nullptr && cm == C.epi_cm;
         for (int comb = 0; comb < ncomb; comb++) {
             const int cab = comb % C.ncab, ccd = comb / C.ncab;
             const int ca = cab % hb.nca, cb = cab / hb.nca;
             const int cc = ccd % hk.nca, cd = ccd / hk.nca;
             const double *cur = acc + (size_t)comb * nEF;
             double *nxt = w0;
-            if (use_table) {
-                // table-driven epilogue: the stages are sparse maps precomputed per class (kernels.h:EpiTable)
-                for (int sidx = 0; sidx < C.epi.nstages; sidx++) {
-                    const EpiStage S = C.epi.st[sidx];
-                    const double *ab = S.which == 1 ? hb.ab : hk.ab;
-                    const int *rp = C.epi.rowptr + S.row0;
-                    for (int idx = tid; idx < S.nout; idx += blockDim.x) {
-                        double v = 0;
-                        for (int e = rp[idx]; e < rp[idx + 1]; e++) {
-                            const int2 en = C.epi.ent[e];
-                            const double f = en.y ? C.epi.coef[e] * ab[en.y - 1] : C.epi.coef[e];
-                            v = fma(f, cur[en.x], v);
-                        }
-                        nxt[idx] = v;
-                    }
-                    __syncthreads();
-                    cur = nxt;
-                    nxt = (nxt == w0) ? w1 : w0;
-                }
-                const int n_out = C.epi.n_out;
-                double *dst = out + task.off + (long long)ca * da * task.sa + (long long)cb * db * task.sb
-                            + (long long)cc * dc * task.sc + (long long)cd * dd * task.sd;
-                const uchar4 *sidx4 = C.epi.store_idx + (task.sa <= task.sb ? 0 : n_out);
-                for (int idx = tid; idx < n_out; idx += blockDim.x) {
-                    const uchar4 m = sidx4[idx];
-                    dst[(long long)m.x * task.sa + (long long)m.y * task.sb + m.z * task.sc + m.w * task.sd]
-                        = cur[((m.x * db + m.y) * dc + m.z) * dd + m.w];
-                }
-                __syncthreads();
-                continue;
-            }
             for (int jb = 1; jb <= lb; jb++) {
-                hrr_level(cur, nxt, 1, nF, la, la + lb - jb + 1, jb, hb.ab);
+                hrr_level(cur, nxt, 1, nF, la, la + lb - jb + 1, jb, hb.ab, s_map);
                 __syncthreads();
                 cur = nxt;
                 nxt = (nxt == w0) ? w1 : w0;
             }
             for (int jd = 1; jd <= ld; jd++) {
-                hrr_level(cur, nxt, nfa * nfb, 1, lc, lc + ld - jd + 1, jd, hk.ab);
+                hrr_level(cur, nxt, nfa * nfb, 1, lc, lc + ld - jd + 1, jd, hk.ab, s_map);
                 __syncthreads();
                 cur = nxt;
                 nxt = (nxt == w0) ? w1 : w0;
@@ -291,11 +284,13 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
             double *dst = out + task.off + (long long)ca * da * task.sa + (long long)cb * db * task.sb
                         + (long long)cc * dc * task.sc + (long long)cd * dd * task.sd;
             const bool a_fast = task.sa <= task.sb;
+            const FastDiv d1(a_fast ? da : db), d2(a_fast ? db : da), d3(dc);
             for (int idx = tid; idx < n_out; idx += blockDim.x) {
-                int ma, mb, r;
-                if (a_fast) { ma = idx % da; r = idx / da; mb = r % db; r /= db; }
-                else        { mb = idx % db; r = idx / db; ma = r % da; r /= da; }
-                const int mc = r % dc, md = r / dc;
+                int r = d1.div(idx);
+                const int m1 = idx - r * d1.d;
+                const int r2 = d2.div(r), m2 = r - r2 * d2.d;
+                const int ma = a_fast ? m1 : m2, mb = a_fast ? m2 : m1;
+                const int md = d3.div(r2), mc = r2 - md * dc;
                 dst[(long long)ma * task.sa + (long long)mb * task.sb + mc * task.sc + md * task.sd]
                     = cur[((ma * db + mb) * dc + mc) * dd + md];
             }
@@ -329,150 +324,6 @@ static size_t epilogue_work_size(int la, int lb, int lc, int ld, int cart)
     return mx;
 }
 
-// ---------------------------------------------------------------- table-driven epilogue (host side)
-// Built once per (class, Cartesian mask 0 / 15) and device, cached for the life of the process: the exact index arithmetic of
-// hrr_level / c2s_index / the store loop above, evaluated on the host.
-#include <map>
-#include <mutex>
-#include <vector>
-#include <array>
-static void host_cart_xyz(int l, int idx, int *lx, int *ly, int *lz)
-{
-    int n = 0;
-    for (int x = l; x >= 0; x--)
-        for (int y = l - x; y >= 0; y--, n++)
-            if (n == idx) { *lx = x; *ly = y; *lz = l - x - y; return; }
-    *lx = *ly = *lz = 0;
-}
-static int host_cart_index(int lx, int lz, int l) { const int r = l - lx; return r * (r + 1) / 2 + lz; }
-
-struct EpiHost { std::vector<int> rowptr; std::vector<int2> ent; std::vector<double> coef; std::vector<EpiStage> st; };
-
-static void epi_add_hrr(EpiHost &H, int which, int pre, int post, int l0, int ltop, int jb)
-{
-    const int nb_in = B200_NCART(jb - 1), nb_out = B200_NCART(jb);
-    int in_part = 0, out_part = 0;
-    for (int le = l0; le <= ltop; le++) in_part += B200_NCART(le) * nb_in;
-    for (int le = l0; le < ltop; le++) out_part += B200_NCART(le) * nb_out;
-    const int total = pre * out_part * post;
-    H.st.push_back(EpiStage{total, which, (int)H.rowptr.size()});
-    for (int idx = 0; idx < total; idx++) {
-        const int q = idx % post;
-        int part = (idx / post) % out_part;
-        const int p = idx / (post * out_part);
-        int le = l0, in_off = 0;
-        while (part >= B200_NCART(le) * nb_out) { part -= B200_NCART(le) * nb_out; in_off += B200_NCART(le) * nb_in; le++; }
-        const int ie = part / nb_out, ib = part - ie * nb_out;
-        int bx, by, bz, ax, ay, az;
-        host_cart_xyz(jb, ib, &bx, &by, &bz);
-        host_cart_xyz(le, ie, &ax, &ay, &az);
-        const int d = bx ? 0 : (by ? 1 : 2);
-        bx -= (d == 0); bz -= (d == 2);
-        const int ibp = host_cart_index(bx, bz, jb - 1), iep = host_cart_index(ax + (d == 0), az + (d == 2), le + 1);
-        const int base = p * in_part * post;
-        H.rowptr.push_back((int)H.ent.size());
-        H.ent.push_back(make_int2(base + (in_off + B200_NCART(le) * nb_in + iep * nb_in + ibp) * post + q, 0)); H.coef.push_back(1.0);
-        H.ent.push_back(make_int2(base + (in_off + ie * nb_in + ibp) * post + q, d + 1)); H.coef.push_back(1.0);
-    }
-    H.rowptr.push_back((int)H.ent.size());
-}
-
-static void epi_add_c2s(EpiHost &H, int pre, int post, int l, const double *cmat)
-{
-    const int nin = B200_NCART(l), nout = 2 * l + 1, total = pre * nout * post;
-    H.st.push_back(EpiStage{total, 1, (int)H.rowptr.size()});
-    for (int idx = 0; idx < total; idx++) {
-        const int q = idx % post, m = (idx / post) % nout, p = idx / (post * nout);
-        H.rowptr.push_back((int)H.ent.size());
-        for (int c = 0; c < nin; c++)
-            if (cmat[m * nin + c] != 0.0) { H.ent.push_back(make_int2(p * nin * post + q + c * post, 0)); H.coef.push_back(cmat[m * nin + c]); }
-    }
-    H.rowptr.push_back((int)H.ent.size());
-}
-
-// c2s_host: the dense cart->sph matrices (host copy of what EngineParams::c2s holds), offsets c2s_off_table[l]
-int epilogue_table(EpiTable *T, int la, int lb, int lc, int ld, int cart, const double *c2s_host, const int *c2s_off_table)
-{
-    struct Dev { EpiTable t; };
-    static std::mutex mtx;
-    static std::map<std::array<int, 6>, Dev> cache;
-    std::lock_guard<std::mutex> lock(mtx);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const std::array<int, 6> key = {dev, la, lb, lc, ld, cart};
-    auto it = cache.find(key);
-    if (it != cache.end()) { *T = it->second.t; return T->rowptr ? 0 : -1; }
-    Dev D;
-    memset(&D.t, 0, sizeof D.t);
-    EpiHost H;
-    const int nF = sum_ncart(lc, lc + ld);
-    const int nfa = B200_NCART(la), nfb = B200_NCART(lb), nfc = B200_NCART(lc), nfd = B200_NCART(ld);
-    const int da = (cart || la < 2) ? nfa : 2 * la + 1, db = (cart || lb < 2) ? nfb : 2 * lb + 1;
-    const int dc = (cart || lc < 2) ? nfc : 2 * lc + 1, dd = (cart || ld < 2) ? nfd : 2 * ld + 1;
-    for (int jb = 1; jb <= lb; jb++) epi_add_hrr(H, 1, 1, nF, la, la + lb - jb + 1, jb);
-    for (int jd = 1; jd <= ld; jd++) epi_add_hrr(H, 2, nfa * nfb, 1, lc, lc + ld - jd + 1, jd);
-    if (!cart) {
-        if (la > 1) epi_add_c2s(H, 1, nfb * nfc * nfd, la, c2s_host + c2s_off_table[la]);
-        if (lb > 1) epi_add_c2s(H, da, nfc * nfd, lb, c2s_host + c2s_off_table[lb]);
-        if (lc > 1) epi_add_c2s(H, da * db, nfd, lc, c2s_host + c2s_off_table[lc]);
-        if (ld > 1) epi_add_c2s(H, da * db * dc, 1, ld, c2s_host + c2s_off_table[ld]);
-    }
-    const int n_out = da * db * dc * dd;
-    bool ok = H.st.size() <= 12 && H.ent.size() <= ((size_t)3 << 20) && da < 256 && db < 256 && dc < 256 && dd < 256;
-    if (ok) {
-        std::vector<uchar4> sidx(2 * (size_t)n_out);
-        for (int fast = 0; fast < 2; fast++)
-            for (int idx = 0; idx < n_out; idx++) {
-                int ma, mb, r;
-                if (fast == 0) { ma = idx % da; r = idx / da; mb = r % db; r /= db; }
-                else           { mb = idx % db; r = idx / db; ma = r % da; r /= da; }
-                sidx[(size_t)fast * n_out + idx] = make_uchar4((unsigned char)ma, (unsigned char)mb, (unsigned char)(r % dc), (unsigned char)(r / dc));
-            }
-        int *d_rp = nullptr; int2 *d_en = nullptr; double *d_cf = nullptr; uchar4 *d_si = nullptr;
-        ok = cudaMalloc((void **)&d_rp, sizeof(int) * std::max<size_t>(1, H.rowptr.size())) == cudaSuccess &&
-             cudaMalloc((void **)&d_en, sizeof(int2) * std::max<size_t>(1, H.ent.size())) == cudaSuccess &&
-             cudaMalloc((void **)&d_cf, sizeof(double) * std::max<size_t>(1, H.coef.size())) == cudaSuccess &&
-             cudaMalloc((void **)&d_si, sizeof(uchar4) * sidx.size()) == cudaSuccess &&
-             cudaMemcpy(d_rp, H.rowptr.data(), sizeof(int) * H.rowptr.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(d_en, H.ent.data(), sizeof(int2) * H.ent.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(d_cf, H.coef.data(), sizeof(double) * H.coef.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-             cudaMemcpy(d_si, sidx.data(), sizeof(uchar4) * sidx.size(), cudaMemcpyHostToDevice) == cudaSuccess;
-        if (ok) {
-            D.t.nstages = (int)H.st.size(); D.t.n_out = n_out;
-            for (size_t k = 0; k < H.st.size(); k++) D.t.st[k] = H.st[k];
-            D.t.rowptr = d_rp; D.t.ent = d_en; D.t.coef = d_cf; D.t.store_idx = d_si;
-        } else { cudaFree(d_rp); cudaFree(d_en); cudaFree(d_cf); cudaFree(d_si); cudaGetLastError(); }
-    }
-    cache[key] = D;
-    *T = D.t;
-    return T->rowptr ? 0 : -1;
-}
-
-int generic_setup_constants()
-{
-    int off[2 * B200_LMAX + 2];
-    static unsigned char xyz[3 * 560];
-    int n = 0;
-    for (int l = 0; l <= 2 * B200_LMAX; l++) {
-        off[l] = n;
-        for (int lx = l; lx >= 0; lx--)
-            for (int ly = l - lx; ly >= 0; ly--, n++) {
-                xyz[3 * n] = (unsigned char)lx;
-                xyz[3 * n + 1] = (unsigned char)ly;
-                xyz[3 * n + 2] = (unsigned char)(l - lx - ly);
-            }
-    }
-    off[2 * B200_LMAX + 1] = n;
-    if (n > 560) return -1;
-    if (cudaMemcpyToSymbol(c_cart_off, off, sizeof off) != cudaSuccess) return -1;
-    if (cudaMemcpyToSymbol(c_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
-    if (cudaMemcpyToSymbol(d_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
-    return 0;
-}
-
-extern const double *engine_c2s_coef();
-int epilogue_table(EpiTable *T, int la, int lb, int lc, int ld, int cart, const double *c2s_host, const int *c2s_off_table);
-
 // Plan a launch for one class; returns 0 on success.  scratch is (re)allocated by the caller.
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
                  int cart, long long ntasks, const int *c2s_off_table, int short_range)
@@ -490,22 +341,27 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     C->c2s_off[2] = c2s_off_table[lc]; C->c2s_off[3] = c2s_off_table[ld];
     const size_t nEF = (size_t)C->nE * C->nF;
     const int nmax = la + lb, mmax = lc + ld;
+    // largest HRR level (entries of one [part] slice) of either pair: the shared-memory map of hrr_level
+    C->map_ints = 0;
+    for (int side = 0; side < 2; side++) {
+        const int l0 = side ? lc : la, l1 = side ? ld : lb;
+        for (int j = 1; j <= l1; j++) {
+            int part = 0;
+            for (int le = l0; le <= l0 + l1 - j; le++) part += B200_NCART(le) * B200_NCART(j);
+            if (part > C->map_ints) C->map_ints = part;
+        }
+    }
+    // FastDiv (kernel) is exact while index x divisor < 2^32: the largest stage times the largest pass-through extent
+    {
+        const double post_max = std::max<double>(C->nF, (double)B200_NCART(lb) * B200_NCART(lc) * B200_NCART(ld));
+        if ((double)C->work_size * post_max >= 4294967296.0) return -1;
+    }
     size_t fixed = sizeof(double) * (2 * C->nreff + (size_t)3 * C->nreff * (nmax + 1) * (mmax + 1))
-                 + sizeof(int) * (C->nE + C->nF + 2);
+                 + sizeof(int) * (C->nE + C->nF + C->map_ints + 2);
     size_t acc_b = sizeof(double) * nEF * ncab * nccd;
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
     const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
     size_t smem = fixed;
-    // table-driven epilogue (pure spherical / pure Cartesian output; needs a device: host-only planning skips it).  OFF by default:
-    // measured slower than the run-time index decoding (C2H6 cc-pVQZ pass 143 -> 168 ms, (ff|ff) 2.2 -> 3.1 us per quartet) --
-    // every block streams the class' whole table (~20 B per entry, up to 1 MB per quartet) from L2, which costs more than the
-    // ~150 instructions per element it saves.  CINTB200_EPITAB=1 enables it (kept for the parity test of the maps).
-    static const bool epi_on = getenv("CINTB200_EPITAB") && atoi(getenv("CINTB200_EPITAB"));
-    int dev_probe = 0;
-    C->epi_cm = cart ? 15 : 0;
-    if (epi_on && (la + lb + lc + ld) > 0 && cudaGetDevice(&dev_probe) == cudaSuccess)
-        epilogue_table(&C->epi, la, lb, lc, ld, cart, engine_c2s_coef(), c2s_off_table);
-    else cudaGetLastError();
     static const bool wide_on = !(getenv("CINTB200_NO_WIDE") && atoi(getenv("CINTB200_NO_WIDE")));
     C->wide = wide_on && wide_eligible(la, lb, lc, ld, ncab, nccd, short_range);
     C->acc_in_smem = !C->wide && (smem + acc_b <= budget);      // wide classes: the accumulators arrive in global scratch

@@ -30,6 +30,7 @@
 #include "types.h"
 #include "rys.cuh"
 #include "c2s_constexpr.inc"
+#include "tune.inc"
 
 // ----------------------------------------------------------------------------- compile-time helpers
 template <class F, int... I>
@@ -305,9 +306,17 @@ template <int L> struct SphDim { static constexpr int value = (L < 2) ? cx_ncart
 // they are kept in SHARED memory (layout [i][thread], conflict-free) when small enough, which frees 2*NACC registers
 // and lets three blocks share an SM instead of two.
 __host__ __device__ constexpr bool reg_acc_in_smem(int nct, int nacc) { return nct > 1 && nacc <= REG_ACC_SMEM_MAX; }
+__host__ __device__ constexpr int reg_min_blocks(int la, int lb, int lc, int ld, int nct, int ncu)
+{
+    return tune_lookup(g_reg_tune, sizeof(g_reg_tune) / sizeof(ClassTune), tune_key(la, lb, lc, ld, nct, ncu), false, REG_MIN_BLOCKS);
+}
+__host__ __device__ constexpr int reg_uq_unroll(int la, int lb, int lc, int ld, int nct, int ncu)
+{
+    return tune_lookup(g_reg_tune, sizeof(g_reg_tune) / sizeof(ClassTune), tune_key(la, lb, lc, ld, nct, ncu), true, REG_UQ_UNROLL);
+}
 
 template <int LA, int LB, int LC, int LD, int NCT, int NCU, bool RS = false, bool CART = false>
-__global__ void __launch_bounds__(REG_THREADS, reg_acc_in_smem(NCT, NCT * NCU * cx_nrange(LA, LA + LB) * cx_nrange(LC, LC + LD)) ? 3 : REG_MIN_BLOCKS)
+__global__ void __launch_bounds__(REG_THREADS, reg_acc_in_smem(NCT, NCT * NCU * cx_nrange(LA, LA + LB) * cx_nrange(LC, LC + LD)) ? 3 : reg_min_blocks(LA, LB, LC, LD, NCT, NCU))
 eri_reg_kernel(const TileParams P)
 {
     constexpr int NMAX = LA + LB, MMAX = LC + LD;
@@ -460,7 +469,7 @@ eri_reg_kernel(const TileParams P)
 #pragma unroll
             for (int i = 0; i < NCU * NEF; i++) accu[i] = 0.0;
         }
-        constexpr int UQ_UNROLL = REG_UQ_UNROLL;
+        constexpr int UQ_UNROLL = reg_uq_unroll(LA, LB, LC, LD, NCT, NCU);
 #pragma unroll UQ_UNROLL
         for (int uq = 0; uq < nppu; uq++) {
             const double *su = s_u + uq * USTR;

@@ -4,20 +4,6 @@
 #include <string.h>
 #include "types.h"
 
-// Epilogue of a class as a chain of precomputed sparse maps (kern_generic.cu:epilogue_table): every HRR level and every
-// cart->sph stage is out[row] = sum_e coef[e] * (code[e] ? AB[code[e]-1] : 1) * in[col[e]] with AB = the bra (which = 1) or ket
-// (which = 2) shift vector -- the index arithmetic of the run-time epilogue (divisions, component decoding: ~150
-// instructions per element) is done once per class on the host instead of once per element and quartet.
-struct EpiStage { int nout, which, row0; };     // row0: first row of this stage in rowptr
-struct EpiTable {
-    int nstages, n_out;
-    EpiStage st[12];
-    const int *rowptr;          // [total rows + 1] first entry of every output row
-    const int2 *ent;            // {input column, code}
-    const double *coef;
-    const uchar4 *store_idx;    // [2][n_out] (ma, mb, mc, md) of output element idx for a-fastest / b-fastest stores
-};
-
 struct GenericClass {           // uniform per launch of eri_generic_kernel
     int la, lb, lc, ld;
     int nroots;
@@ -29,8 +15,7 @@ struct GenericClass {           // uniform per launch of eri_generic_kernel
     int c2s_off[4];             // offsets of the four c2s matrices inside EngineParams::c2s
     double *scratch;            // global scratch, scratch_per_block doubles per block
     size_t scratch_per_block;
-    EpiTable epi;               // epi.nstages >= 0 and epi.rowptr != NULL: table-driven epilogue (pure spherical or pure Cartesian output)
-    int epi_cm;                 // the Cartesian mask the table was built for (0 or 15)
+    int map_ints;               // ints of shared memory for the per-level HRR map (largest level of the class)
     int wide;                   // the quadrature runs on the wide kernel (kern_wide.cu), this kernel does the epilogue only
     int epilogue_only;          // set per launch: accumulators of task task_base + blockIdx.x are already in the block's scratch
     long long task_base;

@@ -324,6 +324,28 @@ static size_t epilogue_work_size(int la, int lb, int lc, int ld, int cart)
     return mx;
 }
 
+int generic_setup_constants()
+{
+    int off[2 * B200_LMAX + 2];
+    static unsigned char xyz[3 * 560];
+    int n = 0;
+    for (int l = 0; l <= 2 * B200_LMAX; l++) {
+        off[l] = n;
+        for (int lx = l; lx >= 0; lx--)
+            for (int ly = l - lx; ly >= 0; ly--, n++) {
+                xyz[3 * n] = (unsigned char)lx;
+                xyz[3 * n + 1] = (unsigned char)ly;
+                xyz[3 * n + 2] = (unsigned char)(l - lx - ly);
+            }
+    }
+    off[2 * B200_LMAX + 1] = n;
+    if (n > 560) return -1;
+    if (cudaMemcpyToSymbol(c_cart_off, off, sizeof off) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(c_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(d_cart_xyz, xyz, 3 * n) != cudaSuccess) return -1;
+    return 0;
+}
+
 // Plan a launch for one class; returns 0 on success.  scratch is (re)allocated by the caller.
 int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int ld, int ncab, int nccd,
                  int cart, long long ntasks, const int *c2s_off_table, int short_range)

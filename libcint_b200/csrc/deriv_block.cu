@@ -70,7 +70,7 @@ static inline void cart_xyz(int l, int idx, int *lx, int *ly, int *lz)
 template <class T>
 static int dev_upload(T **dst, const std::vector<T> &v)
 {
-    if (cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(1, v.size())) != cudaSuccess) return -1;
+    if (b200_dmalloc((void **)dst, sizeof(T) * std::max<size_t>(1, v.size())) != cudaSuccess) return -1;
     if (!v.empty() && cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess) return -1;
     return 0;
 }
@@ -163,7 +163,7 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
         long long dims[5] = {NC[0], NC[1], NC[2], NC[3], 3};
         if (!cart) {
             // 3. cart -> sph along each index (s and p shells: identity; d and higher: the matrices of c2s_tables.inc)
-            if (cudaMalloc((void **)&d_coef, sizeof(double) * (sizeof(C2S_COEF) / sizeof(double) + 1)) != cudaSuccess) { rc = b200_fail(CINTB200_ENOMEM, "c2s table"); goto done; }
+            if (b200_dmalloc((void **)&d_coef, sizeof(double) * (sizeof(C2S_COEF) / sizeof(double) + 1)) != cudaSuccess) { rc = b200_fail(CINTB200_ENOMEM, "c2s table"); goto done; }
             std::vector<double> coef(C2S_COEF, C2S_COEF + sizeof(C2S_COEF) / sizeof(double));
             const int one_off = (int)coef.size();
             coef.push_back(1.0);
@@ -207,8 +207,8 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
 done:
     cudaStreamSynchronize(st);
     b200_big_free(dP); b200_big_free(dM); b200_big_free(dA); b200_big_free(dB);
-    cudaFree(d_coef); cudaFree(d_cP); cudaFree(d_cM); cudaFree(d_ipP); cudaFree(d_ipM);
-    for (int m = 0; m < 4; m++) for (int k = 0; k < 3; k++) cudaFree(d_tab[m][k]);
+    b200_dfree(d_coef); b200_dfree(d_cP); b200_dfree(d_cM); b200_dfree(d_ipP); b200_dfree(d_ipM);
+    for (int m = 0; m < 4; m++) for (int k = 0; k < 3; k++) b200_dfree(d_tab[m][k]);
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return rc;
 }

@@ -49,17 +49,17 @@ struct DigestState {
 void digest_free(DigestState *d)
 {
     if (!d) return;
-    cudaFree(d->d_rowI); cudaFree(d->d_colK); cudaFree(d->d_colg); cudaFree(d->d_rowsums);
-    cudaFree(d->d_rowinfo); cudaFree(d->d_colinfo); cudaFree(d->d_colc); cudaFree(d->d_cold); cudaFree(d->d_units); cudaFree(d->d_entries);
-    cudaFree(d->d_dm); cudaFree(d->d_Dab); cudaFree(d->d_Dcd); b200_big_free(d->d_PA); b200_big_free(d->d_PB);
-    cudaFree(d->d_Jp); cudaFree(d->d_Kp); cudaFree(d->d_jrow); cudaFree(d->d_jcol);
+    b200_dfree(d->d_rowI); b200_dfree(d->d_colK); b200_dfree(d->d_colg); b200_dfree(d->d_rowsums);
+    b200_dfree(d->d_rowinfo); b200_dfree(d->d_colinfo); b200_dfree(d->d_colc); b200_dfree(d->d_cold); b200_dfree(d->d_units); b200_dfree(d->d_entries);
+    b200_dfree(d->d_dm); b200_dfree(d->d_Dab); b200_dfree(d->d_Dcd); b200_big_free(d->d_PA); b200_big_free(d->d_PB);
+    b200_dfree(d->d_Jp); b200_dfree(d->d_Kp); b200_dfree(d->d_jrow); b200_dfree(d->d_jcol);
     delete d;
 }
 
 template <class T>
 static int up(T **dst, const std::vector<T> &src)
 {
-    if (cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(1, src.size())) != cudaSuccess)
+    if (b200_dmalloc((void **)dst, sizeof(T) * std::max<size_t>(1, src.size())) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", sizeof(T) * src.size());
     if (!src.empty() && cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess)
         return b200_fail(CINTB200_ENODEV, "upload failed");
@@ -128,7 +128,7 @@ static int checksums_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
         }
     }
     if (up(&d->d_rowI, rowI) || up(&d->d_colK, colK) || up(&d->d_colg, colg)) return CINTB200_ENOMEM;
-    if (cudaMalloc((void **)&d->d_rowsums, sizeof(double) * 3 * std::max<long long>(1, d->nrows)) != cudaSuccess)
+    if (b200_dmalloc((void **)&d->d_rowsums, sizeof(double) * 3 * std::max<long long>(1, d->nrows)) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate the row-sum buffer");
     return 0;
 }
@@ -364,12 +364,12 @@ static int jk_prepare(CINTOpt *c, JobPlan *plan, DigestState *d)
     if (up(&d->d_rowinfo, rowinfo) || up(&d->d_colinfo, colinfo) || up(&d->d_colc, colc) || up(&d->d_cold, cold) ||
         up(&d->d_units, units) || up(&d->d_entries, entries)) return CINTB200_ENOMEM;
     const size_t n2 = (size_t)nao * nao;
-    if (cudaMalloc((void **)&d->d_dm, sizeof(double) * n2) != cudaSuccess || cudaMalloc((void **)&d->d_Jp, sizeof(double) * n2) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_Kp, sizeof(double) * n2) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_Dab, sizeof(double) * std::max<long long>(1, d->nrows)) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_Dcd, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_jrow, sizeof(double) * std::max<long long>(1, d->nrows)) != cudaSuccess ||
-        cudaMalloc((void **)&d->d_jcol, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
+    if (b200_dmalloc((void **)&d->d_dm, sizeof(double) * n2) != cudaSuccess || b200_dmalloc((void **)&d->d_Jp, sizeof(double) * n2) != cudaSuccess ||
+        b200_dmalloc((void **)&d->d_Kp, sizeof(double) * n2) != cudaSuccess ||
+        b200_dmalloc((void **)&d->d_Dab, sizeof(double) * std::max<long long>(1, d->nrows)) != cudaSuccess ||
+        b200_dmalloc((void **)&d->d_Dcd, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
+        b200_dmalloc((void **)&d->d_jrow, sizeof(double) * std::max<long long>(1, d->nrows)) != cudaSuccess ||
+        b200_dmalloc((void **)&d->d_jcol, sizeof(double) * std::max<long long>(1, d->ncols)) != cudaSuccess ||
         b200_big_alloc((void **)&d->d_PA, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)) ||
         b200_big_alloc((void **)&d->d_PB, sizeof(double) * (size_t)nao * std::max<long long>(1, d->ldmax)))
         return b200_fail(CINTB200_ENOMEM, "J/K digestion: cannot allocate the work arrays (%zu bytes of row partials)", 2 * sizeof(double) * (size_t)nao * d->ldmax);

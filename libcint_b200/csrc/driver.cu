@@ -41,7 +41,7 @@ void jobplan_free(JobPlan *p)
     if (!p) return;
     p->arena.release();                     // every table uploaded while the plan was built
     if (p->own_out) b200_big_free(p->d_out[0]);
-    b200_big_free(p->d_out[1]); cudaFree(p->d_uprefix); cudaFree(p->d_scratch); cudaFree(p->d_counters);
+    b200_big_free(p->d_out[1]); b200_dfree(p->d_uprefix); b200_dfree(p->d_scratch); b200_dfree(p->d_counters);
     if (p->copy_stream) cudaStreamDestroy(p->copy_stream);
     for (int k = 0; k < JobPlan::NS; k++) { if (p->streams[k]) cudaStreamDestroy(p->streams[k]); if (p->ev_join[k]) cudaEventDestroy(p->ev_join[k]); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -85,7 +85,7 @@ static int upload(T **dst, const std::vector<T> &src)
     if (g_arena) {
         *dst = (T *)g_arena->alloc(bytes);
         if (!*dst) return b200_fail(CINTB200_ENOMEM, "device arena: %zu bytes failed", bytes);
-    } else if (cudaMalloc((void **)dst, bytes) != cudaSuccess)
+    } else if (b200_dmalloc((void **)dst, bytes) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", bytes);
     if (!src.empty() && cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess)
         return b200_fail(CINTB200_ENODEV, "upload failed");
@@ -499,11 +499,11 @@ static int build_launches(CINTOpt *c, JobPlan *plan)
     std::stable_sort(plan->launches.begin(), plan->launches.end(), [](const LaunchRec &a, const LaunchRec &b) {
         return a.chunk != b.chunk ? a.chunk < b.chunk : a.flops > b.flops; });
     if (!plan->host_only) {
-        if (cudaMalloc((void **)&plan->d_counters, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size())) != cudaSuccess)
+        if (b200_dmalloc((void **)&plan->d_counters, sizeof(unsigned int) * std::max<size_t>(1, plan->launches.size())) != cudaSuccess)
             return b200_fail(CINTB200_ENOMEM, "cannot allocate launch counters");
         for (size_t k = 0; k < plan->launches.size(); k++) plan->launches[k].P.counter = plan->d_counters + k;
     }
-    if (!plan->host_only && scratch_need && cudaMalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
+    if (!plan->host_only && scratch_need && b200_dmalloc((void **)&plan->d_scratch, sizeof(double) * scratch_need) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cannot allocate generic-kernel scratch");
     return 0;
 }
@@ -840,8 +840,8 @@ extern "C" int cintb200_int2e_sph_jk(cintb200_ctx *c, int rank, int nranks, size
     s.job.jk = 1; s.job.want_k = vk != nullptr; s.job.checksums = c->checksums;
     if (on_device) { s.dm_dev = dm; s.vj_dev = vj; s.vk_dev = vk; }
     else {
-        if (cudaMalloc((void **)&d_io, sizeof(double) * 3 * n2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "J/K: cannot allocate device matrices");
-        if (cudaMemcpy(d_io, dm, sizeof(double) * n2, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d_io); return b200_fail(CINTB200_ENODEV, "J/K: upload of dm failed"); }
+        if (b200_dmalloc((void **)&d_io, sizeof(double) * 3 * n2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "J/K: cannot allocate device matrices");
+        if (cudaMemcpy(d_io, dm, sizeof(double) * n2, cudaMemcpyHostToDevice) != cudaSuccess) { b200_dfree(d_io); return b200_fail(CINTB200_ENODEV, "J/K: upload of dm failed"); }
         s.dm_dev = d_io; s.vj_dev = vj ? d_io + n2 : nullptr; s.vk_dev = vk ? d_io + 2 * n2 : nullptr;
     }
     int rc = run_job(c, 4, 0, rank, nranks, chunk_bytes, s, stats);
@@ -849,7 +849,7 @@ extern "C" int cintb200_int2e_sph_jk(cintb200_ctx *c, int rank, int nranks, size
         if (vj && cudaMemcpy(vj, d_io + n2, sizeof(double) * n2, cudaMemcpyDeviceToHost) != cudaSuccess) rc = b200_fail(CINTB200_ENODEV, "J/K: download failed");
         if (vk && cudaMemcpy(vk, d_io + 2 * n2, sizeof(double) * n2, cudaMemcpyDeviceToHost) != cudaSuccess) rc = b200_fail(CINTB200_ENODEV, "J/K: download failed");
     }
-    cudaFree(d_io);
+    b200_dfree(d_io);
     return rc;
 }
 
@@ -936,7 +936,7 @@ void listtables_free(ListTables *lt)
 {
     if (!lt) return;
     for (ListClass &lc : lt->cls) { b200_big_free(lc.d_tprim); b200_big_free(lc.d_tgeom); b200_big_free(lc.d_tnpp); }
-    cudaFree(lt->d_buf); cudaFree(lt->d_cls_of); cudaFree(lt->d_row_of); cudaFree(lt->d_sdim); cudaFree(lt->d_per); b200_big_free(lt->d_work);
+    b200_dfree(lt->d_buf); b200_dfree(lt->d_cls_of); b200_dfree(lt->d_row_of); b200_dfree(lt->d_sdim); b200_dfree(lt->d_per); b200_big_free(lt->d_work);
     delete lt;
 }
 
@@ -1103,8 +1103,8 @@ int list_mode_run(CINTOpt *c, const Task *tasks, size_t n, double *d_out, unsign
     const size_t o_upair = al(o_tstr + sizeof(int) * 2 * m), o_ustr = al(o_upair + sizeof(int) * upair.size());
     const size_t o_cnt = al(o_ustr + sizeof(int) * ustr2.size()), bytes = al(o_cnt + sizeof(unsigned int) * groups.size());
     if (lt->cap < bytes) {
-        cudaFree(lt->d_buf); lt->d_buf = nullptr; lt->cap = 0;
-        if (cudaMalloc(&lt->d_buf, bytes * 2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "list-mode work arrays: %zu bytes", bytes * 2);
+        b200_dfree(lt->d_buf); lt->d_buf = nullptr; lt->cap = 0;
+        if (b200_dmalloc(&lt->d_buf, bytes * 2) != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "list-mode work arrays: %zu bytes", bytes * 2);
         lt->cap = bytes * 2;
     }
     char *d = (char *)lt->d_buf;

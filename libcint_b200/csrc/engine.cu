@@ -263,13 +263,13 @@ static void build_pairs(CINTOpt *c)
 
 static int ctx_upload(CINTOpt *c)
 {
-    CUDA_OK(cudaMalloc(&c->d_pairs, sizeof(PairHdr) * c->pairs.size()));
-    CUDA_OK(cudaMalloc(&c->d_prims, sizeof(PrimPair) * std::max<size_t>(1, c->prims.size())));
-    CUDA_OK(cudaMalloc(&c->d_pcoef, sizeof(double) * std::max<size_t>(1, c->pcoef.size())));
-    CUDA_OK(cudaMalloc(&c->d_rys, sizeof(RYS_TAB_COEF)));
-    CUDA_OK(cudaMalloc(&c->d_rys_fast, sizeof(RYS_FAST_COEF)));
+    CUDA_OK(b200_dmalloc(&c->d_pairs, sizeof(PairHdr) * c->pairs.size()));
+    CUDA_OK(b200_dmalloc(&c->d_prims, sizeof(PrimPair) * std::max<size_t>(1, c->prims.size())));
+    CUDA_OK(b200_dmalloc(&c->d_pcoef, sizeof(double) * std::max<size_t>(1, c->pcoef.size())));
+    CUDA_OK(b200_dmalloc(&c->d_rys, sizeof(RYS_TAB_COEF)));
+    CUDA_OK(b200_dmalloc(&c->d_rys_fast, sizeof(RYS_FAST_COEF)));
     CUDA_OK(cudaMemcpy(c->d_rys_fast, RYS_FAST_COEF, sizeof(RYS_FAST_COEF), cudaMemcpyHostToDevice));
-    CUDA_OK(cudaMalloc(&c->d_c2s, sizeof(C2S_COEF)));
+    CUDA_OK(b200_dmalloc(&c->d_c2s, sizeof(C2S_COEF)));
     CUDA_OK(cudaMemcpy(c->d_pairs, c->pairs.data(), sizeof(PairHdr) * c->pairs.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->d_prims, c->prims.data(), sizeof(PrimPair) * c->prims.size(), cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->d_pcoef, c->pcoef.data(), sizeof(double) * c->pcoef.size(), cudaMemcpyHostToDevice));
@@ -349,10 +349,16 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
         return;
     }
     cudaSetDevice(c->device);
+    double tph = b200_now();
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_pairs); cudaFree(c->d_prims); cudaFree(c->d_pcoef); cudaFree(c->d_rys); cudaFree(c->d_rys_fast); cudaFree(c->d_c2s);
-    cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_nonzero); cudaFree(c->d_scratch); cudaFree(c->d_counters);
+    b200_phase("destroy: stream sync", tph);
+    tph = b200_now();
+    b200_dfree(c->d_pairs); b200_dfree(c->d_prims); b200_dfree(c->d_pcoef); b200_dfree(c->d_rys); b200_dfree(c->d_rys_fast); b200_dfree(c->d_c2s);
+    b200_dfree(c->d_tasks); b200_dfree(c->d_out); b200_dfree(c->d_nonzero); b200_dfree(c->d_scratch); b200_dfree(c->d_counters);
+    b200_phase("destroy: context tables", tph);
+    tph = b200_now();
     if (c->plan) { jobplan_free(c->plan); c->plan = nullptr; }
+    b200_phase("destroy: job plan", tph);
     if (c->deriv) { cintb200_destroy(c->deriv); c->deriv = nullptr; }
     if (c->ltab) { listtables_free(c->ltab); c->ltab = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -367,9 +373,9 @@ int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_h
 {
     if (*cap >= bytes) return 0;
     size_t want = std::max(bytes, *cap * 2);
-    if (*ptr) { if (pinned_host) cudaFreeHost(*ptr); else cudaFree(*ptr); *ptr = NULL; *cap = 0; }
-    cudaError_t e = pinned_host ? cudaMallocHost(ptr, want) : cudaMalloc(ptr, want);
-    if (e != cudaSuccess && want > bytes) { want = bytes; e = pinned_host ? cudaMallocHost(ptr, want) : cudaMalloc(ptr, want); }
+    if (*ptr) { if (pinned_host) cudaFreeHost(*ptr); else b200_dfree(*ptr); *ptr = NULL; *cap = 0; }
+    cudaError_t e = pinned_host ? cudaMallocHost(ptr, want) : b200_dmalloc(ptr, want);
+    if (e != cudaSuccess && want > bytes) { want = bytes; e = pinned_host ? cudaMallocHost(ptr, want) : b200_dmalloc(ptr, want); }
     if (e != cudaSuccess) return b200_fail(CINTB200_ENOMEM, "allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
     *cap = want;
     (void)c;
@@ -758,14 +764,14 @@ static long run_batch_ip(CINTOpt *c, int ncenter, int dpos, int kind, const int 
     double *d_p = nullptr, *d_m = nullptr, *d_o = nullptr;
     IpTask *d_it = nullptr;
     int *d_c2soff = nullptr;
-    auto cleanup = [&]() { cudaFree(d_p); cudaFree(d_m); cudaFree(d_it); cudaFree(d_c2soff); if (!on_device) cudaFree(d_o); };
-    if (cudaMalloc(&d_p, sizeof(double) * std::max<size_t>(1, totp)) != cudaSuccess || cudaMalloc(&d_m, sizeof(double) * std::max<size_t>(1, totm)) != cudaSuccess ||
-        cudaMalloc(&d_it, sizeof(IpTask) * n) != cudaSuccess || cudaMalloc(&d_c2soff, sizeof(C2S_OFF)) != cudaSuccess) {
+    auto cleanup = [&]() { b200_dfree(d_p); b200_dfree(d_m); b200_dfree(d_it); b200_dfree(d_c2soff); if (!on_device) b200_dfree(d_o); };
+    if (b200_dmalloc(&d_p, sizeof(double) * std::max<size_t>(1, totp)) != cudaSuccess || b200_dmalloc(&d_m, sizeof(double) * std::max<size_t>(1, totm)) != cudaSuccess ||
+        b200_dmalloc(&d_it, sizeof(IpTask) * n) != cudaSuccess || b200_dmalloc(&d_c2soff, sizeof(C2S_OFF)) != cudaSuccess) {
         cleanup();
         return b200_fail(CINTB200_ENOMEM, "derivative scratch allocation failed");
     }
     d_o = out;
-    if (!on_device && cudaMalloc(&d_o, sizeof(double) * toto) != cudaSuccess) { d_o = nullptr; cleanup(); return b200_fail(CINTB200_ENOMEM, "derivative output allocation failed"); }
+    if (!on_device && b200_dmalloc(&d_o, sizeof(double) * toto) != cudaSuccess) { d_o = nullptr; cleanup(); return b200_fail(CINTB200_ENOMEM, "derivative output allocation failed"); }
     std::vector<int> nzp(n, 0), nzm(offm.size(), 0);
     // Cartesian kind: every index of the helper blocks is Cartesian anyway, so they are ordinary int2e_cart batches and run on
     // the specialised tile kernels (list mode); spherical kind: the differentiated index alone stays Cartesian (generic kernel)
@@ -845,10 +851,10 @@ int ctx_compute_schwarz(CINTOpt *c)
     double *d_v = nullptr, *d_q = nullptr;
     size_t *d_off = nullptr, *d_len = nullptr;
     CUDA_OK(cudaSetDevice(c->device));
-    CUDA_OK(cudaMalloc(&d_v, sizeof(double) * total));
-    CUDA_OK(cudaMalloc(&d_q, sizeof(double) * np));
-    CUDA_OK(cudaMalloc(&d_off, sizeof(size_t) * np));
-    CUDA_OK(cudaMalloc(&d_len, sizeof(size_t) * np));
+    CUDA_OK(b200_dmalloc(&d_v, sizeof(double) * total));
+    CUDA_OK(b200_dmalloc(&d_q, sizeof(double) * np));
+    CUDA_OK(b200_dmalloc(&d_off, sizeof(size_t) * np));
+    CUDA_OK(b200_dmalloc(&d_len, sizeof(size_t) * np));
     long rc = run_batch(c, 4, CINTB200_SPH, shls.data(), np, off.data(), d_v, 1, nullptr);
     if (rc >= 0) {
         cudaMemcpy(d_off, off.data(), sizeof(size_t) * np, cudaMemcpyHostToDevice);
@@ -857,7 +863,7 @@ int ctx_compute_schwarz(CINTOpt *c)
         c->schwarz.resize(np);
         if (cudaMemcpy(c->schwarz.data(), d_q, sizeof(double) * np, cudaMemcpyDeviceToHost) != cudaSuccess) { c->schwarz.clear(); rc = -1; }
     }
-    cudaFree(d_v); cudaFree(d_q); cudaFree(d_off); cudaFree(d_len);
+    b200_dfree(d_v); b200_dfree(d_q); b200_dfree(d_off); b200_dfree(d_len);
     return rc < 0 ? b200_fail(CINTB200_ENODEV, "Schwarz bound evaluation failed") : 0;
 }
 
@@ -1275,7 +1281,7 @@ extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
     double *buf;
-    CUDA_OK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    CUDA_OK(b200_dmalloc(&buf, sizeof(double) * blocks * threads));
     cudaEvent_t e0, e1;
     CUDA_OK(cudaEventCreate(&e0));
     CUDA_OK(cudaEventCreate(&e1));
@@ -1293,7 +1299,7 @@ extern "C" int cintb200_fp64_peak(int device, double seconds, double *tflops)
         if (tf > best) best = tf;
         spent += ms * 1e-3;
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); b200_dfree(buf);
     *tflops = best;
     return 0;
 }

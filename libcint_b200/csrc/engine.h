@@ -75,3 +75,8 @@ int ctx_reserve(CINTOpt *c, void **ptr, size_t *cap, size_t bytes, bool pinned_h
 // large device buffers from the stream-ordered pool (kept across contexts; engine.cu)
 int b200_big_alloc(void **p, size_t bytes);
 void b200_big_free(void *p);
+// Every device buffer of the library comes from that pool: a legacy cudaFree at context teardown was measured to stall for
+// 0.1-0.9 s at random while 80 GB of pooled tiles are cached (bench.py's end-to-end step went from 1.6 to 2.2-2.4 s); pooled
+// frees do not.  Same signatures as cudaMalloc / cudaFree.
+template <class T> static inline cudaError_t b200_dmalloc(T **p, size_t bytes) { return b200_big_alloc((void **)p, bytes) ? cudaErrorMemoryAllocation : cudaSuccess; }
+static inline cudaError_t b200_dfree(void *p) { b200_big_free(p); return cudaSuccess; }

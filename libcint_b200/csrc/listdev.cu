@@ -169,7 +169,7 @@ static int listdev_tables(CINTOpt *c)
             per[(size_t)cart * ncls * ncls + g] = ch.fn ? (ch.coop ? 32 / ch.ci.fs : 32) : 0;
         }
     auto up = [&](int **dst, const std::vector<int> &v) {
-        return cudaMalloc((void **)dst, sizeof(int) * std::max<size_t>(1, v.size())) == cudaSuccess &&
+        return b200_dmalloc((void **)dst, sizeof(int) * std::max<size_t>(1, v.size())) == cudaSuccess &&
                cudaMemcpy(*dst, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     };
     if (!up(&lt->d_cls_of, lt->cls_of) || !up(&lt->d_row_of, lt->row_of) || !up(&lt->d_sdim, sdim) || !up(&lt->d_per, per))

@@ -11,7 +11,8 @@ turns such tables into csrc/tune_reg.inc / tune_coop.inc.
 import sys, os, json, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"base": "", "va": "_va", "vb": "_vb", "vc": "_vc", "vd": "_vd", "ve": "_ve"}
+VARIANTS = {"base": "", "va": "_va", "vb": "_vb", "vc": "_vc", "vd": "_vd", "ve": "_ve", "alt": ""}
+VARIANT_ENV = {"alt": {"CINTB200_COOP_ALT": "1"}}       # same library, other orientation of the cooperative kernels (GEN_COOP_ALT=1 builds)
 # knob values of each variant: (reg minb, reg unroll, coop minb for nacc <= 16 / <= 32 / above)
 KNOBS = {"base": (2, 1, (4, 3, 2)), "va": (3, 1, (3, 2, 2)), "vb": (4, 1, (5, 4, 3)), "vc": (2, 2, (6, 5, 4)),
          "vd": (3, 2, (4, 3, 2)), "ve": (4, 2, (4, 3, 2))}
@@ -50,7 +51,7 @@ def run(job, reps):
         lib = os.path.join(ROOT, "libcint_b200", "libcint_b200%s.so" % suffix)
         if not os.path.exists(lib):
             continue
-        env = dict(os.environ, CINTB200_LIB=lib)
+        env = dict(os.environ, CINTB200_LIB=lib, **VARIANT_ENV.get(name, {}))
         p = subprocess.run([sys.executable, os.path.abspath(__file__), "worker", job, str(reps)], env=env, capture_output=True, text=True, timeout=900)
         m = re.search(r"TUNE_JSON (.*)", p.stdout)
         if not m:

@@ -150,7 +150,10 @@ struct JKArgs {
 // The partial sums go to private slots PA / PB[x][row] and are folded over the rows sharing a (or b) by jk_fold_kernel.
 // The Coulomb row part J'[a,b] += 2 s (ab|cd) D[c,d] rides along in the visit from the ket's first shell.
 // JK_RPT tile rows per thread: more loads in flight per thread (ncu: the kernel waits on HBM latency with 16 resident warps per SM),
-// the per-entry decoding shared by all of them
+// the per-entry decoding shared by all of them.  Measured alternative (round 2, removed): the column segments staged by per-warp
+// rings of cp.async.bulk copies completing on mbarriers (16 segments in flight per warp, density values prefetched one item
+// ahead) -- 1516 vs 1502 ms for the C60 J/K pass: the plateau at ~3.5 TB/s is not load latency in the SM but the access pattern
+// (2 KB column segments one leading dimension apart, each in a different DRAM page).
 template <int NX, int JK_RPT>
 __global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
 {
@@ -224,160 +227,6 @@ __global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
 #pragma unroll
     for (int q = 0; q < JK_RPT; q++)
         if (active[q] && jr[q] != 0.0) atomicAdd(A.jrow + A.row0 + row0 + 128 * q, jr[q]);
-}
-
-// ---- the same digestion with the tile columns staged by bulk asynchronous copies (cp.async.bulk + mbarrier) -----------------
-// The register version above waits on HBM latency: a thread has NX * JK_RPT loads in flight and nothing else to do until they
-// return.  Here every WARP owns 64 consecutive tile rows and a private ring of JKB_STAGES(NX) shared-memory stages; lane 0 queues
-// the NX column segments (64 rows x 8 B, one cp.async.bulk each) of the items (ket entry, y) several items ahead and the
-// copies complete on the stage's mbarrier, so ~16 column segments per warp are in flight regardless of registers.  Warps
-// stay independent (no block barriers); a stage is refilled right after the warp's lanes have pulled their values out
-// (__syncwarp orders the generic-proxy reads before the refill is issued).  Column segments that start on an odd double are
-// copied from 8 bytes earlier (cp.async.bulk needs 16-byte alignment) and read with an offset of one.
-__host__ __device__ constexpr int jkb_stages(int nx) { return nx <= 2 ? 8 : nx == 3 ? 5 : 4; }
-#define JKB_ROWS 64                     // tile rows per warp (2 per lane)
-#define JKB_STRIDE (JKB_ROWS + 2)       // doubles per staged column: the rows + one leading element of an unaligned start + padding to 16 B
-
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ bool mbar_try_wait(unsigned mbar, unsigned parity)
-{
-    unsigned ok;
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-    return ok != 0;
-}
-
-template <int NX>
-__global__ void __launch_bounds__(128) jk_rows_bulk_kernel(const JKArgs A)
-{
-    constexpr int S = jkb_stages(NX);
-    extern __shared__ __align__(16) double jkb_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *stage0 = jkb_smem + (size_t)warp * S * NX * JKB_STRIDE;                          // [S][NX][JKB_STRIDE]
-    unsigned long long *bars = (unsigned long long *)(jkb_smem + (size_t)4 * S * NX * JKB_STRIDE) + warp * S;
-    const long long wrow0 = ((long long)blockIdx.x * 4 + warp) * JKB_ROWS;                 // this warp's first tile row
-    if (wrow0 >= A.ld) return;                                                              // warps are independent: no block barriers below
-    const int nrw = (int)min((long long)JKB_ROWS, A.ld - wrow0);
-    if (lane == 0) {
-        for (int s = 0; s < S; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + s)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-    bool active[2];
-    int a[2], b[2], ij[2];
-    double fij[2], jr[2];
-    int maxij = -1;
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const int r = lane + 32 * q;
-        active[q] = r < nrw;
-        const int4 ri = active[q] ? A.rowinfo[A.row0 + wrow0 + r] : make_int4(0, 0, -1, 0);
-        a[q] = ri.x; b[q] = ri.y; ij[q] = ri.z; fij[q] = ri.w ? 0.5 : 1.0; jr[q] = 0.0;
-        maxij = max(maxij, ij[q]);
-    }
-    maxij = __reduce_max_sync(0xffffffffu, maxij);
-    const double *tw = A.tile + wrow0;
-    unsigned n_p = 0, n_c = 0;              // items produced / consumed by this warp so far (stage = n % S, parity = (n / S) & 1)
-
-    for (int u = A.ubeg + blockIdx.y; u < A.uend; u += gridDim.y) {
-        const JKUnit un = A.units[u];
-        // producer cursor (warp-uniform; lane 0 issues): next item = (entry pe, y = py)
-        int pe = un.ebeg, py = 0;
-        JKEntry pen = pe < un.eend ? A.entries[pe] : JKEntry{0, 0x7fffffff, 0, 0};
-        auto produce = [&]() {
-            if (pe >= un.eend || pen.kl > maxij) return;                    // nothing further is valid for this warp
-            const int dy = pen.info & 255, dk = (pen.info >> 8) & 255, xk = pen.info >> 16;
-            if (lane == 0) {
-                const long long sx = (xk ? 1 : dk) * A.ld, sy = (xk ? dk : 1) * A.ld;
-                const double *src0 = tw + (long long)pen.colbase * A.ld + py * sy;
-                double *dst = stage0 + (size_t)(n_p % S) * NX * JKB_STRIDE;
-                const unsigned bar = smem_u32(bars + n_p % S);
-                unsigned total = 0;
-#pragma unroll
-                for (int x = 0; x < NX; x++) {
-                    const double *src = src0 + x * sx;
-                    const unsigned mis = ((unsigned long long)src >> 3) & 1;
-                    total += ((nrw + mis) * 8 + 15) & ~15u;
-                }
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(total) : "memory");
-#pragma unroll
-                for (int x = 0; x < NX; x++) {
-                    const double *src = src0 + x * sx;
-                    const unsigned mis = ((unsigned long long)src >> 3) & 1;
-                    const unsigned bytes = ((nrw + mis) * 8 + 15) & ~15u;
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 :: "r"(smem_u32(dst + x * JKB_STRIDE)), "l"(src - mis), "r"(bytes), "r"(bar) : "memory");
-                }
-            }
-            n_p++;
-            if (++py == dy) { py = 0; pe++; if (pe < un.eend) pen = A.entries[pe]; }
-        };
-        for (int s = 0; s < S - 1; s++) produce();
-
-        double kA[2][NX], kB[2][NX];
-#pragma unroll
-        for (int q = 0; q < 2; q++)
-#pragma unroll
-            for (int x = 0; x < NX; x++) kA[q][x] = kB[q][x] = 0.0;
-        for (int e = un.ebeg; e < un.eend; e++) {
-            const JKEntry en = A.entries[e];
-            if (en.kl > maxij) break;
-            bool valid[2];
-            double w[2];
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                valid[q] = en.kl <= ij[q];
-                w[q] = valid[q] ? (en.kl == ij[q] ? 0.5 * fij[q] : fij[q]) : 0.0;
-            }
-            const int dy = en.info & 255, dk = (en.info >> 8) & 255, xk = en.info >> 16;
-            const long long sx = (xk ? 1 : dk) * A.ld, sy = (xk ? dk : 1) * A.ld;
-            const double *src0 = tw + (long long)en.colbase * A.ld;
-            for (int y = 0; y < dy; y++) {
-                produce();                                                   // keeps S - 1 items in flight ahead of this one
-                const double *st = stage0 + (size_t)(n_c % S) * NX * JKB_STRIDE;
-                const unsigned bar = smem_u32(bars + n_c % S);
-                while (!mbar_try_wait(bar, (n_c / S) & 1)) { }
-                double v[2][NX];
-#pragma unroll
-                for (int x = 0; x < NX; x++) {
-                    const unsigned mis = ((unsigned long long)(src0 + y * sy + x * sx) >> 3) & 1;
-#pragma unroll
-                    for (int q = 0; q < 2; q++) {
-                        const double t = st[x * JKB_STRIDE + mis + lane + 32 * q];
-                        v[q][x] = valid[q] ? t : 0.0;                        // entries outside the loop were never written
-                    }
-                }
-                n_c++;
-                __syncwarp();                                                // every lane has its values: the stage may be refilled
-                const double *Dy = A.dm + (size_t)(en.aoY + y) * A.nao;
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const double dA = w[q] * Dy[a[q]], dB = w[q] * Dy[b[q]];
-#pragma unroll
-                    for (int x = 0; x < NX; x++) {
-                        kA[q][x] = fma(v[q][x], dB, kA[q][x]);
-                        kB[q][x] = fma(v[q][x], dA, kB[q][x]);
-                        if (xk) jr[q] = fma(v[q][x] * w[q], A.Dcd[en.colbase + x + y * dk], jr[q]);
-                    }
-                }
-            }
-        }
-        if (A.want_k) {
-#pragma unroll
-            for (int q = 0; q < 2; q++)
-                if (active[q]) {
-#pragma unroll
-                    for (int x = 0; x < NX; x++) {
-                        A.PA[(size_t)(un.ao0 + x) * A.ldP + wrow0 + lane + 32 * q] = kA[q][x];
-                        A.PB[(size_t)(un.ao0 + x) * A.ldP + wrow0 + lane + 32 * q] = kB[q][x];
-                    }
-                }
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-        if (active[q] && jr[q] != 0.0) atomicAdd(A.jrow + A.row0 + wrow0 + lane + 32 * q, jr[q]);
 }
 
 // K'[a, x] += sum over the chunk's rows with first AO a of PA[x][row];  K'[b, x] += ... PB[x][row].  One block per x.
@@ -569,13 +418,8 @@ int digest_begin(CINTOpt *c, JobPlan *plan, const DigestJob &job, const double *
 }
 
 constexpr int jk_rpt(int nx) { return 2; }          // measured: 4 rows per thread for nx <= 3 is not faster (129 vs 124 ms for nx = 3)
-static size_t jkb_smem_bytes(int nx) { return sizeof(double) * (size_t)4 * jkb_stages(nx) * nx * JKB_STRIDE + sizeof(unsigned long long) * 4 * jkb_stages(nx); }
 template <int NX>
-static void launch_rows(const JKArgs &A, dim3 grid, cudaStream_t st, bool bulk)
-{
-    if (bulk) jk_rows_bulk_kernel<NX><<<grid, 128, jkb_smem_bytes(NX), st>>>(A);
-    else jk_rows_kernel<NX, jk_rpt(NX)><<<grid, 128, 0, st>>>(A);
-}
+static void launch_rows(const JKArgs &A, dim3 grid, cudaStream_t st) { jk_rows_kernel<NX, jk_rpt(NX)><<<grid, 128, 0, st>>>(A); }
 
 int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, const double *tile, cudaStream_t st)
 {
@@ -603,18 +447,15 @@ int digest_tile(CINTOpt *c, JobPlan *plan, const DigestJob &job, int chunk, cons
         for (int nx = 1; nx <= JK_NXMAX; nx++) {
             A.ubeg = d->unit_beg[nx]; A.uend = d->unit_beg[nx + 1];
             if (A.uend <= A.ubeg) continue;
-            // CINTB200_JK_BULK=0: the register version (loads straight into registers) instead of the bulk-copy pipeline
-            static const bool bulk = !(getenv("CINTB200_JK_BULK") && !atoi(getenv("CINTB200_JK_BULK")));
-            const int rows_per_block = bulk ? 4 * JKB_ROWS : 128 * jk_rpt(nx);
-            const unsigned gx = (unsigned)((ld + rows_per_block - 1) / rows_per_block);
+            const unsigned gx = (unsigned)((ld + 128 * jk_rpt(nx) - 1) / (128 * jk_rpt(nx)));
             const unsigned gy = (unsigned)std::max(1, std::min(A.uend - A.ubeg, (sms * 12 + (int)gx - 1) / (int)gx));
             const dim3 grid(gx, gy);
             switch (nx) {
-            case 1: launch_rows<1>(A, grid, st, bulk); break;
-            case 2: launch_rows<2>(A, grid, st, bulk); break;
-            case 3: launch_rows<3>(A, grid, st, bulk); break;
-            case 4: launch_rows<4>(A, grid, st, bulk); break;
-            default: launch_rows<5>(A, grid, st, bulk); break;
+            case 1: launch_rows<1>(A, grid, st); break;
+            case 2: launch_rows<2>(A, grid, st); break;
+            case 3: launch_rows<3>(A, grid, st); break;
+            case 4: launch_rows<4>(A, grid, st); break;
+            default: launch_rows<5>(A, grid, st); break;
             }
             CU_OK(cudaGetLastError());
         }

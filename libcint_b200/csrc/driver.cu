@@ -372,7 +372,7 @@ static int build_plan(CINTOpt *c, JobPlan *plan)
     }
     if (plan->host_only) return 0;
     // one tile buffer; the second one (overlap of D2H with the next chunk's kernels) is allocated on first use of a host sink
-    if (b200_big_alloc((void **)&plan->d_out[0], sizeof(double) * need))
+    if (b200_big_alloc((void **)&plan->d_out[0], sizeof(double) * (need + 16)))      // + slack: the bulk-copy consumers (digest.cu) round a column segment up to 16 bytes
         return b200_fail(CINTB200_ENOMEM, "cannot allocate %zu-byte tile buffer", sizeof(double) * need);
     CU_OK(cudaStreamCreateWithFlags(&plan->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
@@ -559,7 +559,7 @@ static int run_job(cintb200_ctx *c, int ncenter, int aux0, int rank, int nranks,
         if (rc) { jobplan_free(plan); return rc; }
         c->plan = plan;
     }
-    if (sink.sinks && !plan->d_out[1] && b200_big_alloc((void **)&plan->d_out[1], sizeof(double) * plan->out_doubles))
+    if (sink.sinks && !plan->d_out[1] && b200_big_alloc((void **)&plan->d_out[1], sizeof(double) * (plan->out_doubles + 16)))
         return b200_fail(CINTB200_ENOMEM, "cannot allocate the second %zu-byte tile buffer", sizeof(double) * plan->out_doubles);
     if (sink.sinks && plan->out_doubles * sizeof(double) > chunk_bytes)
         return b200_fail(CINTB200_EINVAL, "host sinks: the largest tile (one bra shell x all of this rank's kets) needs %zu bytes, "

@@ -152,8 +152,9 @@ struct JKArgs {
 // JK_RPT tile rows per thread: more loads in flight per thread (ncu: the kernel waits on HBM latency with 16 resident warps per SM),
 // the per-entry decoding shared by all of them.  Measured alternative (round 2, removed): the column segments staged by per-warp
 // rings of cp.async.bulk copies completing on mbarriers (16 segments in flight per warp, density values prefetched one item
-// ahead) -- 1516 vs 1502 ms for the C60 J/K pass: the plateau at ~3.5 TB/s is not load latency in the SM but the access pattern
-// (2 KB column segments one leading dimension apart, each in a different DRAM page).
+// ahead) -- 1516 vs 1502 ms for the C60 J/K pass: so the plateau at ~3.5 TB/s is not the SM-side load
+// latency the stall counters point at (not understood further; candidates: 2 KB column segments one leading dimension apart,
+// the dependent density gathers).
 template <int NX, int JK_RPT>
 __global__ void __launch_bounds__(128) jk_rows_kernel(const JKArgs A)
 {

@@ -11,7 +11,7 @@ turns such tables into csrc/tune_reg.inc / tune_coop.inc.
 import sys, os, json, re, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {"base": "", "va": "_va", "vb": "_vb", "vc": "_vc", "vd": "_vd", "ve": "_ve", "alt": ""}
+VARIANTS = {"base": "", "va": "_va", "vb": "_vb", "vc": "_vc", "vd": "_vd", "ve": "_ve", "alt": "", "fc": "_fc"}
 VARIANT_ENV = {"alt": {"CINTB200_COOP_ALT": "1"}}       # same library, other orientation of the cooperative kernels (GEN_COOP_ALT=1 builds)
 # knob values of each variant: (reg minb, reg unroll, coop minb for nacc <= 16 / <= 32 / above)
 KNOBS = {"base": (2, 1, (4, 3, 2)), "va": (3, 1, (3, 2, 2)), "vb": (4, 1, (5, 4, 3)), "vc": (2, 2, (6, 5, 4)),

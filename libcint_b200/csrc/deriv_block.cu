@@ -136,6 +136,7 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
     const size_t szP = (size_t)(NP * R), szM = (size_t)(NM * R), szD = (size_t)(3 * NC[0] * R);
     double st_p[16] = {0}, st_m[16] = {0};
     cudaStream_t st = c->stream;
+    double tph = b200_now();
     {
         std::lock_guard<std::mutex> lock(c->mtx);
         if (b200_big_alloc((void **)&dP, sizeof(double) * std::max<size_t>(1, szP)) || b200_big_alloc((void **)&dM, sizeof(double) * std::max<size_t>(1, szM)) ||
@@ -145,6 +146,8 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
         }
         if (dev_upload(&d_ipP, ipP) || dev_upload(&d_ipM, ipM) || dev_upload(&d_cP, cP) || dev_upload(&d_cM, cM)) { rc = b200_fail(CINTB200_ENOMEM, "derivative block tables"); goto done; }
     }
+    b200_phase("ip1 block: work tensors + derivative tables", tph);
+    tph = b200_now();
     {
         // 1. the two Cartesian helper blocks on the tile kernels
         int slp[8], slm[8];
@@ -154,6 +157,8 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
         if (!rc) rc = run_block(d, ncenter, slm, dM, 1, st_m, 1);
         if (rc) goto done;
     }
+    b200_phase("ip1 block: helper blocks (plan + kernels)", tph);
+    tph = b200_now();
     {
         std::lock_guard<std::mutex> lock(c->mtx);
         // 2. derivative in the Cartesian basis
@@ -206,9 +211,12 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
     }
 done:
     cudaStreamSynchronize(st);
+    b200_phase("ip1 block: assemble + c2s + copy", tph);
+    tph = b200_now();
     b200_big_free(dP); b200_big_free(dM); b200_big_free(dA); b200_big_free(dB);
     b200_dfree(d_coef); b200_dfree(d_cP); b200_dfree(d_cM); b200_dfree(d_ipP); b200_dfree(d_ipM);
     for (int m = 0; m < 4; m++) for (int k = 0; k < 3; k++) b200_dfree(d_tab[m][k]);
+    b200_phase("ip1 block: release", tph);
     if (prev_dev >= 0) cudaSetDevice(prev_dev);
     return rc;
 }

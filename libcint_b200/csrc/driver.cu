@@ -1313,17 +1313,25 @@ int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_d
             U.push_back(e);
         }
     }
+    double tph = b200_now();
     if (c->plan) { cudaDeviceSynchronize(); jobplan_free(c->plan); c->plan = nullptr; }
+    b200_phase("block: release previous plan", tph);
+    tph = b200_now();
     JobPlan *plan = new JobPlan();
     plan->ncenter = 3;                  // rectangular job: separate ket classes, every ket meets every bra (see build_launches)
     plan->rect = ncenter; plan->aux0 = 0; plan->rank = 0; plan->nranks = 1; plan->chunk_bytes = 0;
     plan->force_generic = c->force_generic; plan->schwarz_thr = 0; plan->cart = cart;
     int rc = build_rect_plan(c, plan, T, U, NI * NJ, NK * NL, on_device ? out : nullptr);
+    b200_phase("block: build_rect_plan", tph);
+    tph = b200_now();
     if (!rc) rc = build_launches(c, plan);
+    b200_phase("block: build_launches", tph);
     if (rc) { jobplan_free(plan); return rc; }
     c->plan = plan;
+    tph = b200_now();
     { TileSink ts; double *one[1] = {out}; if (!on_device) { ts.sinks = one; ts.nsinks = 1; }
       rc = execute_plan(c, plan, ncenter, ts, stats); }
+    b200_phase("block: execute", tph);
     return rc;
 }
 

@@ -139,11 +139,21 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
     double tph = b200_now();
     {
         std::lock_guard<std::mutex> lock(c->mtx);
-        if (b200_big_alloc((void **)&dP, sizeof(double) * std::max<size_t>(1, szP)) || b200_big_alloc((void **)&dM, sizeof(double) * std::max<size_t>(1, szM)) ||
-            b200_big_alloc((void **)&dA, sizeof(double) * std::max<size_t>(1, szD)) || (!cart && b200_big_alloc((void **)&dB, sizeof(double) * std::max<size_t>(1, szD)))) {
-            rc = b200_fail(CINTB200_ENOMEM, "derivative block: %zu bytes of work tensors", sizeof(double) * (szP + szM + 2 * szD));
-            goto done;
+        // the four work tensors live in the context and only grow (a gradient loop calls this once per ket shell: allocating
+        // them per call cost 9 ms of 35 ms per call on C2H6 cc-pVQZ)
+        const size_t want[4] = {szP, szM, szD, cart ? 0 : szD};
+        for (int k = 0; k < 4; k++) {
+            const size_t bytes = sizeof(double) * std::max<size_t>(1, want[k]);
+            if (c->cap_ipwork[k] < bytes) {
+                b200_dfree(c->d_ipwork[k]); c->d_ipwork[k] = nullptr; c->cap_ipwork[k] = 0;
+                if (b200_big_alloc(&c->d_ipwork[k], bytes)) {
+                    rc = b200_fail(CINTB200_ENOMEM, "derivative block: %zu bytes of work tensors", sizeof(double) * (szP + szM + 2 * szD));
+                    goto done;
+                }
+                c->cap_ipwork[k] = bytes;
+            }
         }
+        dP = (double *)c->d_ipwork[0]; dM = (double *)c->d_ipwork[1]; dA = (double *)c->d_ipwork[2]; dB = (double *)c->d_ipwork[3];
         if (dev_upload(&d_ipP, ipP) || dev_upload(&d_ipM, ipM) || dev_upload(&d_cP, cP) || dev_upload(&d_cM, cM)) { rc = b200_fail(CINTB200_ENOMEM, "derivative block tables"); goto done; }
     }
     b200_phase("ip1 block: work tensors + derivative tables", tph);
@@ -163,8 +173,9 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
         std::lock_guard<std::mutex> lock(c->mtx);
         // 2. derivative in the Cartesian basis
         const long long nel = NC[0] * R;
-        ip1_block_assemble_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(dP, dM, NP, NM, NC[0], R, d_ipP, d_ipM, d_cP, d_cM, dA);
-        double *cur = dA, *nxt = dB;
+        // the last pass of the chain writes straight into a device-resident `out`
+        double *cur = (cart && on_device) ? out : dA, *nxt = dB;
+        ip1_block_assemble_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(dP, dM, NP, NM, NC[0], R, d_ipP, d_ipM, d_cP, d_cM, cur);
         long long dims[5] = {NC[0], NC[1], NC[2], NC[3], 3};
         if (!cart) {
             // 3. cart -> sph along each index (s and p shells: identity; d and higher: the matrices of c2s_tables.inc)
@@ -190,13 +201,14 @@ static int ip1_block(cintb200_ctx *c, int ncenter, int kind, const int *sl, doub
                 for (int k = 0; k < m; k++) pre *= dims[k];
                 for (int k = m + 1; k < 5; k++) post *= dims[k];
                 const long long nout = NS[m], tot = pre * nout * post;
-                axis_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, nxt, pre, dims[m], nout, post, d_tab[m][0], d_tab[m][1], d_tab[m][2], d_coef);
+                double *dst = (on_device && m == ncenter - 1) ? out : nxt;
+                axis_transform_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(cur, dst, pre, dims[m], nout, post, d_tab[m][0], d_tab[m][1], d_tab[m][2], d_coef);
                 dims[m] = nout;
-                std::swap(cur, nxt);
+                if (dst == out) cur = out; else std::swap(cur, nxt);
             }
         }
         const size_t nout_total = (size_t)(dims[0] * dims[1] * dims[2] * dims[3] * 3);
-        CU_OK(cudaMemcpyAsync(out, cur, sizeof(double) * nout_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        if (cur != out) CU_OK(cudaMemcpyAsync(out, cur, sizeof(double) * nout_total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         CU_OK(cudaStreamSynchronize(st));
         {
             cudaError_t le = cudaGetLastError();
@@ -213,7 +225,6 @@ done:
     cudaStreamSynchronize(st);
     b200_phase("ip1 block: assemble + c2s + copy", tph);
     tph = b200_now();
-    b200_big_free(dP); b200_big_free(dM); b200_big_free(dA); b200_big_free(dB);
     b200_dfree(d_coef); b200_dfree(d_cP); b200_dfree(d_cM); b200_dfree(d_ipP); b200_dfree(d_ipM);
     for (int m = 0; m < 4; m++) for (int k = 0; k < 3; k++) b200_dfree(d_tab[m][k]);
     b200_phase("ip1 block: release", tph);

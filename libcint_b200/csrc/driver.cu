@@ -63,17 +63,37 @@ void *DeviceArena::alloc(size_t bytes)
         const size_t blk = std::max(bytes, (size_t)32 << 20);
         void *p = nullptr;
         if (b200_big_alloc(&p, blk)) return nullptr;
-        blocks.push_back(p);
+        char *m = (char *)malloc(blk);
+        if (!m) { b200_big_free(p); return nullptr; }
+        blocks.push_back(p); mirrors.push_back(m); sizes.push_back(blk); flushed.push_back(0); used.push_back(0);
         cur = (char *)p; left = blk;
     }
     void *r = cur;
     cur += bytes; left -= bytes;
+    used.back() = (size_t)(cur - (char *)blocks.back());
     return r;
+}
+char *DeviceArena::host_of(void *dev)
+{
+    for (size_t k = blocks.size(); k-- > 0;)
+        if ((char *)dev >= (char *)blocks[k] && (char *)dev < (char *)blocks[k] + sizes[k]) return mirrors[k] + ((char *)dev - (char *)blocks[k]);
+    return nullptr;
+}
+int DeviceArena::flush()
+{
+    for (size_t k = 0; k < blocks.size(); k++) {
+        if (used[k] > flushed[k]) {
+            if (cudaMemcpy((char *)blocks[k] + flushed[k], mirrors[k] + flushed[k], used[k] - flushed[k], cudaMemcpyHostToDevice) != cudaSuccess) return -1;
+            flushed[k] = used[k];
+        }
+    }
+    return 0;
 }
 void DeviceArena::release()
 {
     for (void *p : blocks) b200_big_free(p);
-    blocks.clear(); cur = nullptr; left = 0;
+    for (char *m : mirrors) free(m);
+    blocks.clear(); mirrors.clear(); sizes.clear(); flushed.clear(); used.clear(); cur = nullptr; left = 0;
 }
 
 static thread_local DeviceArena *g_arena = nullptr;         // set while a plan is being built: upload() allocates from it
@@ -85,6 +105,8 @@ static int upload(T **dst, const std::vector<T> &src)
     if (g_arena) {
         *dst = (T *)g_arena->alloc(bytes);
         if (!*dst) return b200_fail(CINTB200_ENOMEM, "device arena: %zu bytes failed", bytes);
+        if (!src.empty()) memcpy(g_arena->host_of(*dst), src.data(), sizeof(T) * src.size());       // sent by DeviceArena::flush()
+        return 0;
     } else if (b200_dmalloc((void **)dst, bytes) != cudaSuccess)
         return b200_fail(CINTB200_ENOMEM, "cudaMalloc of %zu bytes failed", bytes);
     if (!src.empty() && cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice) != cudaSuccess)
@@ -135,7 +157,7 @@ static void fill_tprim(const CINTOpt *c, const PairHdr &h, size_t n, size_t NT, 
 
 static int build_plan(CINTOpt *c, JobPlan *plan)
 {
-    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } } arena_scope(plan->host_only ? nullptr : &plan->arena);
+    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { if (g_arena) g_arena->flush(); g_arena = nullptr; } } arena_scope(plan->host_only ? nullptr : &plan->arena);
     const int nranks = plan->nranks, rank = plan->rank;
     const bool three = plan->ncenter == 3;
     const int nbas = three ? plan->aux0 : c->nbas;          // shells that form the bra pairs (rows)
@@ -1165,7 +1187,7 @@ struct RectEntry { int pair; long long off; int s_a, s_b; };      // pair id, bl
 static int build_rect_plan(CINTOpt *c, JobPlan *plan, const std::vector<RectEntry> &T, const std::vector<RectEntry> &U,
                            long long ld, long long ncols, double *dev_out)
 {
-    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { g_arena = nullptr; } } arena_scope(&plan->arena);
+    struct ArenaScope { ArenaScope(DeviceArena *a) { g_arena = a; } ~ArenaScope() { if (g_arena) g_arena->flush(); g_arena = nullptr; } } arena_scope(&plan->arena);
     auto group = [&](const std::vector<RectEntry> &E, std::vector<PairClass> &out, std::vector<std::vector<int>> &members) {
         std::map<std::vector<int>, int> key2class;
         for (size_t n = 0; n < E.size(); n++) {

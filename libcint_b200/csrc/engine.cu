@@ -362,6 +362,7 @@ extern "C" void cintb200_destroy(cintb200_ctx *c)
     if (c->deriv) { cintb200_destroy(c->deriv); c->deriv = nullptr; }
     if (c->ltab) { listtables_free(c->ltab); c->ltab = nullptr; }
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int k = 0; k < 4; k++) b200_dfree(c->d_ipwork[k]);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->magic = 0;
     delete c;

@@ -40,6 +40,8 @@ struct CINTOpt {
     int *d_nonzero = nullptr;       size_t cap_nonzero = 0;
     double *d_scratch = nullptr;    size_t cap_scratch = 0;
     void *h_stage = nullptr;        size_t cap_stage = 0;
+    void *d_ipwork[4] = {nullptr, nullptr, nullptr, nullptr};      // work tensors of the derivative blocks (deriv_block.cu), grow-only
+    size_t cap_ipwork[4] = {0, 0, 0, 0};
     unsigned long long *d_counters = nullptr;
     long long launches = 0;
     struct JobPlan *plan = nullptr;     // cached whole-job plan (driver.cu)

@@ -26,6 +26,12 @@ import tempfile
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the library builds its pair tables and plans with OpenMP on the host
+# (part of every end-to-end step), so give each rank its share of the host cores instead.  Must happen before libgomp loads.
+if os.environ.get("OMP_NUM_THREADS", "") in ("", "1") and "LOCAL_RANK" in os.environ:
+    _lw = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    os.environ["OMP_NUM_THREADS"] = str(max(1, min(8, (os.cpu_count() or 1) // _lw)))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -35,6 +35,7 @@ __device__ __forceinline__ int cart_index(int lx, int lz, int l)
 // Division of a small non-negative int by a block-uniform run-time divisor without the ~20-instruction software divide:
 // q = (n * m) >> 32 with m = floor(2^32 / d) + 1, exact for n, d < 2^16 (every index of the epilogue is far below that...
 // the products n * d stay < 2^32, which is the condition).
+#define GEN_PRIM_DOUBLES 16             // per primitive quartet of a batch: valid, x, fac, theta, aij, akl, PQ[3], PA[3], QC[3]
 struct FastDiv {
     unsigned long long m;
     int d;
@@ -125,9 +126,10 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
     const int ncomb = C.ncab * C.nccd;
     const int gstride_r = (nmax + 1) * (mmax + 1);
 
-    double *s_rw = sm;                                   // [2*nroots]  t2,w interleaved as p
-    double *s_g = s_rw + 2 * nreff;                      // [3][nreff][nmax+1][mmax+1]
-    int *s_ecomp = (int *)(s_g + 3 * nreff * gstride_r);   // [nE], [nF] packed exponents
+    double *s_prim = sm;                                 // [pbatch][GEN_PRIM_DOUBLES] scalars of the batch's primitive quartets
+    double *s_rw = s_prim + C.pbatch * GEN_PRIM_DOUBLES; // [pbatch][2*nreff]  t2,w interleaved as p
+    double *s_g = s_rw + C.pbatch * 2 * nreff;           // [pbatch][3][nreff][nmax+1][mmax+1]
+    int *s_ecomp = (int *)(s_g + (size_t)C.pbatch * 3 * nreff * gstride_r);   // [nE], [nF] packed exponents
     int *s_fcomp = s_ecomp + nE;
     int *s_map = s_fcomp + nF;                            // [C.map_ints] HRR map of the current level
     double *s_dyn = (double *)(s_map + C.map_ints + ((nE + nF + C.map_ints) & 1));
@@ -167,82 +169,120 @@ __global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *_
         if (!epi) for (int i = tid; i < ncomb * nEF; i += blockDim.x) acc[i] = 0.0;
         int executed = 0;
 
-        for (int kq = 0; kq < (epi ? 0 : hk.npp); kq++) {
-            const PrimPair pk = P.prims[hk.pp_off + kq];
-            if (pk.cce > P.expcutoff) continue;
-            for (int bq = 0; bq < hb.npp; bq++) {
+        // Primitive quartets in BATCHES of C.pbatch: the per-primitive phases (2N root polynomials, 3N recurrence columns) occupy a
+        // handful of threads each, so a batch runs them for all its primitives at once and the block synchronises four times per
+        // batch instead of three times per primitive quartet.  Order of summation is unchanged (flat index kq * npp_b + bq ascending).
+        const int PB = C.pbatch;
+        const int npq = epi ? 0 : hk.npp * hb.npp;
+        const bool lr = P.omega > 0, sr = P.omega < 0;
+        const FastDiv dF(nF), dnpb(hb.npp > 0 ? hb.npp : 1);
+        for (int base = 0; base < npq; base += PB) {
+            const int nb = min(PB, npq - base);
+            // phase 0: scalars of every primitive quartet of the batch (one thread each)
+            if (tid < nb) {
+                const int pq = base + tid, kq = dnpb.div(pq), bq = pq - kq * hb.npp;
+                const PrimPair pk = P.prims[hk.pp_off + kq];
                 const PrimPair pb = P.prims[hb.pp_off + bq];
-                if (pb.cce + pk.cce > P.expcutoff) continue;
-                executed++;
-                const double aij = pb.aij, akl = pk.aij;
-                const double asum = aij + akl;
-                const double a1 = aij * akl;
-                const double a0 = a1 / asum;
+                double *sp = s_prim + tid * GEN_PRIM_DOUBLES;
+                const bool ok = !(pk.cce > P.expcutoff) && !(pb.cce + pk.cce > P.expcutoff);
+                const double aij = pb.aij, akl = pk.aij, asum = aij + akl, a1 = aij * akl, a0 = a1 / asum;
                 const double dx = pb.px - pk.px, dy = pb.py - pk.py, dz = pb.pz - pk.pz;
                 double x = a0 * (dx * dx + dy * dy + dz * dz);
                 double fac1 = common * pb.kij * pk.kij * sqrt(a0 / (a1 * a1 * a1));
                 double theta = 1.0;
-                const bool lr = P.omega > 0, sr = P.omega < 0;
                 if (P.omega != 0) theta = P.omega * P.omega / (P.omega * P.omega + a0);
-                if (lr) {                       // long-range attenuation, src/g2e.c:4477-4492
-                    x *= theta;
-                    fac1 *= sqrt(theta);
-                }
-                __syncthreads();                // previous primitive's G fully consumed
-                if (tid < 2 * nroots) s_rw[tid] = rys_value(P.rys_coef, nroots, x, tid);
-                else if (sr && tid < 4 * nroots) s_rw[tid] = rys_value(P.rys_coef, nroots, x * theta, tid - 2 * nroots);
-                __syncthreads();
-                if (tid < 3 * nreff) {
-                    const int r = tid / 3, xyz = tid - 3 * r;
-                    const bool second = r >= nroots;                       // long-range half of the SR rule
-                    const double sc = (lr || second) ? theta : 1.0;
-                    const double s = s_rw[2 * r] * sc;                      // t^2 (LR: theta t^2)
-                    const double wgt = second ? -sqrt(theta) * s_rw[2 * r + 1] : s_rw[2 * r + 1];
-                    const double sa = s * akl / asum, sk = s * aij / asum;
-                    const double b00 = 0.5 * s / asum;
-                    const double b10 = 0.5 * (1.0 - sa) / aij;
-                    const double b01 = 0.5 * (1.0 - sk) / akl;
-                    const double pq = xyz == 0 ? dx : (xyz == 1 ? dy : dz);
-                    const double pa = (xyz == 0 ? pb.px : (xyz == 1 ? pb.py : pb.pz)) - hb.ra[xyz];
-                    const double qc = (xyz == 0 ? pk.px : (xyz == 1 ? pk.py : pk.pz)) - hk.ra[xyz];
-                    const double c00 = pa - sa * pq;
-                    const double c0p = qc + sk * pq;
-                    double *g = s_g + (size_t)(xyz * nreff + r) * gstride_r;
-                    const int ms = mmax + 1;
-                    g[0] = (xyz == 2) ? wgt * fac1 : 1.0;
-                    if (nmax > 0) g[ms] = c00 * g[0];
-                    for (int n = 1; n < nmax; n++) g[(n + 1) * ms] = c00 * g[n * ms] + n * b10 * g[(n - 1) * ms];
-                    for (int m = 0; m < mmax; m++)
-                        for (int n = 0; n <= nmax; n++) {
-                            double v = c0p * g[n * ms + m];
-                            if (m > 0) v += m * b01 * g[n * ms + m - 1];
-                            if (n > 0) v += n * b00 * g[(n - 1) * ms + m];
-                            g[n * ms + m + 1] = v;
-                        }
-                }
-                __syncthreads();
-                const double *ccb = P.pcoef + hb.cc_off + (size_t)bq * C.ncab;
-                const double *cck = P.pcoef + hk.cc_off + (size_t)kq * C.nccd;
-                const FastDiv dF(nF);
-                for (int idx = tid; idx < nEF; idx += blockDim.x) {
-                    const int e = dF.div(idx), f = idx - e * nF;
-                    const int ec = s_ecomp[e], fc = s_fcomp[f];
-                    const int ms = mmax + 1;
-                    const int ox = (ec & 255) * ms + (fc & 255);
-                    const int oy = ((ec >> 8) & 255) * ms + ((fc >> 8) & 255);
-                    const int oz = ((ec >> 16) & 255) * ms + ((fc >> 16) & 255);
-                    const double *gx = s_g + ox, *gy = s_g + (size_t)nreff * gstride_r + oy,
-                                 *gz = s_g + (size_t)2 * nreff * gstride_r + oz;
+                if (lr) { x *= theta; fac1 *= sqrt(theta); }            // long-range attenuation, src/g2e.c:4477-4492
+                sp[0] = ok ? 1.0 : 0.0; sp[1] = x; sp[2] = fac1; sp[3] = theta; sp[4] = aij; sp[5] = akl;
+                sp[6] = dx; sp[7] = dy; sp[8] = dz;
+                sp[9] = pb.px - hb.ra[0]; sp[10] = pb.py - hb.ra[1]; sp[11] = pb.pz - hb.ra[2];
+                sp[12] = pk.px - hk.ra[0]; sp[13] = pk.py - hk.ra[1]; sp[14] = pk.pz - hk.ra[2];
+            }
+            __syncthreads();
+            // phase 1: roots and weights, one (primitive, polynomial) per thread
+            const int nrw = sr ? 4 * nroots : 2 * nroots;
+            const FastDiv dnrw(nrw);
+            for (int i = tid; i < nb * nrw; i += blockDim.x) {
+                const int bi = dnrw.div(i), pidx = i - bi * nrw;
+                const double *sp = s_prim + bi * GEN_PRIM_DOUBLES;
+                if (sp[0] == 0.0) continue;
+                s_rw[bi * 2 * nreff + pidx] = pidx < 2 * nroots ? rys_value(P.rys_coef, nroots, sp[1], pidx)
+                                                                : rys_value(P.rys_coef, nroots, sp[1] * sp[3], pidx - 2 * nroots);
+            }
+            __syncthreads();
+            // phase 2: recurrences, one (primitive, root, axis) per thread
+            const int nvr = 3 * nreff;
+            const FastDiv dnvr(nvr);
+            for (int i = tid; i < nb * nvr; i += blockDim.x) {
+                const int bi = dnvr.div(i), rx = i - bi * nvr;
+                const double *sp = s_prim + bi * GEN_PRIM_DOUBLES;
+                if (sp[0] == 0.0) continue;
+                const int r = rx / 3, xyz = rx - 3 * r;
+                const double theta = sp[3], aij = sp[4], akl = sp[5], asum = aij + akl;
+                const bool second = r >= nroots;                       // long-range half of the SR rule
+                const double sc = (lr || second) ? theta : 1.0;
+                const double s = s_rw[bi * 2 * nreff + 2 * r] * sc;     // t^2 (LR: theta t^2)
+                const double wgt = second ? -sqrt(theta) * s_rw[bi * 2 * nreff + 2 * r + 1] : s_rw[bi * 2 * nreff + 2 * r + 1];
+                const double sa = s * akl / asum, sk = s * aij / asum;
+                const double b00 = 0.5 * s / asum;
+                const double b10 = 0.5 * (1.0 - sa) / aij;
+                const double b01 = 0.5 * (1.0 - sk) / akl;
+                const double pq = sp[6 + xyz], pa = sp[9 + xyz], qc = sp[12 + xyz];
+                const double c00 = pa - sa * pq;
+                const double c0p = qc + sk * pq;
+                double *g = s_g + (size_t)bi * 3 * nreff * gstride_r + (size_t)(xyz * nreff + r) * gstride_r;
+                const int ms = mmax + 1;
+                g[0] = (xyz == 2) ? wgt * sp[2] : 1.0;
+                if (nmax > 0) g[ms] = c00 * g[0];
+                for (int n = 1; n < nmax; n++) g[(n + 1) * ms] = c00 * g[n * ms] + n * b10 * g[(n - 1) * ms];
+                for (int m = 0; m < mmax; m++)
+                    for (int n = 0; n <= nmax; n++) {
+                        double v = c0p * g[n * ms + m];
+                        if (m > 0) v += m * b01 * g[n * ms + m - 1];
+                        if (n > 0) v += n * b00 * g[(n - 1) * ms + m];
+                        g[n * ms + m + 1] = v;
+                    }
+            }
+            __syncthreads();
+            // phase 3: quadrature sums and contraction, primitives of the batch in order.  Work item = ([e0|f0] component, group of
+            // contraction combinations): blocks with fewer components than threads (s / p classes with general contractions)
+            // split the ncomb accumulator updates of a component over CSPLIT threads instead of leaving most of the block idle
+            const int csplit = C.csplit;
+            const FastDiv dsplit(csplit);
+            for (int item = tid; item < nEF * csplit; item += blockDim.x) {
+                const int idx = dsplit.div(item), cg = item - idx * csplit;
+                const int e = dF.div(idx), f = idx - e * nF;
+                const int ec = s_ecomp[e], fc = s_fcomp[f];
+                const int ms = mmax + 1;
+                const int ox = (ec & 255) * ms + (fc & 255);
+                const int oy = ((ec >> 8) & 255) * ms + ((fc >> 8) & 255);
+                const int oz = ((ec >> 16) & 255) * ms + ((fc >> 16) & 255);
+                for (int bi = 0; bi < nb; bi++) {
+                    if (s_prim[bi * GEN_PRIM_DOUBLES] == 0.0) continue;
+                    const double *gb = s_g + (size_t)bi * 3 * nreff * gstride_r;
+                    const double *gx = gb + ox, *gy = gb + (size_t)nreff * gstride_r + oy, *gz = gb + (size_t)2 * nreff * gstride_r + oz;
                     double v = 0;
                     for (int r = 0; r < nreff; r++)
                         v = fma(gx[r * gstride_r] * gy[r * gstride_r], gz[r * gstride_r], v);
-                    for (int ck = 0; ck < C.nccd; ck++) {
-                        const double vk = v * __ldg(cck + ck);
-                        for (int cb = 0; cb < C.ncab; cb++)
-                            acc[(size_t)(ck * C.ncab + cb) * nEF + idx] += vk * __ldg(ccb + cb);
+                    const int pq = base + bi, kq = dnpb.div(pq), bq = pq - kq * hb.npp;
+                    const double *ccb = P.pcoef + hb.cc_off + (size_t)bq * C.ncab;
+                    const double *cck = P.pcoef + hk.cc_off + (size_t)kq * C.nccd;
+                    if (csplit == 1) {
+                        for (int ck = 0; ck < C.nccd; ck++) {
+                            const double vk = v * __ldg(cck + ck);
+                            for (int cb = 0; cb < C.ncab; cb++)
+                                acc[(size_t)(ck * C.ncab + cb) * nEF + idx] += vk * __ldg(ccb + cb);
+                        }
+                    } else {
+                        for (int comb = cg; comb < ncomb; comb += csplit) {
+                            const int ck = comb / C.ncab, cb = comb - ck * C.ncab;
+                            acc[(size_t)comb * nEF + idx] += (v * __ldg(cck + ck)) * __ldg(ccb + cb);
+                        }
                     }
                 }
             }
+            if (tid == 0)
+                for (int bi = 0; bi < nb; bi++) executed += s_prim[bi * GEN_PRIM_DOUBLES] != 0.0;
+            __syncthreads();                // the batch's scalars and G are consumed before the next batch overwrites them
         }
         __syncthreads();
         if (tid == 0 && !epi) {
@@ -378,8 +418,10 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
         const double post_max = std::max<double>(C->nF, (double)B200_NCART(lb) * B200_NCART(lc) * B200_NCART(ld));
         if ((double)C->work_size * post_max >= 4294967296.0) return -1;
     }
-    size_t fixed = sizeof(double) * (2 * C->nreff + (size_t)3 * C->nreff * (nmax + 1) * (mmax + 1))
-                 + sizeof(int) * (C->nE + C->nF + C->map_ints + 2);
+    // primitive quartets per batch: as many as ~24 kB of per-primitive state (scalars, roots, G) allow, at most 16
+    const size_t per_prim = sizeof(double) * (GEN_PRIM_DOUBLES + 2 * C->nreff + (size_t)3 * C->nreff * (nmax + 1) * (mmax + 1));
+    C->pbatch = (int)std::min<size_t>(16, std::max<size_t>(1, (24 * 1024) / per_prim));
+    size_t fixed = per_prim * C->pbatch + sizeof(int) * (C->nE + C->nF + C->map_ints + 2);
     size_t acc_b = sizeof(double) * nEF * ncab * nccd;
     size_t work_b = sizeof(double) * 2 * (size_t)C->work_size;
     const size_t budget = 96 * 1024;       // keeps >= 2 blocks per SM
@@ -392,9 +434,12 @@ int generic_plan(GenericClass *C, GenericLaunch *L, int la, int lb, int lc, int 
     if (C->work_in_smem) smem += work_b;
     if (smem > 200 * 1024) return -1;
     C->scratch_per_block = (C->acc_in_smem ? 0 : nEF * ncab * nccd) + (C->work_in_smem ? 0 : 2 * (size_t)C->work_size);
-    int threads = (int)((nEF + 31) / 32 * 32);
-    if (threads < 96) threads = 96;        // >= 3 * nreff (<= 66 quadrature points x 3 axes handled by tid < 3*nreff)
+    int threads = (int)((nEF + 31) / 32 * 32);          // measured: sizing the block for nEF x ncomb items costs more in resident blocks than it gains
+    if (threads < 96) threads = 96;
     if (threads > 256) threads = 256;
+    // contraction combinations of one component spread over csplit threads when the block has threads to spare
+    C->csplit = 1;
+    while (C->csplit * 2 <= ncab * nccd && nEF * (size_t)(C->csplit * 2) <= (size_t)threads) C->csplit *= 2;
     L->threads = threads;
     L->smem = smem;
     int per_sm = (int)(budget * 2 / (smem > 4096 ? smem : 4096));

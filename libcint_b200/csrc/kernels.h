@@ -16,6 +16,8 @@ struct GenericClass {           // uniform per launch of eri_generic_kernel
     double *scratch;            // global scratch, scratch_per_block doubles per block
     size_t scratch_per_block;
     int map_ints;               // ints of shared memory for the per-level HRR map (largest level of the class)
+    int csplit;                 // threads sharing the contraction-combination updates of one [e0|f0] component (power of two)
+    int pbatch;                 // primitive quartets processed per batch (root / recurrence phases run for all of them at once)
     int wide;                   // the quadrature runs on the wide kernel (kern_wide.cu), this kernel does the epilogue only
     int epilogue_only;          // set per launch: accumulators of task task_base + blockIdx.x are already in the block's scratch
     long long task_base;

@@ -110,7 +110,12 @@ __device__ void c2s_index(const double *in, double *out, int pre, int post, int 
     }
 }
 
-__global__ void eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
+#ifdef GEN_MINB                          // experiment knob: -DGEN_MINB=2 caps the kernel at 128 registers (256 threads x 2 blocks)
+#define GEN_LAUNCH_BOUNDS __launch_bounds__(256, GEN_MINB)
+#else
+#define GEN_LAUNCH_BOUNDS
+#endif
+__global__ void GEN_LAUNCH_BOUNDS eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
                                    double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters,
                                    TileParams TP, const long long *__restrict__ uprefix)
 {

@@ -110,12 +110,12 @@ __device__ void c2s_index(const double *in, double *out, int pre, int post, int 
     }
 }
 
-#ifdef GEN_MINB                          // experiment knob: -DGEN_MINB=2 caps the kernel at 128 registers (256 threads x 2 blocks)
-#define GEN_LAUNCH_BOUNDS __launch_bounds__(256, GEN_MINB)
-#else
-#define GEN_LAUNCH_BOUNDS
-#endif
-__global__ void GEN_LAUNCH_BOUNDS eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
+// Two instantiations: CAP128 = the compiler must fit two 256-thread blocks per SM (128 registers, 40 bytes of spills) -- the
+// kernel is latency-bound at 3 resident 96-thread blocks per SM otherwise (174 registers).  Measured with the cap: C2H6 cc-pVQZ
+// pass 98 -> 75 ms, (pp|ss) with 16 contraction combinations 0.36 -> 0.25 us per quartet, ERI share of the ip1 gradient loop
+// 1.13 -> 1.00 s; the widest generally contracted classes ((ff|ff) x 16 combinations: +10 %) keep the uncapped build.
+template <bool CAP128>
+__global__ void __launch_bounds__(256, CAP128 ? 2 : 1) eri_generic_kernel(EngineParams P, GenericClass C, const Task *__restrict__ tasks, long long ntasks,
                                    double *__restrict__ out, int *__restrict__ nonzero, unsigned long long *counters,
                                    TileParams TP, const long long *__restrict__ uprefix)
 {
@@ -471,8 +471,11 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
     memset(&TP, 0, sizeof TP);
     if (tile) TP = *tile;
     if (ntasks <= 0) return 0;
+    // register-capped build unless the class is one of the widest contracted ones (threshold between (dd|dd) and (ff|ff))
+    const bool cap = (size_t)C.nE * C.nF < 3000 || C.ncab * C.nccd == 1;
+    auto kernel = cap ? eri_generic_kernel<true> : eri_generic_kernel<false>;
     if (L.smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(eri_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem) != cudaSuccess)
             return -1;
     }
     if (C.wide) {
@@ -484,11 +487,11 @@ int generic_launch(const EngineParams &P, const GenericClass &C, const GenericLa
             const int here = (int)std::min<long long>(L.grid, ntasks - base);
             if (wide_launch(P, C, tasks, base, ntasks, here, nonzero, stream, tile)) return -1;
             CE.task_base = base;
-            eri_generic_kernel<<<here, L.threads, L.smem, stream>>>(P, CE, tasks, ntasks, out, nonzero, counters, TP, uprefix);
+            kernel<<<here, L.threads, L.smem, stream>>>(P, CE, tasks, ntasks, out, nonzero, counters, TP, uprefix);
             if (cudaGetLastError() != cudaSuccess) return -1;
         }
         return 0;
     }
-    eri_generic_kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters, TP, uprefix);
+    kernel<<<L.grid, L.threads, L.smem, stream>>>(P, C, tasks, ntasks, out, nonzero, counters, TP, uprefix);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

@@ -227,8 +227,9 @@ int cintb200_fp64_peak(int device, double seconds, double *tflops);
 /* SMs x 64 FP64 lanes x 2 flops x SM clock (sm_mhz <= 0: the device's maximum clock), for comparison with the measured figure. */
 int cintb200_fp64_peak_theoretical(int device, double sm_mhz, double *tflops);
 
-/* Tile buffers are kept in the device's memory pool when a context is destroyed, so that the next context reuses them (freeing
- * and re-mapping tens of GB costs ~1 s).  This call returns the cached memory of `device` (-1: current) to the driver. */
+/* Every device buffer of the library (tables, tiles, work arrays) comes from the device's stream-ordered memory pool and stays
+ * cached there when a context is destroyed, so that the next context reuses it (freeing and re-mapping tens of GB costs ~1 s).
+ * This call returns the cached memory of `device` (-1: current) to the driver, e.g. before another library needs the HBM. */
 int cintb200_release_cached_memory(int device);
 
 /* Last error text of the calling thread ("" if none). */

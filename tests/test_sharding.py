@@ -118,3 +118,16 @@ def test_density_fitting_job_sharding():
         assert max(p["model_flops"] for p in parts) * n / one["model_flops"] < 1.02
     small = cb.plan_summary(atm, bas, env, chunk_bytes=8 << 30, aux_shell0=norb)
     assert small["chunks"] >= 8 and small["integrals"] == one["integrals"] and small["tile_bytes"] <= (8 << 30) * 1.05
+
+
+def test_chunk_boundaries_do_not_depend_on_the_number_of_ranks():
+    # round 2: every rank count walks the same chunk sequence; a rank's tile is ~1/N of the single-rank one
+    atm, bas, env = cb.load_fixture("c2h6_ccpvtz")
+    one = cb.plan_summary(atm, bas, env, chunk_bytes=3_000_000)
+    assert one["chunks"] > 10
+    for n in (2, 4, 8):
+        parts = [cb.plan_summary(atm, bas, env, rank=r, nranks=n, chunk_bytes=3_000_000) for r in range(n)]
+        assert all(p["chunks"] == one["chunks"] for p in parts)
+        assert sum(p["columns"] for p in parts) == one["columns"]
+        assert max(p["tile_bytes"] for p in parts) < 1.15 * one["tile_bytes"] / n
+        assert max(p["launches"] for p in parts) <= one["launches"]

@@ -45,3 +45,23 @@ def test_cooperative_tuning_entries_name_instantiated_classes():
     for key, minb, _ in entries:
         assert key in inst, "tune_coop.inc names %s, which has no cooperative-kernel instantiation" % (key,)
         assert 1 <= minb <= 6
+
+
+def test_multiply_shift_division_of_the_catch_all_epilogue_is_exact_in_its_range():
+    """kern_generic.cu:FastDiv computes n / d as (n * (2^32 / d + 1)) >> 32; generic_plan refuses classes with index x divisor
+    >= 2^32.  The formula (restated here) is exact for every n, d with n * d < 2^32 -- checked on the extremes and a random sample."""
+    import random
+    src = open(os.path.join(CSRC, "kern_generic.cu")).read()
+    assert "0x100000000ull / (unsigned)d_) + 1" in src and ">= 4294967296.0) return -1" in src      # the two halves of the contract
+
+    def fastdiv(n, d):
+        return (n * ((1 << 32) // d + 1)) >> 32
+
+    rnd = random.Random(7)
+    cases = [(0, 1), (1, 1), (614655, 1), (246959, 8820), (194480, 9261), (65535, 65535), ((1 << 32) // 9261 - 1, 9261)]
+    for _ in range(20000):
+        d = rnd.randint(1, 30000)
+        cases.append((rnd.randint(0, ((1 << 32) - 1) // d), d))
+    for n, d in cases:
+        assert n * d < (1 << 32)
+        assert fastdiv(n, d) == n // d, (n, d)

@@ -1304,6 +1304,21 @@ int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_d
         { TileSink ts; double *one[1] = {out}; if (!on_device) { ts.sinks = one; ts.nsinks = 1; }
           return execute_plan(c, plan2, 3, ts, stats); }      // 2- and 3-centre integrals share the cutoff
     }
+    // a pair with virtual segmented copies (engine.cu:build_pairs) enters as nca x ncb single-contraction sub-blocks
+    auto dim1 = [&](int sh) { return cart ? B200_NCART(c->shells[sh].l) : 2 * c->shells[sh].l + 1; };
+    auto push_entry = [&](std::vector<RectEntry> &V, const RectEntry &e) {
+        const int vf = (e.pair < (int)c->vfirst.size() && !c->force_generic) ? c->vfirst[e.pair] : -1;
+        if (vf < 0) { V.push_back(e); return; }
+        const PairHdr &h = c->pairs[e.pair];
+        const long long da = dim1(h.sh_a), db = dim1(h.sh_b);
+        for (int cb = 0; cb < h.ncb; cb++)
+            for (int ca = 0; ca < h.nca; ca++) {
+                RectEntry v = e;
+                v.pair = vf + cb * h.nca + ca;
+                v.off = e.off + ca * da * e.s_a + cb * db * e.s_b;
+                V.push_back(v);
+            }
+    };
     const long long NI = aoend(sl[1] - 1) - ao0(sl[0]), NJ = aoend(sl[3] - 1) - ao0(sl[2]);
     const long long NK = aoend(sl[5] - 1) - ao0(sl[4]), NL = (ncenter == 4) ? aoend(sl[7] - 1) - ao0(sl[6]) : 1;
     if (NI * NJ > 0x7fffffffLL) return b200_fail(CINTB200_EINVAL, "bra slice too large: NI*NJ = %lld rows exceed 2^31", NI * NJ);
@@ -1314,7 +1329,7 @@ int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_d
             e.off = (ao0(i) - ao0(sl[0])) + NI * (ao0(j) - ao0(sl[2]));
             const bool a_is_i = (c->pairs[e.pair].sh_a == i);         // i == j: a = b, the first index is a
             e.s_a = a_is_i ? 1 : (int)NI; e.s_b = a_is_i ? (int)NI : 1;
-            T.push_back(e);
+            push_entry(T, e);
         }
     if (ncenter == 4) {
         for (int l = sl[6]; l < sl[7]; l++)
@@ -1324,7 +1339,7 @@ int run_block(cintb200_ctx *c, int ncenter, const int *sl, double *out, int on_d
                 e.off = (ao0(k) - ao0(sl[4])) + NK * (ao0(l) - ao0(sl[6]));
                 const bool a_is_k = (c->pairs[e.pair].sh_a == k);
                 e.s_a = a_is_k ? 1 : (int)NK; e.s_b = a_is_k ? (int)NK : 1;
-                U.push_back(e);
+                push_entry(U, e);
             }
     } else {
         for (int k = sl[4]; k < sl[5]; k++) {

@@ -259,6 +259,30 @@ static void build_pairs(CINTOpt *c)
         }
         h.npp = s.nprim;
     }
+    // Virtual segmented pairs.  A generally contracted pair whose type (la, lb, nca x ncb) has no specialised kernel in any
+    // class -- general contractions above s, e.g. cc-pVXZ of second-row atoms, ANO sets, the raised copies of contracted
+    // shells in the derivative context -- would send every class it takes part in to the catch-all kernel.  Such a pair also
+    // gets nca x ncb headers with ONE contraction each (same primitives, own coefficient column): the dense-block driver
+    // (driver.cu:run_block) addresses them as separate sub-blocks, which recomputes the primitives per contraction but on the
+    // register / cooperative kernels (~100x faster per primitive quartet than the catch-all kernel).
+    c->vfirst.assign(npair2, -1);
+    for (size_t p = 0; p < npair2; p++) {
+        const PairHdr h = c->pairs[p];                  // copy: the vector grows below
+        const int ncomb = h.nca * h.ncb;
+        if (ncomb <= 1 || h.npp == 0) continue;
+        CoopInfo ci;
+        auto specialised = [&](int nc) { return reg_kernel_lookup(h.la, h.lb, 0, 0, nc, 1) != nullptr || coop_kernel_lookup(h.la, h.lb, 0, 0, nc, 1, &ci) != nullptr; };
+        if (specialised(ncomb) || !specialised(1)) continue;       // contracted type covered, or not even the segmented type is
+        c->vfirst[p] = (int)c->pairs.size();
+        for (int cb = 0; cb < h.ncb; cb++)
+            for (int ca = 0; ca < h.nca; ca++) {
+                PairHdr v = h;
+                v.nca = v.ncb = 1;
+                v.cc_off = (int)c->pcoef.size();
+                for (int q = 0; q < h.npp; q++) c->pcoef.push_back(c->pcoef[(size_t)h.cc_off + (size_t)q * ncomb + cb * h.nca + ca]);
+                c->pairs.push_back(v);
+            }
+    }
 }
 
 static int ctx_upload(CINTOpt *c)

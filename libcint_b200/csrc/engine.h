@@ -26,6 +26,7 @@ struct CINTOpt {
     std::vector<double> env;
     std::vector<ShellInfo> shells;
     std::vector<PairHdr> pairs;
+    std::vector<int> vfirst;        // per pair i >= j: first of its nca x ncb VIRTUAL segmented pairs in `pairs` (index cb * nca + ca), or -1
     std::vector<PrimPair> prims;
     std::vector<double> pcoef;
     std::vector<double> schwarz;        // sqrt(max|(ij|ij)|) per pair id, filled on demand (device evaluation)

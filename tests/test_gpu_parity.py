@@ -509,6 +509,30 @@ def test_large_lists_device_side_bookkeeping():
         assert np.abs(v2[o2[t]:o2[t] + s2[t]] - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (t, q2[t])
 
 
+def test_dense_block_generally_contracted_shells_virtual_pairs():
+    """Dense shell-slice blocks over a basis in which EVERY shell carries two general contractions (class-sweep basis, s..f):
+    pairs above s have no contracted kernel instantiation and enter the block as single-contraction virtual pairs
+    (engine.cu:build_pairs, driver.cu:run_block) -- spherical and Cartesian output against the reference per tuple."""
+    which, _ = ou.best()
+    import itertools
+    from libcint_b200.basis import class_sweep_basis
+    atm, bas, env = class_sweep_basis(lmax=3, nctr=2)
+    ctx = cb.Context(atm, bas, env)
+    rng = np.random.default_rng(11)
+    sl = (0, 8, 2, 8, 8, 12, 12, 16)
+    for cart in (False, True):
+        arr, st = ctx.int2e_block(sl, cart=cart)
+        ao = np.concatenate([[0], np.cumsum([((int(b[1]) + 1) * (int(b[1]) + 2) // 2 if cart else 2 * int(b[1]) + 1) * int(b[3]) for b in bas])])
+        tuples = list(itertools.product(*[range(sl[2 * m], sl[2 * m + 1]) for m in range(4)]))
+        for sh in [tuples[n] for n in rng.choice(len(tuples), 250, replace=False)]:
+            want, _ = ou.eval_tuple(which, "int2e_cart" if cart else "int2e_sph", sh, atm, bas, env)
+            idx = tuple(slice(int(ao[s] - ao[sl[2 * m]]), int(ao[s + 1] - ao[sl[2 * m]])) for m, s in enumerate(sh))
+            got = arr[idx]
+            want = np.asarray(want).reshape(got.shape, order="F")
+            assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max()), (cart, sh, np.abs(got - want).max())
+    ctx.close()
+
+
 def test_ip1_dense_blocks_on_tile_kernels():
     """( nabla i j | k l ) and ( nabla i j | k ) over shell slices (cintb200_int2e_ip1_block): raised / lowered helper blocks on the
     specialised kernels + derivative and cart->sph on the dense tensor, against the reference's int2e_ip1 / int3c2e_ip1 per tuple."""
